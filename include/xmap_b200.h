@@ -1,0 +1,220 @@
+/*
+ * xmap_b200 -- C ABI of the B200 (sm_100a) implementation of X-MAP's AlterEgo
+ * construction hot path: item-item co-rating similarity, per-item top-k
+ * neighbour selection, X-SIM bridge extension, AlterEgo generation.
+ *
+ * The reference (LPD-EPFL-ML/X-MAP) is pure Python on PySpark RDDs and has no
+ * FFI; its boundary for this path is five pipeline functions
+ * (code/xmap/utils/assist.py:9-150).  The Python facade in x-map_b200/ keeps
+ * those names and signatures and calls the entry points below through ctypes,
+ * one call per stage.  Each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _h;
+ *   - buffers are caller-owned (the facade allocates them with torch);
+ *   - `stream` is a cudaStream_t passed as void*; calls are stream-ordered and
+ *     return without synchronising unless stated;
+ *   - return value 0 = ok, otherwise an error whose text xmap_last_error()
+ *     returns (thread-local);
+ *   - items and users are dense int32 indices; item index < 2^24.
+ */
+#ifndef XMAP_B200_H
+#define XMAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XMAP_B200_ABI_VERSION 1
+#define XMAP_KMAX 64                 /* largest supported top-k (extend_among_topk) */
+#define XMAP_METHOD_ADJUST_COSINE 0  /* baselinerSim.py:144-174 */
+#define XMAP_METHOD_COSINE 1         /* baselinerSim.py:115-142 */
+
+int xmap_abi_version(void);
+const char *xmap_last_error(void);
+
+/* ---------------------------------------------------------------------------
+ * (1) Ratings layout + per-user / per-item statistics.
+ * Replaces: the (uid, [(iid, rating, time)]) record grouping the RDDs carry,
+ * BaselinerSim.get_universal_user_info (baselinerSim.py:17-38) and
+ * get_universal_item_info (baselinerSim.py:40-82), and the two
+ * collectAsMap+broadcast round trips at assist.py:68-73.
+ *
+ * In : nnz deduplicated (user, item, rating) triples in any order.
+ * Out: CSR by user (entries ascending by item) and CSC by item (entries
+ *      ascending by user).  Entry formats (8 bytes each):
+ *        csr_ent[k] = { item | cls(item)<<24 | ge_avg<<29 , float bits of rating }
+ *        csc_ent[k] = { user | ge_avg<<31                  , float bits of rating }
+ *      cls(item) = ceil(log2(count(item))); ge_avg = (rating >= item average),
+ *      the comparison retrieve_path_info makes (baselinerSim.py:106-111).
+ *      csr_src[k] = index of the input triple stored at CSR position k.
+ *      user_mu[u] = mean rating of u (baselinerSim.py:30).
+ *      item_stats[4*i..] = (average, norm2, adjusted norm2, count) exactly the
+ *      tuple of baselinerSim.py:56-63.
+ * ------------------------------------------------------------------------- */
+size_t xmap_layout_workspace_bytes(int64_t nnz, int32_t n_users, int32_t n_items);
+
+int xmap_build_layout(const int32_t *user, const int32_t *item, const float *rating,
+                      int64_t nnz, int32_t n_users, int32_t n_items,
+                      int32_t *csr_ptr, uint64_t *csr_ent, int32_t *csr_src,
+                      int32_t *csc_ptr, uint64_t *csc_ent,
+                      double *user_mu, double *item_stats,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* Per output row i of R^T R: w[i] = sum over raters u of i of degree(u), the
+ * number of co-rating products the row costs (W + nnz in total).
+ * Used to plan which kernel handles which row. */
+int xmap_row_work(const int32_t *csr_ptr, const int32_t *csc_ptr, const uint64_t *csc_ent,
+                  int32_t n_items, int64_t *row_work, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * (2) Similarity rows + fused epilogue + fused per-row top-k selection.
+ * Replaces: produce_pairwise_items + reduceByKey + calculate_*_sim +
+ * retrieve_path_info + filter + detect_domain (baselinerSim.py:84-216),
+ * get_item_sim (:218-233), the BB-item SQL (assist.py:82-87) and
+ * ExtendSim.find_knn_items (extender.py:16-44).
+ *
+ * For every requested row i the kernels accumulate, over all users who rated
+ * both i and j: n_ij, the mutuality count, and the inner product (fixed-point,
+ * order-independent), then compute sim / mutu and apply the reference's filter
+ * (sim != 0 and mutu != 0) and cross-domain label, and select neighbours.
+ *
+ * mode 0 (pass 1): writes row_flags bit0 = "i is a bridge (BB) item",
+ *     row_npairs = #co-rated j, row_nkept = #kept j, and
+ *       BB row : table slot 0 = BB_BB (top-k other-domain), slot 1 = BB_NB
+ *       NB row : table slot 1 = NB_NN (top-k of all kept neighbours)
+ * mode 1 (pass 2, NB rows only, needs bb_in = flags of ALL items):
+ *       NB row : table slot 0 = NB_BB (top-k neighbours that are BB)
+ * mode 2 (emit): appends every kept (j, sim, mutu, n) of row i at
+ *     emit_ptr[i] .. (order within a row unspecified) -- the materialised
+ *     return value of baseliner_calculate_sim_pipeline (assist.py:66-77).
+ * Tables are [n_items][2][k]; ordering = |sim| descending, ties to the smaller
+ * item index (SURVEY.md App. A.6 rule 3).
+ * ------------------------------------------------------------------------- */
+typedef struct xmap_sim_args {
+    /* layout */
+    const int32_t *csr_ptr; const uint64_t *csr_ent;
+    const int32_t *csc_ptr; const uint64_t *csc_ent;
+    const double *user_mu; const double *item_stats;
+    /* per-item codes (host-computed from the id strings) */
+    const int32_t *prefix_code;    /* iid[:2]  -- baselinerSim.py:191 */
+    const uint8_t *dom_code;       /* iid[-2:] -- extender.py:29     */
+    const uint8_t *contains;       /* bit d: label d is a substring of iid -- extender.py:32,34 */
+    const uint8_t *bb_in;          /* mode 1 only */
+    const int64_t *row_work;       /* from xmap_row_work; sizes the per-row hash */
+    int32_t n_items; int32_t method; int32_t num_atleast; int32_t k;
+    int32_t r2_bits;               /* ceil(log2(max |product|)) for the fixed-point scale */
+    int32_t mode;
+    /* outputs */
+    uint8_t *row_flags; int32_t *row_npairs; int32_t *row_nkept;
+    int32_t *tab_idx; double *tab_sim; int32_t *tab_mutu; int32_t *tab_n; int32_t *tab_len;
+    /* emit (mode 2) */
+    const int64_t *emit_ptr; int32_t *emit_j; double *emit_sim; int32_t *emit_mutu; int32_t *emit_n;
+    int32_t *emit_cursor;          /* [n_items] zero-initialised */
+    int32_t *error_flag;           /* device int, set nonzero on table overflow */
+} xmap_sim_args;
+
+/* Rows whose products fit a shared-memory hash: tier 0 needs row_work <=
+ * XMAP_SIM_TIER0_MAXWORK, tier 1 <= XMAP_SIM_TIER1_MAXWORK.  One CTA per row. */
+#define XMAP_SIM_TIER0_MAXWORK 1400
+#define XMAP_SIM_TIER1_MAXWORK 5600
+int xmap_sim_rows_smem(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
+                       int32_t tier, void *stream);
+
+/* Heavy rows: each row is cut into chunks of raters; chunks accumulate into a
+ * dense per-row table in HBM/L2 with 64-bit integer atomics (order-free, so
+ * the result does not depend on the chunking or the GPU count), then one CTA
+ * per row runs the same epilogue + selection.
+ *   table   : [n_slots][n_items] 16-byte cells, zero on entry, zero on exit
+ *   touched : [n_slots][n_items] int32 scratch; touched_n: [n_slots] zero on entry/exit
+ *   chunk_slot/chunk_row/chunk_lo/chunk_hi: [n_chunks] (csc entry range per chunk)
+ *   rows/row_slot semantics: row rows[b] uses table slot b. */
+int xmap_sim_big_accumulate(const xmap_sim_args *args_h,
+                            const int32_t *chunk_slot, const int32_t *chunk_row,
+                            const int32_t *chunk_lo, const int32_t *chunk_hi, int32_t n_chunks,
+                            uint64_t *table, int32_t *touched, int32_t *touched_n,
+                            int32_t *work_counter /* device int, zero on entry */, void *stream);
+int xmap_sim_big_finalize(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
+                          uint64_t *table, int32_t *touched, int32_t *touched_n, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * (3) X-SIM extension: masked path composition with fused aggregation.
+ * Replaces: ExtendSim.sim_extend + get_final_extension (extender.py:46-217).
+ * The facade turns the top-k tables into three index structures (all CSR-like):
+ *   legs      per start item x: the left segments x -> t   (extender.py:160-168)
+ *   partners  per bridge target t: the bridge pairs (t, s) (extender.py:61-81,178)
+ *   rsegs     per bridge source s: the right segments s -> y (extender.py:134-138)
+ * and this kernel evaluates every (leg, partner, rseg) combination = one
+ * reference path: s_p = sum(sim*mutu)/sum(mutu), c_p = prod(frac)
+ * (extender.py:83-89), accumulating xsim[x,y] = sum(s_p c_p)/sum(c_p)
+ * (extender.py:198-201) in a per-start hash table, never materialising paths.
+ * One warp owns one start item, so accumulation order is fixed by structure.
+ * ------------------------------------------------------------------------- */
+typedef struct xmap_xsim_args {
+    int32_t n_starts;
+    const int32_t *start_item;                /* [n_starts] */
+    const int64_t *leg_ptr;                   /* [n_starts+1] */
+    const int32_t *leg_t;                     /* index into partner lists */
+    const uint8_t *leg_joint_only;            /* 1: use only joint partners */
+    const double *leg_e1, *leg_m1, *leg_f1, *leg_e2, *leg_m2, *leg_f2;
+    const int64_t *par_ptr;                   /* [n_t+1] */
+    const int32_t *par_s;                     /* index into rseg lists */
+    const uint8_t *par_joint;
+    const double *par_e, *par_m, *par_f;
+    const int64_t *rs_ptr;                    /* [n_s+1] */
+    const int32_t *rs_end;
+    const double *rs_e1, *rs_m1, *rs_f1, *rs_e2, *rs_m2, *rs_f2;
+    /* per-start hash region: [hash_off[x], hash_off[x]+hash_size[x]) cells, size a power of two */
+    const int64_t *hash_off; const int32_t *hash_size;
+    int32_t *hash_key;                        /* zero on entry */
+    double *hash_num; double *hash_den;
+    int32_t top_m;                            /* <= XMAP_KMAX */
+    int32_t mode;                             /* 0: count + top-m, 2: emit all */
+    int32_t *out_count;                       /* [n_starts] #distinct ends */
+    int64_t *out_combos;                      /* [n_starts] #paths evaluated */
+    int32_t *top_end; double *top_xsim; int32_t *top_len;   /* [n_starts][top_m] */
+    const int64_t *emit_ptr; int32_t *emit_end; double *emit_xsim;
+    int32_t *error_flag;
+} xmap_xsim_args;
+
+int xmap_xsim_extend(const xmap_xsim_args *args_h, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * (4) AlterEgo generation.
+ * Replaces: Generator.cross_private_mapping / cross_nonprivate_mapping
+ * (generator.py:27-111), assist.map_to_dict (assist.py:210-215) and
+ * Generator.build_alterEgo (generator.py:113-157).
+ * choose modes: 0 argmax (the shipped py3 behaviour of the private path),
+ *               1 exponential mechanism, w_i = exp(eps*xsim_i/(2*range*GS)),
+ *                 index = searchsorted_left(cumsum(w/sum w), u)  (generator.py:42-70),
+ *               2 non-private: index floor(u*(m-1)) over the first min(m,4)
+ *                 candidates (generator.py:109-110); m == 1 -> index 0.
+ * uniforms: injected u[row] in [0,1) or NULL -> Philox4x32-10(seed, row).
+ * ------------------------------------------------------------------------- */
+int xmap_choose_mapping(const int32_t *top_end, const double *top_xsim, const int32_t *top_len,
+                        int32_t n_rows, int32_t top_m, int32_t mode, int32_t n_cand,
+                        double epsilon, int32_t mapping_range, int32_t global_sensitivity,
+                        const double *uniforms, uint64_t seed,
+                        int32_t *chosen, void *stream);
+
+/* map[s] = max over rows with chosen == s of start_item[row]; map pre-filled with -1. */
+int xmap_invert_mapping(const int32_t *start_item, const int32_t *chosen, int32_t n_rows,
+                        int32_t *map, void *stream);
+
+/* Rewrite every rating whose item has map >= 0 (CSR order), merge duplicates
+ * of (user, target) by mean with the time of the smallest source item.
+ * Returns the number of merged synthetic records through *n_out_h
+ * (synchronises the stream). Output arrays sized >= nnz. */
+size_t xmap_alterego_workspace_bytes(int64_t nnz);
+int xmap_build_alterego(const int32_t *csr_ptr, const uint64_t *csr_ent, const int32_t *csr_src,
+                        const int64_t *ts, int32_t n_users, int64_t nnz, const int32_t *map,
+                        int32_t *out_user, int32_t *out_item, double *out_rating, int64_t *out_ts,
+                        int64_t *n_out_h, void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XMAP_B200_H */

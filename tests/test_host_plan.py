@@ -1,0 +1,54 @@
+"""CPU: host-side logic -- the X-SIM plan builder (extend.build_plan) evaluated in plain Python
+reproduces the oracle's X-SIM, and the C-ABI library exports every declared symbol."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import restate as RS
+from tests import parity as PT
+
+
+@pytest.mark.parametrize("name", PT.GOLDEN_CASES)
+def test_plan_builder_reproduces_reference_xsim(name):
+    import torch
+    from xmap_b200 import extend as X
+    g = PT.load_golden(name)
+    meta = PT.golden_meta(g)
+    nU, nI = len(g["uids"]), len(g["iids"])
+    P = RS.sim_pairs(g["user"].astype(np.int64), g["item"].astype(np.int64), g["rating"], nU, nI,
+                     meta["prefix_code"], str(g["method"]), int(g["num_atleast"]))
+    k = int(g["k"])
+    knn = RS.select_knn(P, nI, k, meta["dom_code"], meta["contains"])
+    tabs = PT.tables_from_restatement(P, knn, nI, k)
+    plan = X.build_plan(tabs, torch.as_tensor(P["stats"]["count"]), torch.as_tensor(meta["has_S"]),
+                        torch.as_tensor(meta["has_T"]))
+    s, e, v, combos = PT.eval_plan_numpy(plan)
+    PT.compare_xsim(s, e, v, g["xs_start"], g["xs_end"], g["xs_val"], rtol=1e-9)
+    Xr = RS.xsim_extend(P, knn, nI, meta["has_S"], meta["has_T"])
+    assert combos == Xr["combos"] and plan.n_src == Xr["n_src"] and plan.n_joint == Xr["n_joint"]
+    assert int(plan.ub.sum()) == combos            # the per-start bound is exact in total
+
+
+def test_library_exports_every_declared_symbol(native_built):
+    from xmap_b200 import _native
+    hdr = open(os.path.join(PT.ROOT, "include", "xmap_b200.h")).read()
+    declared = set(re.findall(r"\b(xmap_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_native.EXPORTED_SYMBOLS), declared ^ set(_native.EXPORTED_SYMBOLS)
+    L = ctypes.CDLL(_native.LIB_PATH)
+    for s in declared:
+        assert hasattr(L, s), s
+    L.xmap_abi_version.restype = ctypes.c_int
+    assert L.xmap_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    """The product path must fail loudly, not fall back, when CUDA is unavailable."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from xmap_b200 import engine as E
+    with pytest.raises(Exception):
+        E.build_layout(np.zeros(1, np.int32), np.zeros(1, np.int32), np.ones(1), 1, 1)

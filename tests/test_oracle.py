@@ -1,0 +1,72 @@
+"""CPU: the oracle restatement (oracle/restate.py) is pinned against the golden vectors that
+the UNMODIFIED reference produced (oracle/make_golden.py), stage by stage."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import restate as RS
+from tests import parity as PT
+
+
+def _case(name):
+    g = PT.load_golden(name)
+    meta = PT.golden_meta(g)
+    nU, nI = len(g["uids"]), len(g["iids"])
+    P = RS.sim_pairs(g["user"].astype(np.int64), g["item"].astype(np.int64), g["rating"], nU, nI,
+                     meta["prefix_code"], str(g["method"]), int(g["num_atleast"]))
+    return g, meta, nU, nI, P
+
+
+@pytest.mark.parametrize("name", PT.GOLDEN_CASES)
+def test_restatement_similarity_vs_reference(name):
+    g, meta, nU, nI, P = _case(name)
+    assert np.array_equal(P["i"], g["sim_i"]) and np.array_equal(P["j"], g["sim_j"])
+    assert np.array_equal(P["mutu"], g["sim_mutu"]) and np.array_equal(P["frac"], g["sim_frac"])
+    assert np.array_equal(P["label"], g["sim_label"])
+    # bit-equal wherever numpy sums sequentially (n < 8), 1e-12 elsewhere
+    small = P["n"] < 8
+    assert np.array_equal(P["sim"][small], g["sim_val"][small])
+    np.testing.assert_allclose(P["sim"], g["sim_val"], rtol=1e-10)
+    st = P["stats"]
+    assert np.array_equal(st["mu"], g["user_avg"])
+    assert np.array_equal(np.stack([st["avg"], st["norm2"], st["adj_norm2"], st["count"]], 1), g["item_info"])
+
+
+@pytest.mark.parametrize("name", PT.GOLDEN_CASES)
+def test_restatement_selection_extension_generation_vs_reference(name):
+    g, meta, nU, nI, P = _case(name)
+    k = int(g["k"])
+    knn = RS.select_knn(P, nI, k, meta["dom_code"], meta["contains"])
+    assert np.array_equal(knn["bb"], g["bb"]) and np.array_equal(knn["valid_nb"], g["valid_nb"])
+    lists = PT.restate_lists(knn, P)
+    for nm in ("BB_BB", "BB_NB", "NB_BB", "NB_NN"):
+        assert np.array_equal(lists[nm][0], g[nm + "_ptr"]) and np.array_equal(lists[nm][1], g[nm + "_nbr"])
+    X = RS.xsim_extend(P, knn, nI, meta["has_S"], meta["has_T"])
+    PT.compare_xsim(X["start"], X["end"], X["xsim"], g["xs_start"], g["xs_end"], g["xs_val"], rtol=1e-9)
+    if "priv_rows" not in g:
+        return
+    rows, cands = RS.candidates(X["start"], X["end"], X["xsim"], 10)
+    ch, _ = RS.choose(rows, cands, "argmax")
+    assert np.array_equal(rows, g["priv_rows"]) and np.array_equal(ch, g["priv_chosen"])
+    mp = RS.invert_mapping(rows, ch, nI)
+    ae = RS.build_alterego(g["user"], g["item"], g["rating"], g["ts"], mp, meta["has_T"])
+    o = np.lexsort((ae["ts"], ae["rating"], ae["item"], ae["user"]))
+    assert np.array_equal(ae["user"][o], g["priv_ae_user"]) and np.array_equal(ae["item"][o], g["priv_ae_item"])
+    assert np.array_equal(ae["rating"][o], g["priv_ae_rating"]) and np.array_equal(ae["ts"][o], g["priv_ae_ts"])
+    rows4, cands4 = RS.candidates(X["start"], X["end"], X["xsim"], 4)
+    ok = np.array([len(c[0]) >= 2 for c in cands4])
+    u = np.zeros(len(rows4)); u[ok] = g["nonpriv_uniforms"]
+    chn, single = RS.choose(rows4, cands4, "nonprivate", uniforms=u)
+    assert np.array_equal(rows4[ok], g["nonpriv_rows"]) and np.array_equal(chn[ok], g["nonpriv_chosen"])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/code/xmap"), reason="reference tree not mounted")
+def test_harness_runs_the_reference_and_agrees_with_golden():
+    """Where /root/reference exists, re-run the reference itself on the smallest case."""
+    import subprocess, sys
+    code = ("import numpy as np;from oracle import make_golden as M;"
+            "o=M.build_case('adj_all_bridge');g=np.load('tests/golden/adj_all_bridge.npz');"
+            "assert all(np.array_equal(o[k],g[k]) for k in g.files if k!='ref_seconds');print('ok')")
+    r = subprocess.run([sys.executable, "-c", code], cwd=PT.ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

@@ -1,0 +1,108 @@
+"""ctypes binding of libxmap_b200.so (the C ABI declared in include/xmap_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails the
+caller gets an exception.  Build it with ``python -c "import __graft_entry__ as
+g; g.build()"`` (nvcc, sm_100a).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxmap_b200.so")
+
+KMAX = 64
+METHODS = {"adjust_cosine": 0, "cosine": 1}
+TIER0_MAXWORK = 1400
+TIER1_MAXWORK = 5600
+
+_p = C.c_void_p
+
+
+class SimArgs(C.Structure):
+    _fields_ = [
+        ("csr_ptr", _p), ("csr_ent", _p), ("csc_ptr", _p), ("csc_ent", _p),
+        ("user_mu", _p), ("item_stats", _p),
+        ("prefix_code", _p), ("dom_code", _p), ("contains", _p), ("bb_in", _p),
+        ("row_work", _p),
+        ("n_items", C.c_int32), ("method", C.c_int32), ("num_atleast", C.c_int32),
+        ("k", C.c_int32), ("r2_bits", C.c_int32), ("mode", C.c_int32),
+        ("row_flags", _p), ("row_npairs", _p), ("row_nkept", _p),
+        ("tab_idx", _p), ("tab_sim", _p), ("tab_mutu", _p), ("tab_n", _p), ("tab_len", _p),
+        ("emit_ptr", _p), ("emit_j", _p), ("emit_sim", _p), ("emit_mutu", _p), ("emit_n", _p),
+        ("emit_cursor", _p), ("error_flag", _p),
+    ]
+
+
+class XsimArgs(C.Structure):
+    _fields_ = [
+        ("n_starts", C.c_int32),
+        ("start_item", _p), ("leg_ptr", _p), ("leg_t", _p), ("leg_joint_only", _p),
+        ("leg_e1", _p), ("leg_m1", _p), ("leg_f1", _p), ("leg_e2", _p), ("leg_m2", _p), ("leg_f2", _p),
+        ("par_ptr", _p), ("par_s", _p), ("par_joint", _p), ("par_e", _p), ("par_m", _p), ("par_f", _p),
+        ("rs_ptr", _p), ("rs_end", _p),
+        ("rs_e1", _p), ("rs_m1", _p), ("rs_f1", _p), ("rs_e2", _p), ("rs_m2", _p), ("rs_f2", _p),
+        ("hash_off", _p), ("hash_size", _p), ("hash_key", _p), ("hash_num", _p), ("hash_den", _p),
+        ("top_m", C.c_int32), ("mode", C.c_int32),
+        ("out_count", _p), ("out_combos", _p),
+        ("top_end", _p), ("top_xsim", _p), ("top_len", _p),
+        ("emit_ptr", _p), ("emit_end", _p), ("emit_xsim", _p),
+        ("error_flag", _p),
+    ]
+
+
+_SIGS = {
+    "xmap_abi_version": (C.c_int, []),
+    "xmap_last_error": (C.c_char_p, []),
+    "xmap_layout_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
+    "xmap_build_layout": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int32, C.c_int32,
+                                    _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
+    "xmap_row_work": (C.c_int, [_p, _p, _p, C.c_int32, _p, _p]),
+    "xmap_sim_rows_smem": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, C.c_int32, _p]),
+    "xmap_sim_big_accumulate": (C.c_int, [C.POINTER(SimArgs), _p, _p, _p, _p, C.c_int32,
+                                          _p, _p, _p, _p, _p]),
+    "xmap_sim_big_finalize": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, _p, _p, _p, _p]),
+    "xmap_xsim_extend": (C.c_int, [C.POINTER(XsimArgs), _p]),
+    "xmap_choose_mapping": (C.c_int, [_p, _p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_double, C.c_int32, C.c_int32, _p, C.c_uint64, _p, _p]),
+    "xmap_invert_mapping": (C.c_int, [_p, _p, C.c_int32, _p, _p]),
+    "xmap_alterego_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "xmap_build_alterego": (C.c_int, [_p, _p, _p, _p, C.c_int32, C.c_int64, _p,
+                                      _p, _p, _p, _p, C.POINTER(C.c_int64), _p, C.c_size_t, _p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library once; raise loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise NativeError(
+                "%s is missing: the CUDA extension has not been built "
+                "(run __graft_entry__.build()); xmap_b200 has no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.xmap_abi_version() != 1:
+            raise NativeError("libxmap_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise NativeError("%s failed (%d): %s" % (what, rc, lib().xmap_last_error().decode()))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

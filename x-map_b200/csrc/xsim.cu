@@ -1,0 +1,169 @@
+// X-SIM bridge extension: every (left segment, bridge pair, right segment)
+// combination is one path of the reference's enumeration (extender.py:124-169);
+// its similarity s_p = sum(sim*mutu)/sum(mutu) and certainty c_p = prod(frac)
+// (extender.py:83-89) are accumulated per (start, end) into
+// xsim = sum(s_p c_p) / sum(c_p) (extender.py:198-201) without ever storing a
+// path.  One warp owns one start item and walks its legs and partners in a
+// fixed order, so a cell's sum depends only on the path structure (identical
+// items get bit-identical X-SIM values, which keeps top-k ties deterministic).
+//
+// Bound by accumulator traffic: each combo reads 7 doubles + 1 int of the
+// right-segment table (coalesced across the warp, L2-resident because a bridge
+// source is shared by many starts) and does one hash-cell read-modify-write.
+#include "common.cuh"
+
+namespace xmap {
+
+constexpr int XS_THREADS = 256;
+
+__global__ void __launch_bounds__(XS_THREADS) xsim_kernel(xmap_xsim_args a) {
+    const int x = (blockIdx.x * XS_THREADS + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (x >= a.n_starts) return;
+    const int64_t hoff = a.hash_off[x];
+    const int hsize = a.hash_size[x];
+    if (hsize <= 0 || (hsize & (hsize - 1)) != 0) {   // contract: power of two
+        if (lane == 0) atomicExch(a.error_flag, 3);
+        return;
+    }
+    const unsigned mask = (unsigned)hsize - 1u;
+    int shift = 32;
+    for (int s = hsize; s > 1; s >>= 1) --shift;
+    int32_t *hk = a.hash_key + hoff;
+    double *hn = a.hash_num + hoff;
+    double *hd = a.hash_den + hoff;
+    long long combos = 0;
+
+    for (int64_t lg = a.leg_ptr[x]; lg < a.leg_ptr[x + 1]; ++lg) {
+        const int t = a.leg_t[lg];
+        const bool joint_only = a.leg_joint_only[lg] != 0;
+        // sums in path order (extender.py:85-88): left edges first
+        const double Nl = __dadd_rn(a.leg_e1[lg], a.leg_e2[lg]);
+        const double Dl = __dadd_rn(a.leg_m1[lg], a.leg_m2[lg]);
+        const double Cl = __dmul_rn(a.leg_f1[lg], a.leg_f2[lg]);
+        for (int64_t pp = a.par_ptr[t]; pp < a.par_ptr[t + 1]; ++pp) {
+            if (joint_only && !a.par_joint[pp]) continue;
+            const int s = a.par_s[pp];
+            const double Nm = __dadd_rn(Nl, a.par_e[pp]);
+            const double Dm = __dadd_rn(Dl, a.par_m[pp]);
+            const double Cm = __dmul_rn(Cl, a.par_f[pp]);
+            const int64_t rb = a.rs_ptr[s], re = a.rs_ptr[s + 1];
+            for (int64_t r0 = rb; r0 < re; r0 += 32) {
+                const int64_t r = r0 + lane;
+                const bool valid = r < re;
+                int y = -1;
+                double num = 0.0, den = 0.0;
+                if (valid) {
+                    y = a.rs_end[r];
+                    const double Nn = __dadd_rn(__dadd_rn(Nm, a.rs_e1[r]), a.rs_e2[r]);
+                    const double Dd = __dadd_rn(__dadd_rn(Dm, a.rs_m1[r]), a.rs_m2[r]);
+                    const double cp = __dmul_rn(__dmul_rn(Cm, a.rs_f1[r]), a.rs_f2[r]);
+                    const double sp = (Dd != 0.0) ? __ddiv_rn(Nn, Dd) : 0.0;
+                    num = __dmul_rn(sp, cp);
+                    den = cp;
+                    ++combos;
+                }
+                // lanes that hit the same end: the lowest lane adds the terms in lane order
+                const unsigned grp = __match_any_sync(0xffffffffu, y);
+                const bool leader = valid && ((__ffs(grp) - 1) == lane);
+                unsigned rem = leader ? grp : 0u;
+                double an = 0.0, ad = 0.0;
+                while (__any_sync(0xffffffffu, rem != 0u)) {
+                    const int src = rem ? (__ffs(rem) - 1) : lane;
+                    const double n2 = __shfl_sync(0xffffffffu, num, src);
+                    const double d2 = __shfl_sync(0xffffffffu, den, src);
+                    if (rem) { an = __dadd_rn(an, n2); ad = __dadd_rn(ad, d2); rem &= rem - 1u; }
+                }
+                if (leader) {
+                    const int key = y + 1;
+                    unsigned slot = ((unsigned)y * 2654435761u) >> shift;
+                    if (shift == 32) slot = 0;
+                    bool done = false;
+                    for (int probe = 0; probe < hsize; ++probe) {
+                        int cur = *(volatile int32_t *)&hk[slot];
+                        if (cur != key) {
+                            if (cur == 0) {
+                                cur = atomicCAS(&hk[slot], 0, key);
+                                if (cur == 0) { hn[slot] = 0.0; hd[slot] = 0.0; }
+                            }
+                            if (cur != 0 && cur != key) { slot = (slot + 1) & mask; continue; }
+                        }
+                        hn[slot] = __dadd_rn(hn[slot], an);
+                        hd[slot] = __dadd_rn(hd[slot], ad);
+                        done = true;
+                        break;
+                    }
+                    if (!done) atomicExch(a.error_flag, 2);
+                }
+                __syncwarp();
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) combos += __shfl_xor_sync(0xffffffffu, combos, off);
+
+    if (a.mode == 2) {  // emit every (end, xsim) of this start
+        int64_t base = a.emit_ptr[x];
+        int written = 0;
+        for (int s0 = 0; s0 < hsize; s0 += 32) {
+            const int s = s0 + lane;
+            const int key = (s < hsize) ? hk[s] : 0;
+            const unsigned m = __ballot_sync(0xffffffffu, key != 0);
+            if (key != 0) {
+                const int64_t p = base + written + __popc(m & ((1u << lane) - 1u));
+                a.emit_end[p] = key - 1;
+                a.emit_xsim[p] = __ddiv_rn(hn[s], hd[s]);
+            }
+            written += __popc(m);
+        }
+        return;
+    }
+
+    // count + top-m by |xsim| desc, ties to the smaller end index (generator.py:85,109)
+    int cnt = 0;
+    for (int s = lane; s < hsize; s += 32) cnt += (hk[s] != 0);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    if (lane == 0) { a.out_count[x] = cnt; a.out_combos[x] = combos; }
+    const int M = min(a.top_m, cnt);
+    unsigned long long last_k = ~0ull;
+    int last_t = -1;
+    for (int r = 0; r < M; ++r) {
+        unsigned long long bk = 0;
+        int bt = 0x7FFFFFFF, bp = -1;
+        for (int s = lane; s < hsize; s += 32) {
+            const int key = hk[s];
+            if (key == 0) continue;
+            const unsigned long long kk = abs_key(__ddiv_rn(hn[s], hd[s]));
+            const int tt = key - 1;
+            // strictly after the previous winner in the total order
+            if (r > 0 && !better(last_k, last_t, kk, tt)) continue;
+            if (bp < 0 || better(kk, tt, bk, bt)) { bk = kk; bt = tt; bp = s; }
+        }
+        warp_argbest(bk, bt, bp);
+        if (bp < 0) break;
+        if (lane == 0) {
+            a.top_end[(size_t)x * a.top_m + r] = bt;
+            a.top_xsim[(size_t)x * a.top_m + r] = __ddiv_rn(hn[bp], hd[bp]);
+        }
+        last_k = bk; last_t = bt;
+    }
+    if (lane == 0) a.top_len[x] = M;
+}
+
+}  // namespace xmap
+
+using namespace xmap;
+
+extern "C" int xmap_xsim_extend(const xmap_xsim_args *args_h, void *stream_) {
+    const xmap_xsim_args &a = *args_h;
+    if (a.n_starts <= 0) return 0;
+    if (a.top_m < 1 || a.top_m > XMAP_KMAX) return fail_msg("xmap_xsim_extend: top_m out of range");
+    if (a.mode != 0 && a.mode != 2) return fail_msg("xmap_xsim_extend: bad mode");
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int warps_per_cta = XS_THREADS / 32;
+    const unsigned grid = (unsigned)((a.n_starts + warps_per_cta - 1) / warps_per_cta);
+    xsim_kernel<<<grid, XS_THREADS, 0, st>>>(a);
+    XMAP_LAUNCH_CHECK();
+    return 0;
+}

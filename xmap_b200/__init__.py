@@ -1,0 +1,9 @@
+"""Import alias: the package lives in ``x-map_b200/`` (a directory name Python
+cannot import directly); ``import xmap_b200`` resolves to it."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "x-map_b200")
+__path__ = [_real]
+__file__ = _os.path.join(_real, "__init__.py")
+with open(__file__) as _f:
+    exec(compile(_f.read(), __file__, "exec"))
