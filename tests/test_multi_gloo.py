@@ -1,0 +1,62 @@
+"""CPU, world_size 2, gloo: work-balanced row sharding and the table all-gather."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from xmap_b200.multi import RowShard, allgather_rows
+    g = torch.Generator().manual_seed(3)
+    work = (torch.rand(1001, generator=g) ** 4 * 1e5).long()
+    sh = RowShard(work, rank, world)
+    assert sh.bounds[0] == 0 and sh.bounds[-1] == 1001 and sh.bounds == sorted(sh.bounds)
+    full = torch.arange(1001 * 6, dtype=torch.float64).reshape(1001, 2, 3)
+    mine = torch.zeros_like(full)
+    mine[sh.lo:sh.hi] = full[sh.lo:sh.hi]
+    allgather_rows(mine, sh)
+    flags = torch.zeros(1001, dtype=torch.uint8)
+    flags[sh.lo:sh.hi] = (torch.arange(sh.lo, sh.hi) % 3 == 0).to(torch.uint8)
+    allgather_rows(flags, sh)
+    ok = bool(torch.equal(mine, full)) and bool(torch.equal(flags, (torch.arange(1001) % 3 == 0).to(torch.uint8)))
+    loads = [float(work[sh.bounds[r]:sh.bounds[r + 1]].sum()) for r in range(world)]
+    q.put((rank, ok, loads))
+    dist.destroy_process_group()
+
+
+def test_row_shard_and_allgather_world2():
+    import sys
+    from tests import parity  # noqa: F401  (puts the repo root on sys.path for the children)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res)
+    loads = res[0][2]
+    assert max(loads) / (sum(loads) / 2) < 1.25        # blocks balanced by work, not by row count
+
+
+def test_row_shard_single_rank_and_edge_cases():
+    from xmap_b200.multi import RowShard
+    sh = RowShard(torch.tensor([5, 0, 7]), 0, 1)
+    assert (sh.lo, sh.hi) == (0, 3)
+    for world in (2, 4, 8):
+        w = torch.zeros(3, dtype=torch.long)
+        b = [RowShard(w, r, world) for r in range(world)]
+        assert b[0].lo == 0 and b[-1].hi == 3 and all(x.hi == y.lo for x, y in zip(b, b[1:]))

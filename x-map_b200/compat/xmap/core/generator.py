@@ -1,0 +1,3 @@
+from xmap_b200.core.generator import *  # noqa: F401,F403
+from xmap_b200.core import generator as _m
+globals().update({k: getattr(_m, k) for k in dir(_m) if not k.startswith('__')})
