@@ -130,15 +130,21 @@ int xmap_sim_rows_smem(const xmap_sim_args *args_h, const int32_t *rows, int32_t
  * per row runs the same epilogue + selection.
  *   table   : [n_slots][n_items] 16-byte cells, zero on entry, zero on exit
  *   touched : [n_slots][n_items] int32 scratch; touched_n: [n_slots] zero on entry/exit
- *   chunk_slot/chunk_row/chunk_lo/chunk_hi: [n_chunks] (csc entry range per chunk)
- *   rows/row_slot semantics: row rows[b] uses table slot b. */
-int xmap_sim_big_accumulate(const xmap_sim_args *args_h,
-                            const int32_t *chunk_slot, const int32_t *chunk_row,
-                            const int32_t *chunk_lo, const int32_t *chunk_hi, int32_t n_chunks,
+ *   row rows[b] uses table slot b; work is fetched by warps in groups of 128 raters, row-major.
+ *   A dense-scanned row (touched >= n_items/8) takes n_items candidate records in the epilogue. */
+int xmap_sim_big_accumulate(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
+                            const int64_t *grp_off /* [n_rows+1] scan of ceil(raters/128) */,
                             uint64_t *table, int32_t *touched, int32_t *touched_n,
                             int32_t *work_counter /* device int, zero on entry */, void *stream);
+/* Epilogue of the heavy rows in three launches: scan of touched_n, a grid-wide evaluation of
+ * every touched cell (similarity, filter, label -> compact candidate records; clears the
+ * table), and one CTA per row for the top-k selection over its candidate records.
+ * `capacity` = upper bound on the batch's touched cells (sum over rows of min(row_work, n_items));
+ * scratch >= xmap_sim_big_scratch_bytes(n_rows, capacity).  Mode 2 needs emit_cursor zeroed. */
+size_t xmap_sim_big_scratch_bytes(int32_t n_rows, int64_t capacity);
 int xmap_sim_big_finalize(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
-                          uint64_t *table, int32_t *touched, int32_t *touched_n, void *stream);
+                          uint64_t *table, int32_t *touched, int32_t *touched_n,
+                          int64_t capacity, void *scratch, size_t scratch_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------
  * (3) X-SIM extension: masked path composition with fused aggregation.
@@ -151,12 +157,16 @@ int xmap_sim_big_finalize(const xmap_sim_args *args_h, const int32_t *rows, int3
  * reference path: s_p = sum(sim*mutu)/sum(mutu), c_p = prod(frac)
  * (extender.py:83-89), accumulating xsim[x,y] = sum(s_p c_p)/sum(c_p)
  * (extender.py:198-201) in a per-start hash table, never materialising paths.
- * One warp owns one start item, so accumulation order is fixed by structure.
+ * One warp owns one start item (or one slice of the legs of a heavy start; slices are merged
+ * by a fixed binary tree), so the summation order of every cell is fixed by structure.
  * ------------------------------------------------------------------------- */
 typedef struct xmap_xsim_args {
-    int32_t n_starts;
+    int32_t n_starts;                         /* start items in this launch */
+    int32_t n_units;                          /* work units: one per start, several (leg slices) per heavy start */
     const int32_t *start_item;                /* [n_starts] */
-    const int64_t *leg_ptr;                   /* [n_starts+1] */
+    const int32_t *start_unit;                /* [n_starts] unit whose table holds the start's merged cells */
+    const int64_t *unit_leg_lo, *unit_leg_hi; /* [n_units] leg range of the unit */
+    int64_t *unit_combos;                     /* [n_units] paths evaluated by the unit */
     const int32_t *leg_t;                     /* index into partner lists */
     const uint8_t *leg_joint_only;            /* 1: use only joint partners */
     const double *leg_e1, *leg_m1, *leg_f1, *leg_e2, *leg_m2, *leg_f2;
@@ -167,14 +177,16 @@ typedef struct xmap_xsim_args {
     const int64_t *rs_ptr;                    /* [n_s+1] */
     const int32_t *rs_end;
     const double *rs_e1, *rs_m1, *rs_f1, *rs_e2, *rs_m2, *rs_f2;
-    /* per-start hash region: [hash_off[x], hash_off[x]+hash_size[x]) cells, size a power of two */
+    /* per-unit hash region: [hash_off[u], hash_off[u]+hash_size[u]) cells, size a power of two >= 32 */
     const int64_t *hash_off; const int32_t *hash_size;
     int32_t *hash_key;                        /* zero on entry */
     double *hash_num; double *hash_den;
+    /* merge tree of the heavy starts: round r merges pairs [round_ptr_h[r], round_ptr_h[r+1]) */
+    int32_t n_rounds; const int32_t *round_ptr_h;   /* HOST array, n_rounds + 1 entries */
+    const int32_t *pair_dst, *pair_src;       /* unit indices; dst's table is sized for the union */
     int32_t top_m;                            /* <= XMAP_KMAX */
     int32_t mode;                             /* 0: count + top-m, 2: emit all */
     int32_t *out_count;                       /* [n_starts] #distinct ends */
-    int64_t *out_combos;                      /* [n_starts] #paths evaluated */
     int32_t *top_end; double *top_xsim; int32_t *top_len;   /* [n_starts][top_m] */
     const int64_t *emit_ptr; int32_t *emit_end; double *emit_xsim;
     int32_t *error_flag;

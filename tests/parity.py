@@ -287,12 +287,14 @@ def compare_xsim(start, end, val, ref_start, ref_end, ref_val, rtol=SIM_RTOL):
     return float(rel.max()) if rel.size else 0.0
 
 
-def run_gpu_extend(tabs, lay, meta, top_m=10, hash_budget=None):
+def run_gpu_extend(tabs, lay, meta, top_m=10, hash_budget=None, unit_combos=None):
     import torch
     from xmap_b200 import extend as X
     dm = to_device_meta(meta)
     plan = X.build_plan(tabs, lay.item_stats[:, 3].contiguous(), dm.has_S, dm.has_T)
     kw = {} if hash_budget is None else dict(hash_budget=hash_budget)
+    if unit_combos is not None:
+        kw["unit_combos"] = unit_combos
     xe = X.XsimEngine(plan, top_m, **kw)
     res = xe.run()
     s, e, v = xe.emit(res)

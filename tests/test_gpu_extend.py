@@ -67,8 +67,15 @@ def test_xsim_vs_restatement_and_batching():
     plan2, xe2, res2, (s2, e2, v2) = PT.run_gpu_extend(out["tabs"], out["lay"], case["meta"],
                                                        hash_budget=1 << 16)
     assert xe2.launches > xe.launches
-    assert np.array_equal(v, v2) and np.array_equal(e, e2)
+    assert np.array_equal(v, v2) and np.array_equal(e, e2)          # batching never changes a bit
     assert np.array_equal(res.top_end.cpu().numpy(), res2.top_end.cpu().numpy())
+    # heavy starts cut into leg slices + tree merge: same key sets and counts, values to 1e-9 (fp64 association differs)
+    plan3, xe3, res3, (s3, e3, v3) = PT.run_gpu_extend(out["tabs"], out["lay"], case["meta"], unit_combos=2000)
+    assert xe3.n_units > plan3.start_item.numel() and int(xe3.G.max()) > 8
+    assert np.array_equal(e, e3) and np.array_equal(s, s3)
+    np.testing.assert_allclose(v3, v, rtol=1e-9)
+    assert int(res3.combos.sum()) == X["combos"]
+    assert np.array_equal(res3.count.cpu().numpy(), res.count.cpu().numpy())
     # top-m rows = first m of the full rows ordered by |xsim| desc, ties to smaller end
     rows, cands = RS.candidates(X["start"], X["end"], X["xsim"], 10)
     te, tl = res.top_end.cpu().numpy(), res.top_len.cpu().numpy()

@@ -35,15 +35,17 @@ class SimArgs(C.Structure):
 
 class XsimArgs(C.Structure):
     _fields_ = [
-        ("n_starts", C.c_int32),
-        ("start_item", _p), ("leg_ptr", _p), ("leg_t", _p), ("leg_joint_only", _p),
+        ("n_starts", C.c_int32), ("n_units", C.c_int32),
+        ("start_item", _p), ("start_unit", _p), ("unit_leg_lo", _p), ("unit_leg_hi", _p), ("unit_combos", _p),
+        ("leg_t", _p), ("leg_joint_only", _p),
         ("leg_e1", _p), ("leg_m1", _p), ("leg_f1", _p), ("leg_e2", _p), ("leg_m2", _p), ("leg_f2", _p),
         ("par_ptr", _p), ("par_s", _p), ("par_joint", _p), ("par_e", _p), ("par_m", _p), ("par_f", _p),
         ("rs_ptr", _p), ("rs_end", _p),
         ("rs_e1", _p), ("rs_m1", _p), ("rs_f1", _p), ("rs_e2", _p), ("rs_m2", _p), ("rs_f2", _p),
         ("hash_off", _p), ("hash_size", _p), ("hash_key", _p), ("hash_num", _p), ("hash_den", _p),
+        ("n_rounds", C.c_int32), ("round_ptr_h", _p), ("pair_dst", _p), ("pair_src", _p),
         ("top_m", C.c_int32), ("mode", C.c_int32),
-        ("out_count", _p), ("out_combos", _p),
+        ("out_count", _p),
         ("top_end", _p), ("top_xsim", _p), ("top_len", _p),
         ("emit_ptr", _p), ("emit_end", _p), ("emit_xsim", _p),
         ("error_flag", _p),
@@ -58,9 +60,10 @@ _SIGS = {
                                     _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "xmap_row_work": (C.c_int, [_p, _p, _p, C.c_int32, _p, _p]),
     "xmap_sim_rows_smem": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, C.c_int32, _p]),
-    "xmap_sim_big_accumulate": (C.c_int, [C.POINTER(SimArgs), _p, _p, _p, _p, C.c_int32,
-                                          _p, _p, _p, _p, _p]),
-    "xmap_sim_big_finalize": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, _p, _p, _p, _p]),
+    "xmap_sim_big_accumulate": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, _p, _p, _p, _p, _p, _p]),
+    "xmap_sim_big_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
+    "xmap_sim_big_finalize": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, _p, _p, _p,
+                                        C.c_int64, _p, C.c_size_t, _p]),
     "xmap_xsim_extend": (C.c_int, [C.POINTER(XsimArgs), _p]),
     "xmap_choose_mapping": (C.c_int, [_p, _p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_double, C.c_int32, C.c_int32, _p, C.c_uint64, _p, _p]),

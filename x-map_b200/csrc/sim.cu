@@ -24,18 +24,40 @@ namespace xmap {
 
 constexpr int KMAX = XMAP_KMAX;
 
-template <int THREADS>
+#ifdef XMAP_PHASE_TIMING
+__device__ unsigned long long g_phase[8];
+#define PHASE_MARK(i) do { __syncthreads(); if (threadIdx.x == 0) { long long _t = clock64(); atomicAdd(&g_phase[i], (unsigned long long)(_t - _t0)); _t0 = _t; } } while (0)
+#else
+#define PHASE_MARK(i) do {} while (0)
+#endif
+
+// Candidate buffer of the per-row top-k selection.  A candidate belongs to exactly one of the
+// row's two lists; it is stored as a 128-bit sortable record:
+//   skey = (list 0 ? 1<<63 : 0) | bits(|sim|)        (0 = empty pad)
+//   spay = sign(sim)<<63 | item<<16 | position        (position indexes c_mutu / c_n)
+// A CTA-wide bitonic sort (descending skey, ties to the smaller item) then leaves list 0's best
+// first and list 1's best right after list 0's block.
+template <int THREADS, int CAP_>
 struct Scratch {
-    static constexpr int CAP = 2 * THREADS + 2 * KMAX;
-    double c_sim[CAP];
+    static constexpr int CAP = CAP_;
+    unsigned long long skey[CAP];
+    unsigned long long spay[CAP];
     double t_sim[2][KMAX];
     unsigned long long thr[2];
-    int c_j[CAP], c_mutu[CAP], c_n[CAP];
+    int c_mutu[CAP], c_n[CAP];
     int t_j[2][KMAX], t_mutu[2][KMAX], t_n[2][KMAX];
     int t_len[2];
-    int ncand, n_pairs, n_kept, any_label;
-    unsigned char c_l0[CAP], c_l1[CAP];
+    int ncand, n0, n_pairs, n_kept, any_label;
 };
+
+constexpr unsigned long long LIST0_BIT = 1ull << 63;
+constexpr unsigned long long ABS_MASK = ~LIST0_BIT;
+
+__device__ __forceinline__ int pay_item(unsigned long long pay) { return int((pay & ABS_MASK) >> 16); }
+__device__ __forceinline__ bool ranks_before(unsigned long long ka, unsigned long long pa,
+                                             unsigned long long kb, unsigned long long pb) {
+    return ka > kb || (ka == kb && pay_item(pa) < pay_item(pb));
+}
 
 struct RowCtx {
     int row, dom_i, prefix_i, cls_i;
@@ -69,17 +91,18 @@ __device__ __forceinline__ bool eval_pair(const xmap_sim_args &a, const RowCtx &
     return sim != 0.0 && mutu != 0;
 }
 
-// Walk raters [lo, hi) of `row` (CSC order); for every other item j in each
-// rater's CSR row call add(valid, j, agree, fx) with ALL lanes converged.
+// Walk raters [lo, hi) of `row` (CSC order); for every other item j in each rater's CSR row call
+// add(valid, j, agree, fx) with ALL lanes converged.  The raters are dealt round-robin to the
+// `nwarps` warps (a row with few raters still occupies every warp of its CTA) and each warp
+// prefetches the CSR extents of 32 of its raters lane-parallel (one latency round per 32 raters).
 template <class Add>
 __device__ __forceinline__ void accumulate_raters(const xmap_sim_args &a, int row, int cls_i, int lo, int hi,
                                                   int warp, int nwarps, Add add) {
     const int lane = lane_id();
     const bool adj = (a.method == XMAP_METHOD_ADJUST_COSINE);
     const int qbase = 62 - a.r2_bits;
-    for (int base = lo + warp * 32; base < hi; base += nwarps * 32) {
-        // lane-parallel prefetch of 32 raters' row extents (one latency round per 32 raters)
-        int e = base + lane;
+    for (int first = lo + warp; first < hi; first += nwarps * 32) {
+        const int e = first + nwarps * lane;
         uint32_t ux = 0;
         float r_l = 0.f;
         int rb = 0, re = 0;
@@ -93,7 +116,7 @@ __device__ __forceinline__ void accumulate_raters(const xmap_sim_args &a, int ro
             re = __ldg(a.csr_ptr + u + 1);
             if (adj) mu_l = __ldg(a.user_mu + u);
         }
-        const int cnt = min(32, hi - base);
+        const int cnt = min(32, (hi - first + nwarps - 1) / nwarps);
         for (int t = 0; t < cnt; ++t) {
             const uint32_t ux_t = __shfl_sync(0xffffffffu, ux, t);
             const float r_t = __shfl_sync(0xffffffffu, r_l, t);
@@ -125,70 +148,82 @@ __device__ __forceinline__ void accumulate_raters(const xmap_sim_args &a, int ro
 }
 
 // --------------------------------------------------------------------------
-// Selection: keep the best K of a candidate buffer per list, one warp per list.
+// Selection: sort the candidate buffer (plus the running tops) and keep the best K per list.
 // --------------------------------------------------------------------------
-template <int THREADS>
-__device__ void select_lists(Scratch<THREADS> &S, int K, bool use0, bool use1) {
+template <int THREADS, int CAP>
+__device__ void select_lists(Scratch<THREADS, CAP> &S, int K) {
     const int tid = threadIdx.x;
-    const int n0 = S.t_len[0], n1 = S.t_len[1];
+    const int n0t = S.t_len[0], n1t = S.t_len[1];
     const int nc = S.ncand;
     // running tops re-enter as candidates of their own list
-    if (tid < n0) {
-        int p = nc + tid;
-        S.c_sim[p] = S.t_sim[0][tid]; S.c_j[p] = S.t_j[0][tid];
+    if (tid < n0t) {
+        const int p = nc + tid;
+        const double v = S.t_sim[0][tid];
+        S.skey[p] = LIST0_BIT | abs_key(v);
+        S.spay[p] = (v < 0.0 ? LIST0_BIT : 0ull) | ((unsigned long long)S.t_j[0][tid] << 16) | (unsigned)p;
         S.c_mutu[p] = S.t_mutu[0][tid]; S.c_n[p] = S.t_n[0][tid];
-        S.c_l0[p] = 1; S.c_l1[p] = 0;
-    } else if (tid >= KMAX && tid < KMAX + n1) {
-        int q = tid - KMAX, p = nc + n0 + q;
-        S.c_sim[p] = S.t_sim[1][q]; S.c_j[p] = S.t_j[1][q];
+    } else if (tid >= KMAX && tid < KMAX + n1t) {
+        const int q = tid - KMAX, p = nc + n0t + q;
+        const double v = S.t_sim[1][q];
+        S.skey[p] = abs_key(v);
+        S.spay[p] = (v < 0.0 ? LIST0_BIT : 0ull) | ((unsigned long long)S.t_j[1][q] << 16) | (unsigned)p;
         S.c_mutu[p] = S.t_mutu[1][q]; S.c_n[p] = S.t_n[1][q];
-        S.c_l0[p] = 0; S.c_l1[p] = 1;
     }
+    const int total = nc + n0t + n1t;
+    const int n0 = S.n0 + n0t;
+    int N = 32;
+    while (N < total) N <<= 1;
+    for (int p = total + tid; p < N; p += THREADS) { S.skey[p] = 0ull; S.spay[p] = 0ull; }
     __syncthreads();
-    const int total = nc + n0 + n1;
-    const int warp = tid >> 5, lane = tid & 31;
-    if (warp < 2 && ((warp == 0) ? use0 : use1)) {
-        unsigned char *flag = (warp == 0) ? S.c_l0 : S.c_l1;
-        int got = 0;
-        for (int r = 0; r < K; ++r) {
-            unsigned long long bk = 0;
-            int bt = 0x7FFFFFFF, bp = -1;
-            for (int p = lane; p < total; p += 32) {
-                if (flag[p]) {
-                    unsigned long long kk = abs_key(S.c_sim[p]);
-                    int tt = S.c_j[p];
-                    if (bp < 0 || better(kk, tt, bk, bt)) { bk = kk; bt = tt; bp = p; }
+    for (int k = 2; k <= N; k <<= 1) {
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int i = tid; i < N; i += THREADS) {
+                const int l = i ^ jj;
+                if (l > i) {
+                    const unsigned long long ka = S.skey[i], pa = S.spay[i], kb = S.skey[l], pb = S.spay[l];
+                    const bool desc = ((i & k) == 0);
+                    const bool swap = desc ? ranks_before(kb, pb, ka, pa) : ranks_before(ka, pa, kb, pb);
+                    if (swap) { S.skey[i] = kb; S.spay[i] = pb; S.skey[l] = ka; S.spay[l] = pa; }
                 }
             }
-            warp_argbest(bk, bt, bp);
-            if (bp < 0) break;
-            if (lane == 0) {
-                S.t_sim[warp][r] = S.c_sim[bp]; S.t_j[warp][r] = S.c_j[bp];
-                S.t_mutu[warp][r] = S.c_mutu[bp]; S.t_n[warp][r] = S.c_n[bp];
-                flag[bp] = 0;
-            }
-            __syncwarp();
-            got = r + 1;
-        }
-        if (lane == 0) {
-            S.t_len[warp] = got;
-            S.thr[warp] = (got == K) ? abs_key(S.t_sim[warp][K - 1]) : 0ull;
+            __syncthreads();
         }
     }
+    const int L0 = min(K, n0), L1 = min(K, total - n0);
+    int src = -1, lst = 0, dst = 0;
+    if (tid < L0) { src = tid; lst = 0; dst = tid; }
+    else if (tid >= KMAX && tid < KMAX + L1) { src = n0 + (tid - KMAX); lst = 1; dst = tid - KMAX; }
+    double w_sim = 0.0; int w_j = 0, w_m = 0, w_n = 0;
+    if (src >= 0) {
+        const unsigned long long key = S.skey[src], pay = S.spay[src];
+        const double mag = __longlong_as_double((long long)(key & ABS_MASK));
+        w_sim = (pay & LIST0_BIT) ? -mag : mag;
+        w_j = pay_item(pay);
+        const int pos = int(pay & 0xFFFFull);
+        w_m = S.c_mutu[pos]; w_n = S.c_n[pos];
+    }
     __syncthreads();
-    if (tid == 0) S.ncand = 0;
+    if (src >= 0) { S.t_sim[lst][dst] = w_sim; S.t_j[lst][dst] = w_j; S.t_mutu[lst][dst] = w_m; S.t_n[lst][dst] = w_n; }
+    if (tid == 0) {
+        S.t_len[0] = L0; S.t_len[1] = L1;
+        S.thr[0] = (L0 == K) ? (S.skey[K - 1] & ABS_MASK) : 0ull;
+        S.thr[1] = (L1 == K) ? (S.skey[n0 + K - 1] & ABS_MASK) : 0ull;
+        S.ncand = 0; S.n0 = 0;
+    }
     __syncthreads();
 }
 
-// Fetch(e, j, n, mutu, fx, last_sweep) -> bool (false: empty entry)
-template <int THREADS, class Fetch>
-__device__ void finalize_row(const xmap_sim_args &a, const RowCtx &c, int n_entries, Fetch fetch,
-                             Scratch<THREADS> &S) {
+struct PreCounts { int have, n_pairs, n_kept, any_label; };
+
+// Get(e, j, n, mutu, sim, label, last_sweep) -> 0: empty entry, 1: co-rated but filtered, 2: kept
+template <int THREADS, int CAP, class Get>
+__device__ void finalize_row(const xmap_sim_args &a, const RowCtx &c, int n_entries, Get get,
+                             Scratch<THREADS, CAP> &S, PreCounts pre) {
     const int tid = threadIdx.x;
     const int K = a.k;
     const int row = c.row;
     if (tid == 0) {
-        S.ncand = 0; S.n_pairs = 0; S.n_kept = 0; S.any_label = 0;
+        S.ncand = 0; S.n0 = 0; S.n_pairs = 0; S.n_kept = 0; S.any_label = 0;
         S.t_len[0] = S.t_len[1] = 0; S.thr[0] = S.thr[1] = 0ull;
     }
     __syncthreads();
@@ -196,9 +231,8 @@ __device__ void finalize_row(const xmap_sim_args &a, const RowCtx &c, int n_entr
     if (a.mode == 2) {  // emit every kept pair (materialised sim RDD, assist.py:75-77)
         const int64_t base = a.emit_ptr[row];
         for (int e = tid; e < n_entries; e += THREADS) {
-            int j, n, mutu, label; long long fx; double sim;
-            if (!fetch(e, j, n, mutu, fx, true)) continue;
-            if (!eval_pair(a, c, j, n, mutu, fx, sim, label)) continue;
+            int j, n, mutu, label; double sim;
+            if (get(e, j, n, mutu, sim, label, true) != 2) continue;
             int pos = atomicAdd(&S.n_kept, 1);
             a.emit_j[base + pos] = j; a.emit_sim[base + pos] = sim;
             a.emit_mutu[base + pos] = mutu; a.emit_n[base + pos] = n;
@@ -207,24 +241,30 @@ __device__ void finalize_row(const xmap_sim_args &a, const RowCtx &c, int n_entr
     }
 
     bool bb = false;
-    if (a.mode == 0) {  // sweep 1: counts + is this a bridge item (assist.py:84-86)
-        int lp = 0, lk = 0, ll = 0;
-        for (int e = tid; e < n_entries; e += THREADS) {
-            int j, n, mutu, label; long long fx; double sim;
-            if (!fetch(e, j, n, mutu, fx, false)) continue;
-            ++lp;
-            if (eval_pair(a, c, j, n, mutu, fx, sim, label)) { ++lk; ll |= label; }
-        }
+    if (a.mode == 0) {  // counts + is this a bridge item (assist.py:84-86)
+        if (!pre.have) {
+            int lp = 0, lk = 0, ll = 0;
+            for (int e = tid; e < n_entries; e += THREADS) {
+                int j, n, mutu, label; double sim;
+                int st = get(e, j, n, mutu, sim, label, false);
+                if (st == 0) continue;
+                ++lp;
+                if (st == 2) { ++lk; ll |= label; }
+            }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            lp += __shfl_xor_sync(0xffffffffu, lp, off);
-            lk += __shfl_xor_sync(0xffffffffu, lk, off);
-            ll |= __shfl_xor_sync(0xffffffffu, ll, off);
-        }
-        if ((tid & 31) == 0) {
-            if (lp) atomicAdd(&S.n_pairs, lp);
-            if (lk) atomicAdd(&S.n_kept, lk);
-            if (ll) atomicOr(&S.any_label, 1);
+            for (int off = 16; off > 0; off >>= 1) {
+                lp += __shfl_xor_sync(0xffffffffu, lp, off);
+                lk += __shfl_xor_sync(0xffffffffu, lk, off);
+                ll |= __shfl_xor_sync(0xffffffffu, ll, off);
+            }
+            if ((tid & 31) == 0) {
+                if (lp) atomicAdd(&S.n_pairs, lp);
+                if (lk) atomicAdd(&S.n_kept, lk);
+                if (ll) atomicOr(&S.any_label, 1);
+            }
+            __syncthreads();
+        } else if (tid == 0) {
+            S.n_pairs = pre.n_pairs; S.n_kept = pre.n_kept; S.any_label = pre.any_label;
         }
         __syncthreads();
         bb = S.any_label != 0;
@@ -234,30 +274,31 @@ __device__ void finalize_row(const xmap_sim_args &a, const RowCtx &c, int n_entr
             a.row_nkept[row] = S.n_kept;
         }
     }
-    // list definitions (extender.py:30-43)
+    // list definitions (extender.py:30-43); every candidate belongs to exactly one list
     const bool use0 = (a.mode == 1) || bb;
     const bool use1 = (a.mode == 0);
     for (int base = 0; base < n_entries; base += THREADS) {
-        if (S.ncand > THREADS) select_lists<THREADS>(S, K, use0, use1);
+        if (S.ncand + THREADS + 2 * KMAX > CAP) select_lists<THREADS, CAP>(S, K);
         const int e = base + tid;
-        int j, n, mutu, label; long long fx; double sim;
-        if (e < n_entries && fetch(e, j, n, mutu, fx, true) && eval_pair(a, c, j, n, mutu, fx, sim, label)) {
-            bool l0, l1;
-            if (a.mode == 1) { l0 = a.bb_in[j] != 0; l1 = false; }
-            else if (bb) { bool same = (a.contains[j] >> c.dom_i) & 1; l0 = !same; l1 = same; }
-            else { l0 = false; l1 = true; }
+        int j, n, mutu, label; double sim;
+        if (e < n_entries && get(e, j, n, mutu, sim, label, true) == 2) {
+            int lst;
+            if (a.mode == 1) lst = (a.bb_in[j] != 0) ? 0 : -1;
+            else if (bb) lst = ((a.contains[j] >> c.dom_i) & 1) ? 1 : 0;
+            else lst = 1;
             const unsigned long long key = abs_key(sim);
-            if (l0 && S.thr[0] && key < S.thr[0]) l0 = false;
-            if (l1 && S.thr[1] && key < S.thr[1]) l1 = false;
-            if (l0 || l1) {
-                int p = atomicAdd(&S.ncand, 1);
-                S.c_sim[p] = sim; S.c_j[p] = j; S.c_mutu[p] = mutu; S.c_n[p] = n;
-                S.c_l0[p] = l0; S.c_l1[p] = l1;
+            if (lst >= 0 && S.thr[lst] && key < S.thr[lst]) lst = -1;
+            if (lst >= 0) {
+                const int p = atomicAdd(&S.ncand, 1);
+                if (lst == 0) atomicAdd(&S.n0, 1);
+                S.skey[p] = (lst == 0 ? LIST0_BIT : 0ull) | key;
+                S.spay[p] = (sim < 0.0 ? LIST0_BIT : 0ull) | ((unsigned long long)j << 16) | (unsigned)p;
+                S.c_mutu[p] = mutu; S.c_n[p] = n;
             }
         }
         __syncthreads();
     }
-    select_lists<THREADS>(S, K, use0, use1);
+    select_lists<THREADS, CAP>(S, K);
     // write tables [n_items][2][K]
     for (int slot = 0; slot < 2; ++slot) {
         const bool wr = (slot == 0) ? (a.mode == 1 || a.mode == 0) : (a.mode == 0);
@@ -280,11 +321,19 @@ __global__ void __launch_bounds__(THREADS) sim_hash_kernel(xmap_sim_args a, cons
                                                             int n_rows) {
     constexpr int SLOTS = 1 << LOG2_SLOTS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long *h_inner = reinterpret_cast<unsigned long long *>(smem_raw);
-    unsigned *h_key = reinterpret_cast<unsigned *>(h_inner + SLOTS);
+    // per slot: key (item+1, label in bit 31 after the epilogue), packed counts n<<16|mutu, and the
+    // 64-bit fixed-point inner product split in two 32-bit words (native 32-bit shared atomics;
+    // a 64-bit shared atomicAdd compiles to a compare-and-swap spin loop).
+    unsigned *h_lo = reinterpret_cast<unsigned *>(smem_raw);
+    unsigned *h_hi = h_lo + SLOTS;
+    unsigned *h_key = h_hi + SLOTS;
     unsigned *h_cnt = h_key + SLOTS;
-    Scratch<THREADS> &S = *reinterpret_cast<Scratch<THREADS> *>(h_cnt + SLOTS);
+    using ScratchT = Scratch<THREADS, 4 * THREADS>;
+    ScratchT &S = *reinterpret_cast<ScratchT *>(h_cnt + SLOTS);
 
+#ifdef XMAP_PHASE_TIMING
+    long long _t0 = clock64();
+#endif
     const int tid = threadIdx.x;
     const int row = rows[blockIdx.x];
     const RowCtx c = make_ctx(a, row);
@@ -295,8 +344,9 @@ __global__ void __launch_bounds__(THREADS) sim_hash_kernel(xmap_sim_args a, cons
     const int nslots = 1 << log2n;
     const unsigned mask = nslots - 1;
     const int shift = 32 - log2n;
-    for (int s = tid; s < nslots; s += THREADS) { h_key[s] = 0u; h_cnt[s] = 0u; h_inner[s] = 0ull; }
+    for (int s = tid; s < nslots; s += THREADS) { h_key[s] = 0u; h_cnt[s] = 0u; h_lo[s] = 0u; h_hi[s] = 0u; }
     __syncthreads();
+    PHASE_MARK(0);
 
     auto add = [&](bool valid, int j, unsigned agree, long long fx) {
         if (!valid) return;
@@ -309,50 +359,124 @@ __global__ void __launch_bounds__(THREADS) sim_hash_kernel(xmap_sim_args a, cons
                 if (cur != 0u && cur != key) { slot = (slot + 1) & mask; continue; }
             }
             atomicAdd(&h_cnt[slot], (1u << 16) | agree);
-            atomicAdd(&h_inner[slot], (unsigned long long)fx);
+            const unsigned lo32 = (unsigned)(unsigned long long)fx, hi32 = (unsigned)((unsigned long long)fx >> 32);
+            const unsigned old = atomicAdd(&h_lo[slot], lo32);
+            const unsigned carry = (old + lo32 < old) ? 1u : 0u;
+            if (hi32 + carry) atomicAdd(&h_hi[slot], hi32 + carry);
             return;
         }
         atomicExch(a.error_flag, 1);
     };
     accumulate_raters(a, row, c.cls_i, lo, hi, tid >> 5, THREADS >> 5, add);
     __syncthreads();
+    PHASE_MARK(1);
 
-    auto fetch = [&](int e, int &j, int &n, int &mutu, long long &fx, bool) -> bool {
-        unsigned key = h_key[e];
-        if (key == 0u) return false;
-        j = int(key - 1u);
-        unsigned cn = h_cnt[e];
+    // ---- compaction of the occupied slots (so the epilogue runs at full lane utilisation) ----
+    unsigned short *ent = reinterpret_cast<unsigned short *>(&S + 1);
+    __shared__ int s_nent, s_kept, s_label;
+    if (tid == 0) { s_nent = 0; s_kept = 0; s_label = 0; }
+    __syncthreads();
+    for (int base = 0; base < nslots; base += THREADS) {
+        const int e = base + tid;
+        const bool occ = (e < nslots) && (h_key[e] != 0u);
+        const unsigned m = __ballot_sync(0xffffffffu, occ);
+        if (m) {
+            int pos = 0;
+            const int leader = __ffs(m) - 1;
+            if ((tid & 31) == leader) pos = atomicAdd(&s_nent, __popc(m));
+            pos = __shfl_sync(0xffffffffu, pos, leader);
+            if (occ) ent[pos + __popc(m & ((1u << (tid & 31)) - 1u))] = (unsigned short)e;
+        }
+    }
+    __syncthreads();
+    const int n_ent = s_nent;
+    PHASE_MARK(2);
+    // ---- one evaluation per pair; the similarity replaces the accumulator in place ----
+    {
+        int lk = 0, ll = 0;
+        for (int q = tid; q < n_ent; q += THREADS) {
+            const int e = ent[q];
+            const unsigned key = h_key[e];
+            const unsigned cn = h_cnt[e];
+            double sim; int label;
+            const long long fx = (long long)(((unsigned long long)h_hi[e] << 32) | h_lo[e]);
+            const bool keep = eval_pair(a, c, int(key - 1u), int(cn >> 16), int(cn & 0xFFFFu), fx, sim, label);
+            const unsigned long long sb = keep ? (unsigned long long)__double_as_longlong(sim) : 0ull;
+            h_lo[e] = (unsigned)sb; h_hi[e] = (unsigned)(sb >> 32);
+            h_key[e] = key | (label ? 0x80000000u : 0u);
+            if (keep) { ++lk; ll |= label; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            lk += __shfl_xor_sync(0xffffffffu, lk, off);
+            ll |= __shfl_xor_sync(0xffffffffu, ll, off);
+        }
+        if ((tid & 31) == 0) {
+            if (lk) atomicAdd(&s_kept, lk);
+            if (ll) atomicOr(&s_label, 1);
+        }
+    }
+    __syncthreads();
+    PHASE_MARK(3);
+    auto get = [&](int q, int &j, int &n, int &mutu, double &sim, int &label, bool) -> int {
+        const int e = ent[q];
+        const unsigned long long sb = ((unsigned long long)h_hi[e] << 32) | h_lo[e];
+        if (sb == 0ull) return 1;
+        sim = __longlong_as_double((long long)sb);
+        const unsigned key = h_key[e];
+        j = int((key & 0x7FFFFFFFu) - 1u);
+        label = int(key >> 31);
+        const unsigned cn = h_cnt[e];
         n = int(cn >> 16); mutu = int(cn & 0xFFFFu);
-        fx = (long long)h_inner[e];
-        return true;
+        return 2;
     };
-    finalize_row<THREADS>(a, c, nslots, fetch, S);
+    finalize_row<THREADS, 4 * THREADS>(a, c, n_ent, get, S, PreCounts{1, n_ent, s_kept, s_label});
+    PHASE_MARK(4);
 }
 
 // --------------------------------------------------------------------------
 // Heavy rows: chunks of raters -> dense per-row table with 64-bit atomics.
 // --------------------------------------------------------------------------
-constexpr int BIG_THREADS = 512;
+constexpr int BIG_THREADS = 256;
+constexpr int RATER_GROUP = 128;       // raters per unit of work (one warp fetches one group)
 
+// Work = groups of RATER_GROUP consecutive raters, row-major (so concurrently running warps work
+// on the same few rows and their tables stay L2-resident).  Every warp fetches its own groups
+// from a global counter: no CTA-wide barrier anywhere.
 __global__ void __launch_bounds__(BIG_THREADS) sim_big_accum_kernel(
-    xmap_sim_args a, const int32_t *__restrict__ chunk_slot, const int32_t *__restrict__ chunk_row,
-    const int32_t *__restrict__ chunk_lo, const int32_t *__restrict__ chunk_hi, int n_chunks,
+    xmap_sim_args a, const int32_t *__restrict__ rows, int n_rows, const int64_t *__restrict__ grp_off,
     ulonglong2 *__restrict__ table, int32_t *__restrict__ touched, int32_t *__restrict__ touched_n,
     int32_t *__restrict__ work_counter) {
-    __shared__ int s_chunk;
-    const int tid = threadIdx.x, lane = tid & 31;
+    __shared__ int s_stage[BIG_THREADS / 32][64];     // per-warp staging of first-touched columns
+    const int lane = threadIdx.x & 31;
+    int *stage = s_stage[threadIdx.x >> 5];
+    const long long n_groups = grp_off[n_rows];
     while (true) {
-        if (tid == 0) s_chunk = atomicAdd(work_counter, 1);
-        __syncthreads();
-        const int cidx = s_chunk;
-        __syncthreads();
-        if (cidx >= n_chunks) break;
-        const int b = chunk_slot[cidx], row = chunk_row[cidx];
-        const int lo = chunk_lo[cidx], hi = chunk_hi[cidx];
+        int g = 0;
+        if (lane == 0) g = atomicAdd(work_counter, 1);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= n_groups) break;
+        int lo_b = 0, hi_b = n_rows;                  // largest b with grp_off[b] <= g
+        while (hi_b - lo_b > 1) {
+            const int mid = (lo_b + hi_b) >> 1;
+            if (grp_off[mid] <= g) lo_b = mid; else hi_b = mid;
+        }
+        const int b = lo_b, row = rows[b];
+        const int c_lo = a.csc_ptr[row], c_hi = a.csc_ptr[row + 1];
+        const int lo = c_lo + (int)(g - grp_off[b]) * RATER_GROUP;
+        const int hi = min(lo + RATER_GROUP, c_hi);
         const int cls_i = ceil_log2_u32((uint32_t)a.item_stats[4 * (size_t)row + 3]);
         ulonglong2 *T = table + (size_t)b * a.n_items;
         int32_t *tl = touched + (size_t)b * a.n_items;
         int32_t *tn = touched_n + b;
+        int nstage = 0;                                // warp-uniform
+        auto flush = [&](int count) {                  // move `count` staged columns to the row's list
+            int basep = 0;
+            if (lane == 0) basep = atomicAdd(tn, count);
+            basep = __shfl_sync(0xffffffffu, basep, 0);
+            for (int q = lane; q < count; q += 32) tl[basep + q] = stage[q];
+            __syncwarp();
+        };
         auto add = [&](bool valid, int j, unsigned agree, long long fx) {
             bool first = false;
             if (valid) {
@@ -362,45 +486,244 @@ __global__ void __launch_bounds__(BIG_THREADS) sim_big_accum_kernel(
             }
             const unsigned m = __ballot_sync(0xffffffffu, first);
             if (m) {
-                const int leader = __ffs(m) - 1;
-                int basep = 0;
-                if (lane == leader) basep = atomicAdd(tn, __popc(m));
-                basep = __shfl_sync(0xffffffffu, basep, leader);
-                if (first) tl[basep + __popc(m & ((1u << lane) - 1u))] = j;
+                if (first) stage[nstage + __popc(m & ((1u << lane) - 1u))] = j;
+                nstage += __popc(m);
+                __syncwarp();
+                if (nstage > 32) {                     // keep at most 32 staged so the next round fits
+                    flush(nstage);
+                    nstage = 0;
+                }
             }
         };
-        accumulate_raters(a, row, cls_i, lo, hi, tid >> 5, BIG_THREADS >> 5, add);
+        accumulate_raters(a, row, cls_i, lo, hi, 0, 1, add);
+        if (nstage) flush(nstage);
     }
 }
 
 constexpr int FIN_THREADS = 256;
+constexpr int EVAL_TILE = 2048;
+constexpr int EVAL_UNROLL = 4;
 
-__global__ void __launch_bounds__(FIN_THREADS) sim_big_finalize_kernel(
-    xmap_sim_args a, const int32_t *__restrict__ rows, int n_rows, ulonglong2 *__restrict__ table,
-    int32_t *__restrict__ touched, int32_t *__restrict__ touched_n) {
-    __shared__ Scratch<FIN_THREADS> S;
+// Scratch of the heavy-row epilogue (device memory, caller-provided):
+struct BigScratch {
+    long long *ent_off;     // [n_rows + 1] scan of per-row entry counts (n_items for dense rows)
+    long long *tile_off;    // [n_rows + 1] scan of per-row tile counts
+    int *row_kept;          // [n_rows]
+    int *row_label;         // [n_rows]
+    int *tile_counter;      // [1]
+    double *c_sim;          // [capacity] 0.0 = filtered / empty
+    int *c_j, *c_mutu, *c_n;
+    unsigned char *c_label;
+    long long capacity;
+};
+
+// A row whose touched list covers >= 1/8 of the columns is evaluated by a linear scan of its
+// dense table (coalesced) instead of through the list (random access).
+__device__ __forceinline__ bool row_is_dense(int touched, int n_items) { return (long long)touched * 8 >= n_items; }
+
+__global__ void big_scan_kernel(const int32_t *__restrict__ touched_n, int n_rows, int n_items, BigScratch sc,
+                                int32_t *error_flag) {
+    __shared__ long long s_ent[1024], s_tile[1024];
+    const int tid = threadIdx.x;
+    const int per = (n_rows + 1023) / 1024;
+    long long le = 0, lt = 0;
+    for (int q = 0; q < per; ++q) {
+        int b = tid * per + q;
+        if (b < n_rows) {
+            const int t = touched_n[b];
+            const long long len = row_is_dense(t, n_items) ? n_items : t;
+            le += len; lt += (len + EVAL_TILE - 1) / EVAL_TILE;
+        }
+    }
+    s_ent[tid] = le; s_tile[tid] = lt;
+    __syncthreads();
+    if (tid == 0) {
+        long long re = 0, rt = 0;
+        for (int t = 0; t < 1024; ++t) {
+            long long v = s_ent[t]; s_ent[t] = re; re += v;
+            v = s_tile[t]; s_tile[t] = rt; rt += v;
+        }
+        sc.ent_off[n_rows] = re; sc.tile_off[n_rows] = rt;
+        *sc.tile_counter = 0;
+        if (re > sc.capacity) atomicExch(error_flag, 4);
+    }
+    __syncthreads();
+    long long re = s_ent[tid], rt = s_tile[tid];
+    for (int q = 0; q < per; ++q) {
+        int b = tid * per + q;
+        if (b < n_rows) {
+            const int t = touched_n[b];
+            const long long len = row_is_dense(t, n_items) ? n_items : t;
+            sc.ent_off[b] = re; sc.tile_off[b] = rt;
+            re += len; rt += (len + EVAL_TILE - 1) / EVAL_TILE;
+            sc.row_kept[b] = 0; sc.row_label[b] = 0;
+        }
+    }
+}
+
+// Grid-wide epilogue over every touched cell of the batch: similarity, filter, label -> compact
+// candidate records; clears the table cell.  Work is cut into tiles of EVAL_TILE entries of ONE row,
+// so a row with 400 K neighbours is spread over ~200 CTAs instead of being one CTA's long pole.
+__global__ void __launch_bounds__(256) big_eval_kernel(xmap_sim_args a, const int32_t *__restrict__ rows, int n_rows,
+                                                       ulonglong2 *__restrict__ table,
+                                                       const int32_t *__restrict__ touched,
+                                                       const int32_t *__restrict__ touched_n, BigScratch sc) {
+    __shared__ int s_tile, s_b, s_kept, s_label;
+    const int tid = threadIdx.x;
+    if (sc.ent_off[n_rows] > sc.capacity) return;
+    const long long n_tiles = sc.tile_off[n_rows];
+    while (true) {
+        if (tid == 0) {
+            const int t = atomicAdd(sc.tile_counter, 1);
+            s_tile = t; s_kept = 0; s_label = 0;
+            int lo = 0, hi = n_rows;                  // largest b with tile_off[b] <= t
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (sc.tile_off[mid] <= t) lo = mid; else hi = mid;
+            }
+            s_b = lo;
+        }
+        __syncthreads();
+        const long long t = s_tile;
+        const int b = s_b;
+        if (t >= n_tiles) break;
+        const int row = rows[b];
+        const RowCtx c = make_ctx(a, row);
+        const int tn = touched_n[b];
+        const bool dense = row_is_dense(tn, a.n_items);
+        const int len = dense ? a.n_items : tn;
+        const int e0 = (int)(t - sc.tile_off[b]) * EVAL_TILE;
+        const int e1 = min(e0 + EVAL_TILE, len);
+        ulonglong2 *T = table + (size_t)b * a.n_items;
+        const int32_t *tl = touched + (size_t)b * a.n_items;
+        const long long goff = sc.ent_off[b];
+        const bool cosine = (a.method == XMAP_METHOD_COSINE);
+        int lk = 0, ll = 0;
+        for (int eb = e0 + tid; eb < e1; eb += 256 * EVAL_UNROLL) {
+            int j[EVAL_UNROLL];
+            ulonglong2 cell[EVAL_UNROLL];
+            double den_j[EVAL_UNROLL], cnt_j[EVAL_UNROLL];
+            int pre_j[EVAL_UNROLL];
+#pragma unroll
+            for (int u = 0; u < EVAL_UNROLL; ++u) {
+                const int e = eb + u * 256;
+                j[u] = (e < e1) ? (dense ? e : tl[e]) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < EVAL_UNROLL; ++u) {
+                cell[u] = make_ulonglong2(0ull, 0ull);
+                if (j[u] >= 0) cell[u] = T[j[u]];
+            }
+#pragma unroll
+            for (int u = 0; u < EVAL_UNROLL; ++u) {
+                if (j[u] >= 0 && cell[u].x != 0ull) {
+                    const double *sj = a.item_stats + 4 * (size_t)j[u];
+                    den_j[u] = cosine ? sj[1] : sj[2];
+                    cnt_j[u] = sj[3];
+                    pre_j[u] = a.prefix_code[j[u]];
+                    T[j[u]] = make_ulonglong2(0ull, 0ull);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < EVAL_UNROLL; ++u) {
+                const int e = eb + u * 256;
+                if (j[u] < 0) continue;
+                const long long g = goff + e;
+                if (cell[u].x == 0ull) {               // dense scan: an untouched column
+                    if (a.mode != 2) sc.c_sim[g] = 0.0;
+                    continue;
+                }
+                const int n = int(cell[u].x >> 32), mutu = int(cell[u].x & 0xFFFFFFFFull);
+                const int q = 62 - a.r2_bits - min(c.cls_i, ceil_log2_u32((uint32_t)cnt_j[u]));
+                const double inner = (double)(long long)cell[u].y * pow2d(-q);
+                const double dd = __dmul_rn(c.den_i, den_j[u]);
+                const double cosv = (dd != 0.0) ? __ddiv_rn(inner, dd) : 0.0;
+                const double sim = __ddiv_rn(__dmul_rn(cosv, (double)min(n, a.num_atleast)), (double)a.num_atleast);
+                const int label = (pre_j[u] != c.prefix_i) ? 1 : 0;
+                const bool keep = sim != 0.0 && mutu != 0;
+                if (a.mode == 2) {
+                    if (keep) {
+                        const int pos = atomicAdd(&a.emit_cursor[row], 1);
+                        const int64_t o = a.emit_ptr[row] + pos;
+                        a.emit_j[o] = j[u]; a.emit_sim[o] = sim; a.emit_mutu[o] = mutu; a.emit_n[o] = n;
+                    }
+                } else {
+                    sc.c_sim[g] = keep ? sim : 0.0; sc.c_j[g] = j[u]; sc.c_mutu[g] = mutu; sc.c_n[g] = n;
+                    sc.c_label[g] = (unsigned char)label;
+                }
+                if (keep) { ++lk; ll |= label; }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            lk += __shfl_xor_sync(0xffffffffu, lk, off);
+            ll |= __shfl_xor_sync(0xffffffffu, ll, off);
+        }
+        if ((tid & 31) == 0) {
+            if (lk) atomicAdd(&s_kept, lk);
+            if (ll) atomicOr(&s_label, 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (s_kept) atomicAdd(&sc.row_kept[b], s_kept);
+            if (s_label) atomicOr(&sc.row_label[b], 1);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(FIN_THREADS) big_select_kernel(xmap_sim_args a, const int32_t *__restrict__ rows,
+                                                                 int n_rows, int32_t *__restrict__ touched_n,
+                                                                 BigScratch sc) {
+    __shared__ Scratch<FIN_THREADS, 4 * FIN_THREADS> S;
     const int b = blockIdx.x;
     const int row = rows[b];
-    const RowCtx c = make_ctx(a, row);
-    ulonglong2 *T = table + (size_t)b * a.n_items;
-    const int32_t *tl = touched + (size_t)b * a.n_items;
-    const int n_entries = touched_n[b];
-    auto fetch = [&](int e, int &j, int &n, int &mutu, long long &fx, bool last) -> bool {
-        j = tl[e];
-        ulonglong2 cell = T[j];
-        n = int(cell.x >> 32); mutu = int(cell.x & 0xFFFFFFFFull);
-        fx = (long long)cell.y;
-        if (last) T[j] = make_ulonglong2(0ull, 0ull);
-        return true;
-    };
-    finalize_row<FIN_THREADS>(a, c, n_entries, fetch, S);
+    const long long total = sc.ent_off[n_rows];
+    if (total > sc.capacity) return;
+    const long long off = sc.ent_off[b];
+    const int n_entries = (int)(sc.ent_off[b + 1] - off);
+    const int n_touched = touched_n[b];
     __syncthreads();
     if (threadIdx.x == 0) touched_n[b] = 0;
+    if (a.mode == 2) return;
+    const RowCtx c = make_ctx(a, row);
+    auto get = [&](int e, int &j, int &n, int &mutu, double &sim, int &label, bool) -> int {
+        sim = sc.c_sim[off + e];
+        if (sim == 0.0) return 1;
+        j = sc.c_j[off + e]; mutu = sc.c_mutu[off + e]; n = sc.c_n[off + e]; label = sc.c_label[off + e];
+        return 2;
+    };
+    finalize_row<FIN_THREADS, 4 * FIN_THREADS>(a, c, n_entries, get, S,
+                              PreCounts{1, n_touched, sc.row_kept[b], sc.row_label[b]});
+}
+
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t big_scratch_layout(int n_rows, long long capacity, char *base, BigScratch *sc) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += al256(bytes); return base ? base + o : (char *)nullptr; };
+    char *p_off = take(sizeof(long long) * ((size_t)n_rows + 1));
+    char *p_toff = take(sizeof(long long) * ((size_t)n_rows + 1));
+    char *p_kept = take(sizeof(int) * (size_t)n_rows);
+    char *p_lab = take(sizeof(int) * (size_t)n_rows);
+    char *p_cnt = take(256);
+    char *p_sim = take(sizeof(double) * (size_t)capacity);
+    char *p_j = take(sizeof(int) * (size_t)capacity);
+    char *p_m = take(sizeof(int) * (size_t)capacity);
+    char *p_n = take(sizeof(int) * (size_t)capacity);
+    char *p_l = take((size_t)capacity);
+    if (sc) {
+        sc->ent_off = (long long *)p_off; sc->tile_off = (long long *)p_toff; sc->row_kept = (int *)p_kept; sc->row_label = (int *)p_lab;
+        sc->tile_counter = (int *)p_cnt; sc->c_sim = (double *)p_sim; sc->c_j = (int *)p_j;
+        sc->c_mutu = (int *)p_m; sc->c_n = (int *)p_n; sc->c_label = (unsigned char *)p_l;
+        sc->capacity = capacity;
+    }
+    return off;
 }
 
 template <int LOG2_SLOTS, int THREADS>
 static int launch_hash(const xmap_sim_args &a, const int32_t *rows, int n_rows, cudaStream_t st) {
-    size_t smem = (size_t)(1 << LOG2_SLOTS) * 16 + sizeof(Scratch<THREADS>);
+    size_t smem = (size_t)(1 << LOG2_SLOTS) * 16 + sizeof(Scratch<THREADS, 4 * THREADS>) + (size_t)(1 << LOG2_SLOTS) * 2;
     auto kern = sim_hash_kernel<LOG2_SLOTS, THREADS>;
     XMAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<n_rows, THREADS, smem, st>>>(a, rows, n_rows);
@@ -427,17 +750,15 @@ extern "C" int xmap_sim_rows_smem(const xmap_sim_args *args_h, const int32_t *ro
     if (n_rows <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream_;
     if (tier == 0) return launch_hash<11, 256>(*args_h, rows, n_rows, st);
-    if (tier == 1) return launch_hash<13, 1024>(*args_h, rows, n_rows, st);
+    if (tier == 1) return launch_hash<13, 512>(*args_h, rows, n_rows, st);
     return fail_msg("xmap_sim_rows_smem: bad tier");
 }
 
-extern "C" int xmap_sim_big_accumulate(const xmap_sim_args *args_h, const int32_t *chunk_slot,
-                                       const int32_t *chunk_row, const int32_t *chunk_lo,
-                                       const int32_t *chunk_hi, int32_t n_chunks, uint64_t *table,
-                                       int32_t *touched, int32_t *touched_n, int32_t *work_counter,
-                                       void *stream_) {
+extern "C" int xmap_sim_big_accumulate(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
+                                       const int64_t *grp_off, uint64_t *table, int32_t *touched,
+                                       int32_t *touched_n, int32_t *work_counter, void *stream_) {
     if (int rc = check_args(*args_h)) return rc;
-    if (n_chunks <= 0) return 0;
+    if (n_rows <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream_;
     int dev = 0, sms = 148;
     XMAP_CUDA(cudaGetDevice(&dev));
@@ -445,23 +766,50 @@ extern "C" int xmap_sim_big_accumulate(const xmap_sim_args *args_h, const int32_
     int per_sm = 2;
     XMAP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sim_big_accum_kernel, BIG_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
-    int grid = sms * per_sm;
-    if (grid > n_chunks) grid = n_chunks;
-    sim_big_accum_kernel<<<grid, BIG_THREADS, 0, st>>>(*args_h, chunk_slot, chunk_row, chunk_lo, chunk_hi,
-                                                      n_chunks, reinterpret_cast<ulonglong2 *>(table),
-                                                      touched, touched_n, work_counter);
+    sim_big_accum_kernel<<<sms * per_sm, BIG_THREADS, 0, st>>>(*args_h, rows, n_rows, grp_off,
+                                                              reinterpret_cast<ulonglong2 *>(table), touched,
+                                                              touched_n, work_counter);
     XMAP_LAUNCH_CHECK();
     return 0;
 }
 
+extern "C" size_t xmap_sim_big_scratch_bytes(int32_t n_rows, int64_t capacity) {
+    return big_scratch_layout(n_rows, capacity, nullptr, nullptr);
+}
+
 extern "C" int xmap_sim_big_finalize(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
-                                     uint64_t *table, int32_t *touched, int32_t *touched_n, void *stream_) {
+                                     uint64_t *table, int32_t *touched, int32_t *touched_n,
+                                     int64_t capacity, void *scratch, size_t scratch_bytes, void *stream_) {
     if (int rc = check_args(*args_h)) return rc;
     if (n_rows <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream_;
-    sim_big_finalize_kernel<<<n_rows, FIN_THREADS, 0, st>>>(*args_h, rows, n_rows,
-                                                            reinterpret_cast<ulonglong2 *>(table), touched,
-                                                            touched_n);
+    BigScratch sc;
+    if (big_scratch_layout(n_rows, capacity, (char *)scratch, &sc) > scratch_bytes)
+        return fail_msg("xmap_sim_big_finalize: scratch too small");
+    int dev = 0, sms = 148;
+    XMAP_CUDA(cudaGetDevice(&dev));
+    XMAP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    big_scan_kernel<<<1, 1024, 0, st>>>(touched_n, n_rows, args_h->n_items, sc, args_h->error_flag);
+    XMAP_LAUNCH_CHECK();
+    int eval_per_sm = 3;
+    XMAP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_per_sm, big_eval_kernel, 256, 0));
+    if (eval_per_sm < 1) eval_per_sm = 1;
+    big_eval_kernel<<<sms * eval_per_sm, 256, 0, st>>>(*args_h, rows, n_rows,
+                                                      reinterpret_cast<ulonglong2 *>(table), touched, touched_n, sc);
+    XMAP_LAUNCH_CHECK();
+    big_select_kernel<<<n_rows, FIN_THREADS, 0, st>>>(*args_h, rows, n_rows, touched_n, sc);
     XMAP_LAUNCH_CHECK();
     return 0;
 }
+
+#ifdef XMAP_PHASE_TIMING
+extern "C" int xmap_debug_phase_cycles(unsigned long long *out_h, int reset) {
+    XMAP_CUDA(cudaDeviceSynchronize());
+    XMAP_CUDA(cudaMemcpyFromSymbol(out_h, xmap::g_phase, sizeof(unsigned long long) * 8));
+    if (reset) {
+        unsigned long long z[8] = {0};
+        XMAP_CUDA(cudaMemcpyToSymbol(xmap::g_phase, z, sizeof(z)));
+    }
+    return 0;
+}
+#endif

@@ -16,25 +16,50 @@ namespace xmap {
 
 constexpr int XS_THREADS = 256;
 
-__global__ void __launch_bounds__(XS_THREADS) xsim_kernel(xmap_xsim_args a) {
+// find-or-insert `key` (item + 1) in an open-addressing table; returns the slot or -1 (full).
+// Only one warp (accumulate) or one CTA (merge) ever writes a given table, so a plain CAS on the
+// key is enough; num/den of a fresh slot are initialised by the inserting thread.
+__device__ __forceinline__ int table_slot(int32_t *hk, double *hn, double *hd, int hsize, int shift, int key) {
+    const unsigned mask = (unsigned)hsize - 1u;
+    unsigned slot = ((unsigned)(key - 1) * 2654435761u) >> shift;
+    for (int probe = 0; probe < hsize; ++probe) {
+        int cur = *(volatile int32_t *)&hk[slot];
+        if (cur != key) {
+            if (cur == 0) {
+                cur = atomicCAS(&hk[slot], 0, key);
+                if (cur == 0) { hn[slot] = 0.0; hd[slot] = 0.0; }
+            }
+            if (cur != 0 && cur != key) { slot = (slot + 1) & mask; continue; }
+        }
+        return (int)slot;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ int table_shift(int hsize) {
+    int shift = 32;
+    for (int s = hsize; s > 1; s >>= 1) --shift;
+    return shift;
+}
+
+// One warp per work unit (a start item, or a slice of the legs of a heavy start).
+__global__ void __launch_bounds__(XS_THREADS) xsim_accum_kernel(xmap_xsim_args a) {
     const int x = (blockIdx.x * XS_THREADS + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (x >= a.n_starts) return;
+    if (x >= a.n_units) return;
     const int64_t hoff = a.hash_off[x];
     const int hsize = a.hash_size[x];
-    if (hsize <= 0 || (hsize & (hsize - 1)) != 0) {   // contract: power of two
+    if (hsize < 32 || (hsize & (hsize - 1)) != 0) {   // contract: power of two >= 32
         if (lane == 0) atomicExch(a.error_flag, 3);
         return;
     }
-    const unsigned mask = (unsigned)hsize - 1u;
-    int shift = 32;
-    for (int s = hsize; s > 1; s >>= 1) --shift;
+    const int shift = table_shift(hsize);
     int32_t *hk = a.hash_key + hoff;
     double *hn = a.hash_num + hoff;
     double *hd = a.hash_den + hoff;
     long long combos = 0;
 
-    for (int64_t lg = a.leg_ptr[x]; lg < a.leg_ptr[x + 1]; ++lg) {
+    for (int64_t lg = a.unit_leg_lo[x]; lg < a.unit_leg_hi[x]; ++lg) {
         const int t = a.leg_t[lg];
         const bool joint_only = a.leg_joint_only[lg] != 0;
         // sums in path order (extender.py:85-88): left edges first
@@ -75,25 +100,9 @@ __global__ void __launch_bounds__(XS_THREADS) xsim_kernel(xmap_xsim_args a) {
                     if (rem) { an = __dadd_rn(an, n2); ad = __dadd_rn(ad, d2); rem &= rem - 1u; }
                 }
                 if (leader) {
-                    const int key = y + 1;
-                    unsigned slot = ((unsigned)y * 2654435761u) >> shift;
-                    if (shift == 32) slot = 0;
-                    bool done = false;
-                    for (int probe = 0; probe < hsize; ++probe) {
-                        int cur = *(volatile int32_t *)&hk[slot];
-                        if (cur != key) {
-                            if (cur == 0) {
-                                cur = atomicCAS(&hk[slot], 0, key);
-                                if (cur == 0) { hn[slot] = 0.0; hd[slot] = 0.0; }
-                            }
-                            if (cur != 0 && cur != key) { slot = (slot + 1) & mask; continue; }
-                        }
-                        hn[slot] = __dadd_rn(hn[slot], an);
-                        hd[slot] = __dadd_rn(hd[slot], ad);
-                        done = true;
-                        break;
-                    }
-                    if (!done) atomicExch(a.error_flag, 2);
+                    const int slot = table_slot(hk, hn, hd, hsize, shift, y + 1);
+                    if (slot < 0) atomicExch(a.error_flag, 2);
+                    else { hn[slot] = __dadd_rn(hn[slot], an); hd[slot] = __dadd_rn(hd[slot], ad); }
                 }
                 __syncwarp();
             }
@@ -101,6 +110,40 @@ __global__ void __launch_bounds__(XS_THREADS) xsim_kernel(xmap_xsim_args a) {
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) combos += __shfl_xor_sync(0xffffffffu, combos, off);
+    if (lane == 0) a.unit_combos[x] = combos;
+}
+
+// One CTA per (dst, src) pair of a merge round: dst[y] += src[y] for every cell of src.
+// The rounds form a fixed binary tree over the slices of a heavy start, so the summation order of
+// every cell is a function of the path structure only.
+__global__ void __launch_bounds__(XS_THREADS) xsim_merge_kernel(xmap_xsim_args a, const int32_t *__restrict__ pair_dst,
+                                                                const int32_t *__restrict__ pair_src) {
+    const int d = pair_dst[blockIdx.x], sx = pair_src[blockIdx.x];
+    const int dsize = a.hash_size[d], ssize = a.hash_size[sx];
+    const int dshift = table_shift(dsize);
+    int32_t *dk = a.hash_key + a.hash_off[d];
+    double *dn = a.hash_num + a.hash_off[d], *dd = a.hash_den + a.hash_off[d];
+    const int32_t *sk = a.hash_key + a.hash_off[sx];
+    const double *sn = a.hash_num + a.hash_off[sx], *sd = a.hash_den + a.hash_off[sx];
+    for (int q = threadIdx.x; q < ssize; q += XS_THREADS) {
+        const int key = sk[q];
+        if (key == 0) continue;
+        const int slot = table_slot(dk, dn, dd, dsize, dshift, key);
+        if (slot < 0) { atomicExch(a.error_flag, 2); continue; }
+        dn[slot] = __dadd_rn(dn[slot], sn[q]);
+        dd[slot] = __dadd_rn(dd[slot], sd[q]);
+    }
+}
+
+// One warp per start: count the ends, pick the top-m, or emit every (end, xsim).
+__global__ void __launch_bounds__(XS_THREADS) xsim_finalize_kernel(xmap_xsim_args a) {
+    const int x = (blockIdx.x * XS_THREADS + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (x >= a.n_starts) return;
+    const int u = a.start_unit[x];                    // the unit whose table holds the merged result
+    const int hsize = a.hash_size[u];
+    const int32_t *hk = a.hash_key + a.hash_off[u];
+    const double *hn = a.hash_num + a.hash_off[u], *hd = a.hash_den + a.hash_off[u];
 
     if (a.mode == 2) {  // emit every (end, xsim) of this start
         int64_t base = a.emit_ptr[x];
@@ -124,7 +167,7 @@ __global__ void __launch_bounds__(XS_THREADS) xsim_kernel(xmap_xsim_args a) {
     for (int s = lane; s < hsize; s += 32) cnt += (hk[s] != 0);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
-    if (lane == 0) { a.out_count[x] = cnt; a.out_combos[x] = combos; }
+    if (lane == 0) a.out_count[x] = cnt;
     const int M = min(a.top_m, cnt);
     unsigned long long last_k = ~0ull;
     int last_t = -1;
@@ -157,13 +200,21 @@ using namespace xmap;
 
 extern "C" int xmap_xsim_extend(const xmap_xsim_args *args_h, void *stream_) {
     const xmap_xsim_args &a = *args_h;
-    if (a.n_starts <= 0) return 0;
+    if (a.n_starts <= 0 || a.n_units <= 0) return 0;
     if (a.top_m < 1 || a.top_m > XMAP_KMAX) return fail_msg("xmap_xsim_extend: top_m out of range");
     if (a.mode != 0 && a.mode != 2) return fail_msg("xmap_xsim_extend: bad mode");
     cudaStream_t st = (cudaStream_t)stream_;
-    const int warps_per_cta = XS_THREADS / 32;
-    const unsigned grid = (unsigned)((a.n_starts + warps_per_cta - 1) / warps_per_cta);
-    xsim_kernel<<<grid, XS_THREADS, 0, st>>>(a);
+    const int wpc = XS_THREADS / 32;
+    xsim_accum_kernel<<<(unsigned)((a.n_units + wpc - 1) / wpc), XS_THREADS, 0, st>>>(a);
+    XMAP_LAUNCH_CHECK();
+    for (int r = 0; r < a.n_rounds; ++r) {
+        const int lo = a.round_ptr_h[r], hi = a.round_ptr_h[r + 1];
+        if (hi > lo) {
+            xsim_merge_kernel<<<(unsigned)(hi - lo), XS_THREADS, 0, st>>>(a, a.pair_dst + lo, a.pair_src + lo);
+            XMAP_LAUNCH_CHECK();
+        }
+    }
+    xsim_finalize_kernel<<<(unsigned)((a.n_starts + wpc - 1) / wpc), XS_THREADS, 0, st>>>(a);
     XMAP_LAUNCH_CHECK();
     return 0;
 }

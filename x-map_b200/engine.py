@@ -14,8 +14,9 @@ import torch
 
 from . import _native as N
 
-CHUNK_PRODUCTS = 32768           # co-rating products per heavy-row chunk
-BIG_TABLE_BUDGET = 4 << 30       # bytes of HBM for heavy-row tables per batch
+RATER_GROUP = 128                # raters per unit of heavy-row work (matches sim.cu)
+BIG_TABLE_BUDGET = 8 << 30       # bytes of HBM for heavy-row tables per batch
+BIG_CAND_CAPACITY = 96 << 20     # candidate records (21 B each) per heavy-row batch
 
 
 def _stream_ptr():
@@ -161,7 +162,7 @@ class SimEngine:
         a.tab_mutu, a.tab_n, a.tab_len = N.ptr(self.tab_mutu), N.ptr(self.tab_n), N.ptr(self.tab_len)
         if emit is not None:
             a.emit_ptr, a.emit_j, a.emit_sim = N.ptr(emit["ptr"]), N.ptr(emit["j"]), N.ptr(emit["sim"])
-            a.emit_mutu, a.emit_n, a.emit_cursor = N.ptr(emit["mutu"]), N.ptr(emit["n"]), None
+            a.emit_mutu, a.emit_n, a.emit_cursor = N.ptr(emit["mutu"]), N.ptr(emit["n"]), N.ptr(emit["cursor"])
         a.error_flag = N.ptr(self.error_flag)
         return a
 
@@ -183,18 +184,40 @@ class SimEngine:
         big = rows[wr > N.TIER1_MAXWORK]
         return t0.contiguous(), t1.contiguous(), big.contiguous()
 
-    def _big_workspace(self, n_big):
+    def _big_batches(self, big):
+        """Cut the heavy rows (already sorted by descending work) into batches bounded by the
+        table budget and by the candidate-record capacity.  One host sync per plan."""
         I = self.lay.n_items
         per_row = I * 20 + 4
-        B = int(max(1, min(n_big, self.table_budget // per_row)))
+        b_max = int(max(1, self.table_budget // per_row))
+        w = self.lay.row_work[big.long()]
+        cap = torch.where(w * 8 >= I, torch.full_like(w, I), w).cpu().tolist()
+        batches, lo, acc = [], 0, 0
+        for q, c in enumerate(cap):
+            if q > lo and (q - lo >= b_max or acc + c > BIG_CAND_CAPACITY):
+                batches.append((lo, q, acc)); lo, acc = q, 0
+            acc += c
+        if len(cap) > lo:
+            batches.append((lo, len(cap), acc))
+        return batches, b_max
+
+    def _big_workspace(self, n_rows, capacity):
+        I = self.lay.n_items
+        L = N.lib()
         ws = self._big_ws
-        if ws is None or ws["B"] < B:
+        need = L.xmap_sim_big_scratch_bytes(n_rows, capacity)
+        if ws is None or ws["B"] < n_rows or ws["scratch"].numel() < need:
             dev = self.device
+            B = max(n_rows, ws["B"] if ws else 0)
+            need = max(need, ws["scratch"].numel() if ws else 0)
+            ws = None
+            self._big_ws = None
             ws = dict(B=B,
                       table=torch.zeros(B * I * 2, dtype=torch.int64, device=dev),
                       touched=torch.empty(B * I, dtype=torch.int32, device=dev),
                       touched_n=torch.zeros(B, dtype=torch.int32, device=dev),
-                      counter=torch.zeros(1, dtype=torch.int32, device=dev))
+                      counter=torch.zeros(1, dtype=torch.int32, device=dev),
+                      scratch=torch.empty(need, dtype=torch.uint8, device=dev))
             self._big_ws = ws
         return ws
 
@@ -208,41 +231,29 @@ class SimEngine:
             N.check(L.xmap_sim_rows_smem(args, N.ptr(t1), t1.numel(), 1, st), "xmap_sim_rows_smem[1]")
             self.launches += 1
         if big.numel():
-            ws = self._big_workspace(big.numel())
-            B = ws["B"]
             lay = self.lay
-            for s in range(0, big.numel(), B):
-                rows = big[s:s + B].contiguous()
+            batches, _ = self._big_batches(big)
+            ws = self._big_workspace(max(hi - lo for lo, hi, _ in batches), max(c for _, _, c in batches))
+            for lo_b, hi_b, capacity in batches:
+                rows = big[lo_b:hi_b].contiguous()
                 rl = rows.long()
-                lo = lay.csc_ptr[rl].long()
-                hi = lay.csc_ptr[rl + 1].long()
-                c = hi - lo
-                w = lay.row_work[rl]
-                nch = torch.clamp((w + CHUNK_PRODUCTS - 1) // CHUNK_PRODUCTS, min=1)
-                nch = torch.minimum(nch, c)
-                per = (c + nch - 1) // nch
-                nch = (c + per - 1) // per
-                slot = torch.repeat_interleave(torch.arange(rows.numel(), device=self.device), nch)
-                first = torch.cumsum(nch, 0) - nch
-                within = torch.arange(slot.numel(), device=self.device) - first[slot]
-                c_lo = lo[slot] + within * per[slot]
-                c_hi = torch.minimum(c_lo + per[slot], hi[slot])
-                chunk_slot = slot.to(torch.int32)
-                chunk_row = rows[slot]
-                c_lo32, c_hi32 = c_lo.to(torch.int32), c_hi.to(torch.int32)
+                c = (lay.csc_ptr[rl + 1] - lay.csc_ptr[rl]).long()
+                grp_off = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=self.device)
+                grp_off[1:] = torch.cumsum((c + RATER_GROUP - 1) // RATER_GROUP, 0)
                 ws["counter"].zero_()
                 N.check(L.xmap_sim_big_accumulate(
-                    args, N.ptr(chunk_slot), N.ptr(chunk_row), N.ptr(c_lo32), N.ptr(c_hi32),
-                    chunk_slot.numel(), N.ptr(ws["table"]), N.ptr(ws["touched"]),
-                    N.ptr(ws["touched_n"]), N.ptr(ws["counter"]), st), "xmap_sim_big_accumulate")
+                    args, N.ptr(rows), rows.numel(), N.ptr(grp_off), N.ptr(ws["table"]),
+                    N.ptr(ws["touched"]), N.ptr(ws["touched_n"]), N.ptr(ws["counter"]), st),
+                    "xmap_sim_big_accumulate")
                 N.check(L.xmap_sim_big_finalize(
                     args, N.ptr(rows), rows.numel(), N.ptr(ws["table"]), N.ptr(ws["touched"]),
-                    N.ptr(ws["touched_n"]), st), "xmap_sim_big_finalize")
-                self.launches += 2
+                    N.ptr(ws["touched_n"]), capacity, N.ptr(ws["scratch"]), ws["scratch"].numel(), st),
+                    "xmap_sim_big_finalize")
+                self.launches += 4
 
     def _check_error(self):
         if int(self.error_flag.item()) != 0:
-            raise N.NativeError("similarity kernel reported a hash-table overflow")
+            raise N.NativeError("similarity kernel error %d (1: hash overflow, 4: candidate capacity)" % int(self.error_flag.item()))
 
     # -- passes ------------------------------------------------------------
     def pass1(self, rows=None):
@@ -290,7 +301,8 @@ class SimEngine:
                     j=torch.empty(total, dtype=torch.int32, device=dev),
                     sim=torch.empty(total, dtype=torch.float64, device=dev),
                     mutu=torch.empty(total, dtype=torch.int32, device=dev),
-                    n=torch.empty(total, dtype=torch.int32, device=dev))
+                    n=torch.empty(total, dtype=torch.int32, device=dev),
+                    cursor=torch.zeros(I, dtype=torch.int32, device=dev))
         t0, t1, big = self.plan(rows)
         self._run_rows(self._args(2, emit=emit), t0, t1, big)
         self._check_error()

@@ -26,7 +26,8 @@ import torch
 
 from . import _native as N
 
-XSIM_HASH_BUDGET = 6 << 30      # bytes of per-start hash tables per launch
+XSIM_HASH_BUDGET = 48 << 30     # bytes of per-unit hash tables per launch
+XSIM_UNIT_COMBOS = 1 << 20      # a start with more paths than this is cut into leg slices
 
 
 def _excl_cumsum(x):
@@ -52,7 +53,8 @@ class XsimPlan:
     rs_ptr: torch.Tensor
     rs_end: torch.Tensor
     rs_vals: tuple               # e1, m1, f1, e2, m2, f2
-    ub: torch.Tensor             # per start: upper bound on combos
+    ub: torch.Tensor             # per start: combos (= reference paths) it will evaluate
+    ub_leg: torch.Tensor         # per leg
     n_src: int
     n_joint: int
     t_items: torch.Tensor        # bridge targets, indexed by leg_t / par_ptr
@@ -222,7 +224,7 @@ def build_plan(tabs, item_count, has_S, has_T):
         par_ptr=par_ptr, par_s=par_s.contiguous(), par_joint=joint.to(torch.uint8).contiguous(),
         par_vals=(src_e.contiguous(), src_m_.contiguous(), src_f.contiguous()),
         rs_ptr=rs_ptr, rs_end=rs_end, rs_vals=(rs_e1, rs_m1, rs_f1, rs_e2, rs_m2, rs_f2),
-        ub=ub, n_src=int(src_t.numel()), n_joint=int(joint.sum().item()) if joint.numel() else 0,
+        ub=ub, ub_leg=ub_leg, n_src=int(src_t.numel()), n_joint=int(joint.sum().item()) if joint.numel() else 0,
         t_items=t_items, s_items=s_items)
 
 
@@ -248,97 +250,159 @@ class XsimResult:
 
 
 class XsimEngine:
-    def __init__(self, plan, top_m=10, hash_budget=XSIM_HASH_BUDGET):
+    """Runs the extension kernels over an XsimPlan.
+
+    Work units: a start whose path count exceeds `unit_combos` is cut, at leg granularity, into
+    slices that run as independent warps with private hash tables; the slices are then merged by
+    a fixed binary tree (slice g absorbs g + 2^r in round r), so every cell's summation order is
+    a function of the path structure only -- results do not depend on launch batching."""
+
+    def __init__(self, plan, top_m=10, hash_budget=XSIM_HASH_BUDGET, unit_combos=XSIM_UNIT_COMBOS):
         if not (1 <= top_m <= N.KMAX):
             raise ValueError("top_m must be in [1, %d]" % N.KMAX)
         self.plan, self.top_m, self.hash_budget = plan, int(top_m), hash_budget
-        self.device = plan.start_item.device
-        self.launches = 0
         p = plan
-        # heaviest starts first; per-start hash size = pow2 >= 2 * min(ub, n_items), >= 32
+        dev = self.device = p.start_item.device
+        self.launches = 0
+        n = p.start_item.numel()
+        self.error_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        i64 = torch.int64
+        lc = p.leg_ptr[1:] - p.leg_ptr[:-1]
+        leg_start = _segment_ids(lc)
+        # slice id of a leg = (paths of the start before this leg) // unit_combos
+        before = torch.cumsum(p.ub_leg, 0) - p.ub_leg
+        start_base = torch.zeros(n, dtype=i64, device=dev)
+        if n:
+            start_base = before[p.leg_ptr[:-1].clamp(max=max(before.numel() - 1, 0))] if before.numel() else start_base
+        gid = (before - start_base[leg_start]) // int(unit_combos) if before.numel() else before
+        ukey = leg_start * (1 << 24) + gid
+        _, ucnt = torch.unique_consecutive(ukey, return_counts=True)
+        self.unit_leg_hi = torch.cumsum(ucnt, 0)
+        self.unit_leg_lo = self.unit_leg_hi - ucnt
+        self.unit_start = leg_start[self.unit_leg_lo] if ucnt.numel() else leg_start
+        n_units = int(ucnt.numel())
+        unit_ub = torch.zeros(n_units, dtype=i64, device=dev)
+        if n_units:
+            unit_ub.index_add_(0, _segment_ids(ucnt), p.ub_leg)
+        self.G = torch.bincount(self.unit_start, minlength=n) if n_units else torch.zeros(n, dtype=i64, device=dev)
+        self.u0 = torch.cumsum(self.G, 0) - self.G
+        g = torch.arange(n_units, device=dev) - self.u0[self.unit_start] if n_units else unit_ub
+        self.unit_g = g
+        # table of slice g must hold the union of its merge subtree [g, g + lowbit(g)) (all for g == 0)
+        lowbit = torch.where(g > 0, g & (-g), self.G[self.unit_start] if n_units else g)
+        hi = torch.minimum(g + lowbit, self.G[self.unit_start]) if n_units else g
+        P = torch.zeros(n_units + 1, dtype=i64, device=dev)
+        P[1:] = torch.cumsum(unit_ub, 0)
+        base_u = self.u0[self.unit_start] if n_units else g
+        sub_ub = P[base_u + hi] - P[base_u + g] if n_units else unit_ub
+        end_cap = int(torch.unique(p.rs_end).numel()) if p.rs_end.numel() else 1
+        self.hsize = torch.clamp(_pow2_at_least(2 * torch.clamp(sub_ub, max=end_cap)), min=32)
+        self.start_bytes = torch.zeros(n, dtype=i64, device=dev)
+        if n_units:
+            self.start_bytes.index_add_(0, self.unit_start, self.hsize * 20)
         self.order = torch.argsort(p.ub, descending=True, stable=True)
-        cap = torch.clamp(p.ub, max=p.n_items)
-        self.hsize = torch.clamp(_pow2_at_least(2 * cap), min=32)
-        self.error_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.n_units = n_units
+
+    # ------------------------------------------------------------------
+    def _batches(self):
+        order = self.order
+        if order.numel() == 0:
+            return
+        cum = torch.cumsum(self.start_bytes[order], 0).cpu()
+        lo, n = 0, order.numel()
+        while lo < n:
+            base = int(cum[lo - 1]) if lo else 0
+            hi = int(torch.searchsorted(cum, torch.tensor(base + self.hash_budget)))
+            hi = min(max(hi, lo + 1), n)
+            yield order[lo:hi]
+            lo = hi
 
     def _launch(self, sel, mode, out, emit=None):
-        """Run the kernel over the starts `sel` (indices into the plan)."""
+        """Run accumulate -> merge rounds -> finalize over the starts `sel` (plan indices)."""
         L = N.lib()
         p, dev = self.plan, self.device
-        n = int(sel.numel())
-        hs = self.hsize[sel]
+        ns = int(sel.numel())
+        G = self.G[sel]
+        units = torch.repeat_interleave(self.u0[sel], G) + \
+            (torch.arange(int(G.sum().item()), device=dev) - torch.repeat_interleave(torch.cumsum(G, 0) - G, G))
+        nu = int(units.numel())
+        first_unit = torch.cumsum(G, 0) - G                       # batch-local index of each start's slice 0
+        hs = self.hsize[units]
         hoff = torch.cumsum(hs, 0) - hs
         total = int(hs.sum().item())
         hkey = torch.zeros(total, dtype=torch.int32, device=dev)
         hnum = torch.empty(total, dtype=torch.float64, device=dev)
         hden = torch.empty(total, dtype=torch.float64, device=dev)
-        # gather this batch's leg lists into a compact CSR
-        lc = (p.leg_ptr[1:] - p.leg_ptr[:-1])[sel]
-        lptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
-        lptr[1:] = torch.cumsum(lc, 0)
-        seg = _segment_ids(lc)
-        li = p.leg_ptr[sel][seg] + (torch.arange(seg.numel(), device=dev) - lptr[:-1][seg])
+        # merge tree
+        g = self.unit_g[units]
+        Gu = torch.repeat_interleave(G, G)
+        loc = torch.arange(nu, device=dev)
+        rounds, pd, ps = [0], [], []
+        r, gmax = 0, int(G.max().item()) if ns else 1
+        while (1 << r) < gmax:
+            m = ((g % (1 << (r + 1))) == 0) & (g + (1 << r) < Gu)
+            d = loc[m]
+            pd.append(d); ps.append(d + (1 << r))
+            rounds.append(rounds[-1] + int(d.numel()))
+            r += 1
+        pair_dst = torch.cat(pd).to(torch.int32) if pd else torch.zeros(0, dtype=torch.int32, device=dev)
+        pair_src = torch.cat(ps).to(torch.int32) if ps else torch.zeros(0, dtype=torch.int32, device=dev)
+        import ctypes as C
+        round_ptr = (C.c_int32 * len(rounds))(*rounds)
         a = N.XsimArgs()
-        keep = []
+        keep = [round_ptr]
 
         def P(t):
             t = t.contiguous()
             keep.append(t)
             return N.ptr(t)
-        a.n_starts = n
-        a.start_item = P(p.start_item[sel])
-        a.leg_ptr = P(lptr); a.leg_t = P(p.leg_t[li]); a.leg_joint_only = P(p.leg_joint_only[li])
-        (a.leg_e1, a.leg_m1, a.leg_f1, a.leg_e2, a.leg_m2, a.leg_f2) = [P(v[li]) for v in p.leg_vals]
+        a.n_starts, a.n_units = ns, nu
+        a.start_item = P(p.start_item[sel]); a.start_unit = P(first_unit.to(torch.int32))
+        a.unit_leg_lo, a.unit_leg_hi = P(self.unit_leg_lo[units]), P(self.unit_leg_hi[units])
+        ucomb = torch.zeros(nu, dtype=torch.int64, device=dev)
+        a.unit_combos = P(ucomb)
+        a.leg_t, a.leg_joint_only = P(p.leg_t), P(p.leg_joint_only)
+        (a.leg_e1, a.leg_m1, a.leg_f1, a.leg_e2, a.leg_m2, a.leg_f2) = [P(v) for v in p.leg_vals]
         a.par_ptr = P(p.par_ptr); a.par_s = P(p.par_s); a.par_joint = P(p.par_joint)
         a.par_e, a.par_m, a.par_f = [P(v) for v in p.par_vals]
         a.rs_ptr = P(p.rs_ptr); a.rs_end = P(p.rs_end)
         (a.rs_e1, a.rs_m1, a.rs_f1, a.rs_e2, a.rs_m2, a.rs_f2) = [P(v) for v in p.rs_vals]
         a.hash_off = P(hoff); a.hash_size = P(hs.to(torch.int32))
         a.hash_key, a.hash_num, a.hash_den = P(hkey), P(hnum), P(hden)
+        a.n_rounds = len(rounds) - 1
+        a.round_ptr_h = C.cast(round_ptr, C.c_void_p)
+        a.pair_dst, a.pair_src = P(pair_dst), P(pair_src)
         a.top_m, a.mode = self.top_m, mode
-        cnt = torch.zeros(n, dtype=torch.int32, device=dev)
-        comb = torch.zeros(n, dtype=torch.int64, device=dev)
-        te = torch.full((n, self.top_m), -1, dtype=torch.int32, device=dev)
-        tx = torch.zeros((n, self.top_m), dtype=torch.float64, device=dev)
-        tl = torch.zeros(n, dtype=torch.int32, device=dev)
-        a.out_count, a.out_combos = P(cnt), P(comb)
+        cnt = torch.zeros(ns, dtype=torch.int32, device=dev)
+        te = torch.full((ns, self.top_m), -1, dtype=torch.int32, device=dev)
+        tx = torch.zeros((ns, self.top_m), dtype=torch.float64, device=dev)
+        tl = torch.zeros(ns, dtype=torch.int32, device=dev)
+        a.out_count = P(cnt)
         a.top_end, a.top_xsim, a.top_len = P(te), P(tx), P(tl)
         if emit is not None:
             a.emit_ptr, a.emit_end, a.emit_xsim = P(emit[0]), P(emit[1]), P(emit[2])
         a.error_flag = N.ptr(self.error_flag)
         N.check(L.xmap_xsim_extend(a, torch.cuda.current_stream().cuda_stream), "xmap_xsim_extend")
-        self.launches += 1
+        self.launches += 2 + a.n_rounds
         if mode == 0:
+            comb = torch.zeros(ns, dtype=torch.int64, device=dev)
+            comb.index_add_(0, torch.repeat_interleave(torch.arange(ns, device=dev), G), ucomb)
             out["count"][sel] = cnt; out["combos"][sel] = comb
             out["top_end"][sel] = te; out["top_xsim"][sel] = tx; out["top_len"][sel] = tl
         torch.cuda.current_stream().synchronize()      # the batch's temporaries die here
         if int(self.error_flag.item()):
-            raise N.NativeError("X-SIM kernel error %d (2: hash overflow, 3: bad table size)" % int(self.error_flag.item()))
+            raise N.NativeError("X-SIM kernel error %d (2: hash overflow, 3: bad table size)"
+                                % int(self.error_flag.item()))
 
-    def _batches(self, starts=None):
-        order = self.order if starts is None else starts
-        if order.numel() == 0:
-            return
-        bytes_per = self.hsize[order] * 20
-        cum = torch.cumsum(bytes_per, 0)
-        lo = 0
-        n = order.numel()
-        while lo < n:
-            base = int(cum[lo - 1].item()) if lo else 0
-            hi = int(torch.searchsorted(cum, torch.tensor(base + self.hash_budget, device=cum.device)).item())
-            hi = max(hi, lo + 1)
-            yield order[lo:hi]
-            lo = hi
-
-    def run(self, starts=None):
-        """count + top-m for the given starts (default: all).  `starts` are plan indices."""
+    def run(self):
+        """count + top-m for every start of the plan."""
         p, dev, n = self.plan, self.device, self.plan.start_item.numel()
         out = dict(count=torch.zeros(n, dtype=torch.int32, device=dev),
                    combos=torch.zeros(n, dtype=torch.int64, device=dev),
                    top_end=torch.full((n, self.top_m), -1, dtype=torch.int32, device=dev),
                    top_xsim=torch.zeros((n, self.top_m), dtype=torch.float64, device=dev),
                    top_len=torch.zeros(n, dtype=torch.int32, device=dev))
-        for sel in self._batches(starts):
+        for sel in self._batches():
             self._launch(sel, 0, out)
         return XsimResult(p.start_item, out["count"], out["combos"], out["top_end"], out["top_xsim"],
                           out["top_len"], self.launches)
