@@ -117,12 +117,19 @@ typedef struct xmap_sim_args {
     int32_t *error_flag;           /* device int, set nonzero on table overflow */
 } xmap_sim_args;
 
-/* Rows whose products fit a shared-memory hash: tier 0 needs row_work <=
- * XMAP_SIM_TIER0_MAXWORK, tier 1 <= XMAP_SIM_TIER1_MAXWORK.  One CTA per row. */
-#define XMAP_SIM_TIER0_MAXWORK 1400
-#define XMAP_SIM_TIER1_MAXWORK 5600
-int xmap_sim_rows_smem(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
-                       int32_t tier, void *stream);
+/* Rows whose products fit one hash table: ONE WARP per row, private table, no barriers.
+ *   tier 0: row_work <= 350   (512 slots, shared memory)
+ *   tier 1: row_work <= 700   (1024 slots, shared memory)
+ *   tier 2: row_work <= 1400  (2048 slots, shared memory)
+ *   tier 3: row_work <= 5600  (8192 slots in a per-warp slice of `workspace`, persistent warps)
+ * workspace >= xmap_sim_rows_workspace_bytes(tier) (0 for the shared-memory tiers). */
+#define XMAP_SIM_TIER0_MAXWORK 350
+#define XMAP_SIM_TIER1_MAXWORK 700
+#define XMAP_SIM_TIER2_MAXWORK 1400
+#define XMAP_SIM_TIER3_MAXWORK 5600
+size_t xmap_sim_rows_workspace_bytes(int32_t tier);
+int xmap_sim_rows(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows, int32_t tier,
+                  void *workspace, size_t workspace_bytes, void *stream);
 
 /* Heavy rows: each row is cut into chunks of raters; chunks accumulate into a
  * dense per-row table in HBM/L2 with 64-bit integer atomics (order-free, so

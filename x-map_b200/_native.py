@@ -12,8 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libxmap_b200.so")
 
 KMAX = 64
 METHODS = {"adjust_cosine": 0, "cosine": 1}
-TIER0_MAXWORK = 1400
-TIER1_MAXWORK = 5600
+TIER_MAXWORK = (350, 700, 1400, 5600)     # XMAP_SIM_TIER{0..3}_MAXWORK
 
 _p = C.c_void_p
 
@@ -59,7 +58,8 @@ _SIGS = {
     "xmap_build_layout": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int32, C.c_int32,
                                     _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "xmap_row_work": (C.c_int, [_p, _p, _p, C.c_int32, _p, _p]),
-    "xmap_sim_rows_smem": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, C.c_int32, _p]),
+    "xmap_sim_rows_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "xmap_sim_rows": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, C.c_int32, _p, C.c_size_t, _p]),
     "xmap_sim_big_accumulate": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, _p, _p, _p, _p, _p, _p]),
     "xmap_sim_big_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
     "xmap_sim_big_finalize": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, _p, _p, _p,

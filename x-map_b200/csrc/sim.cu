@@ -24,12 +24,6 @@ namespace xmap {
 
 constexpr int KMAX = XMAP_KMAX;
 
-#ifdef XMAP_PHASE_TIMING
-__device__ unsigned long long g_phase[8];
-#define PHASE_MARK(i) do { __syncthreads(); if (threadIdx.x == 0) { long long _t = clock64(); atomicAdd(&g_phase[i], (unsigned long long)(_t - _t0)); _t0 = _t; } } while (0)
-#else
-#define PHASE_MARK(i) do {} while (0)
-#endif
 
 // Candidate buffer of the per-row top-k selection.  A candidate belongs to exactly one of the
 // row's two lists; it is stored as a 128-bit sortable record:
@@ -47,6 +41,7 @@ struct Scratch {
     int c_mutu[CAP], c_n[CAP];
     int t_j[2][KMAX], t_mutu[2][KMAX], t_n[2][KMAX];
     int t_len[2];
+    int fin_len[2][THREADS / 32];
     int ncand, n0, n_pairs, n_kept, any_label;
 };
 
@@ -148,11 +143,19 @@ __device__ __forceinline__ void accumulate_raters(const xmap_sim_args &a, int ro
 }
 
 // --------------------------------------------------------------------------
-// Selection: sort the candidate buffer (plus the running tops) and keep the best K per list.
+// Selection: two-stage tournament over the candidate buffer (plus the running tops).
+//   stage 1  every warp takes a contiguous slice of the buffer, holds it in registers (up to
+//            PER_LANE records per lane) and extracts its own best K per list with K rounds of
+//            a register-local max + a 5-step warp arg-best; no shared-memory traffic, no barrier;
+//   stage 2  warp 0 (list 0) and warp 1 (list 1) pick the best K among the <= nwarps*K finalists.
+// K is small (10 by default, <= 64) against hundreds or thousands of candidates, so this is far
+// cheaper than sorting the buffer.
 // --------------------------------------------------------------------------
 template <int THREADS, int CAP>
 __device__ void select_lists(Scratch<THREADS, CAP> &S, int K) {
-    const int tid = threadIdx.x;
+    constexpr int NW = THREADS / 32;
+    constexpr int PER_LANE = CAP / THREADS;               // slice = PER_LANE * 32 records per warp
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n0t = S.t_len[0], n1t = S.t_len[1];
     const int nc = S.ncand;
     // running tops re-enter as candidates of their own list
@@ -169,47 +172,87 @@ __device__ void select_lists(Scratch<THREADS, CAP> &S, int K) {
         S.spay[p] = (v < 0.0 ? LIST0_BIT : 0ull) | ((unsigned long long)S.t_j[1][q] << 16) | (unsigned)p;
         S.c_mutu[p] = S.t_mutu[1][q]; S.c_n[p] = S.t_n[1][q];
     }
-    const int total = nc + n0t + n1t;
-    const int n0 = S.n0 + n0t;
-    int N = 32;
-    while (N < total) N <<= 1;
-    for (int p = total + tid; p < N; p += THREADS) { S.skey[p] = 0ull; S.spay[p] = 0ull; }
     __syncthreads();
-    for (int k = 2; k <= N; k <<= 1) {
-        for (int jj = k >> 1; jj > 0; jj >>= 1) {
-            for (int i = tid; i < N; i += THREADS) {
-                const int l = i ^ jj;
-                if (l > i) {
-                    const unsigned long long ka = S.skey[i], pa = S.spay[i], kb = S.skey[l], pb = S.spay[l];
-                    const bool desc = ((i & k) == 0);
-                    const bool swap = desc ? ranks_before(kb, pb, ka, pa) : ranks_before(ka, pa, kb, pb);
-                    if (swap) { S.skey[i] = kb; S.spay[i] = pb; S.skey[l] = ka; S.spay[l] = pa; }
+    const int total = nc + n0t + n1t;
+    // ---- stage 1: per-warp top-K of its slice, from registers --------------------------------
+    unsigned long long rk[PER_LANE], rp[PER_LANE];
+    const int base = warp * (PER_LANE * 32);
+#pragma unroll
+    for (int r = 0; r < PER_LANE; ++r) {
+        const int p = base + r * 32 + lane;
+        rk[r] = (p < total) ? S.skey[p] : 0ull;
+        rp[r] = (p < total) ? S.spay[p] : 0ull;
+    }
+    __syncthreads();                                        // everybody has its slice; reuse skey/spay
+    // finalists of warp w, list l live at skey[(l * NW + w) * K + r]   (needs 2*NW*K <= CAP)
+    for (int list = 0; list < 2; ++list) {
+        const unsigned long long want = (list == 0) ? LIST0_BIT : 0ull;
+        int got = 0;
+        for (int rr = 0; rr < K; ++rr) {
+            unsigned long long bk = 0ull, bpay = 0ull;
+            int bt = 0x7FFFFFFF, bp = -1;
+#pragma unroll
+            for (int r = 0; r < PER_LANE; ++r) {
+                const unsigned long long key = rk[r];
+                if (key == 0ull || (key & LIST0_BIT) != want) continue;
+                const int tt = pay_item(rp[r]);
+                if (bp < 0 || better(key, tt, bk, bt)) { bk = key; bt = tt; bp = r * 32 + lane; bpay = rp[r]; }
+            }
+            // arg-best across the warp, carrying the payload of the winner
+            unsigned long long k2 = bk; int t2 = bt, p2 = bp;
+            warp_argbest(k2, t2, p2);
+            if (p2 < 0) break;
+            const int owner = p2 & 31, slot = p2 >> 5;
+            const unsigned long long wpay = __shfl_sync(0xffffffffu, bpay, owner);
+            if (lane == owner) {
+#pragma unroll
+                for (int r = 0; r < PER_LANE; ++r) if (r == slot) rk[r] = 0ull;   // taken
+            }
+            if (lane == 0) {
+                const int f = (list * NW + warp) * K + rr;
+                S.skey[f] = k2; S.spay[f] = wpay;
+            }
+            got = rr + 1;
+        }
+        if (lane == 0) S.fin_len[list][warp] = got;
+    }
+    __syncthreads();
+    // ---- stage 2: best K among the finalists, one warp per list --------------------------------
+    if (warp < 2) {
+        const int list = warp;
+        int got = 0;
+        unsigned long long last_k = ~0ull; int last_t = -1;
+        for (int rr = 0; rr < K; ++rr) {
+            unsigned long long bk = 0ull; int bt = 0x7FFFFFFF, bp = -1;
+            for (int w = 0; w < NW; ++w) {
+                const int fl = S.fin_len[list][w];
+                for (int r = lane; r < fl; r += 32) {
+                    const int f = (list * NW + w) * K + r;
+                    const unsigned long long key = S.skey[f];
+                    const int tt = pay_item(S.spay[f]);
+                    if (rr > 0 && !better(last_k, last_t, key, tt)) continue;   // already taken
+                    if (bp < 0 || better(key, tt, bk, bt)) { bk = key; bt = tt; bp = f; }
                 }
             }
-            __syncthreads();
+            warp_argbest(bk, bt, bp);
+            if (bp < 0) break;
+            if (lane == 0) {
+                const unsigned long long pay = S.spay[bp];
+                const double mag = __longlong_as_double((long long)(bk & ABS_MASK));
+                const int pos = int(pay & 0xFFFFull);
+                S.t_sim[list][rr] = (pay & LIST0_BIT) ? -mag : mag;
+                S.t_j[list][rr] = bt; S.t_mutu[list][rr] = S.c_mutu[pos]; S.t_n[list][rr] = S.c_n[pos];
+            }
+            last_k = bk; last_t = bt;
+            got = rr + 1;
+        }
+        if (lane == 0) {
+            S.t_len[list] = got;
+            S.thr[list] = (got == K) ? (last_k & ABS_MASK) : 0ull;
         }
     }
-    const int L0 = min(K, n0), L1 = min(K, total - n0);
-    int src = -1, lst = 0, dst = 0;
-    if (tid < L0) { src = tid; lst = 0; dst = tid; }
-    else if (tid >= KMAX && tid < KMAX + L1) { src = n0 + (tid - KMAX); lst = 1; dst = tid - KMAX; }
-    double w_sim = 0.0; int w_j = 0, w_m = 0, w_n = 0;
-    if (src >= 0) {
-        const unsigned long long key = S.skey[src], pay = S.spay[src];
-        const double mag = __longlong_as_double((long long)(key & ABS_MASK));
-        w_sim = (pay & LIST0_BIT) ? -mag : mag;
-        w_j = pay_item(pay);
-        const int pos = int(pay & 0xFFFFull);
-        w_m = S.c_mutu[pos]; w_n = S.c_n[pos];
-    }
     __syncthreads();
-    if (src >= 0) { S.t_sim[lst][dst] = w_sim; S.t_j[lst][dst] = w_j; S.t_mutu[lst][dst] = w_m; S.t_n[lst][dst] = w_n; }
-    if (tid == 0) {
-        S.t_len[0] = L0; S.t_len[1] = L1;
-        S.thr[0] = (L0 == K) ? (S.skey[K - 1] & ABS_MASK) : 0ull;
-        S.thr[1] = (L1 == K) ? (S.skey[n0 + K - 1] & ABS_MASK) : 0ull;
-        S.ncand = 0; S.n0 = 0;
-    }
+    if (tid == 0) { S.ncand = 0; S.n0 = 0; }
     __syncthreads();
 }
 
@@ -314,124 +357,316 @@ __device__ void finalize_row(const xmap_sim_args &a, const RowCtx &c, int n_entr
 }
 
 // --------------------------------------------------------------------------
-// Tier 0 / 1: one CTA per row, accumulators in a shared-memory hash table.
+// Warp tiers: every row whose products fit one hash table is owned by ONE WARP.
+//   - private open-addressing table (key, n<<16|mutu, 64-bit fixed-point inner product);
+//   - plain read-modify-write: within one rater's CSR row all columns are distinct, so lanes never
+//     collide on a value; only the insertion of a new key uses a compare-and-swap;
+//   - no CTA-wide barrier anywhere: rows are independent, tens of them are in flight per SM;
+//   - epilogue (similarity, filter, label), BB detection and both top-k lists in the same warp.
+// Table placement: shared memory for 512 / 1024 / 2048 slots (row_work <= 350 / 700 / 1400),
+// a per-warp slice of a global workspace (L2) for 8192 slots (row_work <= 5600), where warps are
+// persistent and fetch rows from a counter.
 // --------------------------------------------------------------------------
-template <int LOG2_SLOTS, int THREADS>
-__global__ void __launch_bounds__(THREADS) sim_hash_kernel(xmap_sim_args a, const int32_t *__restrict__ rows,
-                                                            int n_rows) {
-    constexpr int SLOTS = 1 << LOG2_SLOTS;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // per slot: key (item+1, label in bit 31 after the epilogue), packed counts n<<16|mutu, and the
-    // 64-bit fixed-point inner product split in two 32-bit words (native 32-bit shared atomics;
-    // a 64-bit shared atomicAdd compiles to a compare-and-swap spin loop).
-    unsigned *h_lo = reinterpret_cast<unsigned *>(smem_raw);
-    unsigned *h_hi = h_lo + SLOTS;
-    unsigned *h_key = h_hi + SLOTS;
-    unsigned *h_cnt = h_key + SLOTS;
-    using ScratchT = Scratch<THREADS, 4 * THREADS>;
-    ScratchT &S = *reinterpret_cast<ScratchT *>(h_cnt + SLOTS);
+struct WarpTab {
+    unsigned long long *inner;   // fixed-point inner product, then the similarity bits (0 = filtered)
+    unsigned *key;               // item + 1 (label in bit 31 after the epilogue)
+    unsigned *cnt;               // n << 16 | mutu
+    unsigned short *ent;         // compacted occupied slots
+    signed char *lst;            // list of the candidate, -1 = none / taken
+};
 
-#ifdef XMAP_PHASE_TIMING
-    long long _t0 = clock64();
-#endif
-    const int tid = threadIdx.x;
-    const int row = rows[blockIdx.x];
+__host__ __device__ constexpr size_t warp_tab_bytes(int slots) { return (((size_t)slots * (8 + 4 + 4 + 2 + 1) + 15) / 16) * 16; }
+
+__device__ __forceinline__ WarpTab carve_tab(unsigned char *base, int slots) {
+    WarpTab T;
+    T.inner = reinterpret_cast<unsigned long long *>(base);
+    T.key = reinterpret_cast<unsigned *>(T.inner + slots);
+    T.cnt = T.key + slots;
+    T.ent = reinterpret_cast<unsigned short *>(T.cnt + slots);
+    T.lst = reinterpret_cast<signed char *>(T.ent + slots);
+    return T;
+}
+
+constexpr int SEL_BINS = 256;
+constexpr int SEL_BUF = 192;                 // survivors buffer (aliases the histogram): 192 * 12 B
+constexpr int SEL_BYTES = SEL_BUF * 12;      // >= SEL_BINS * 4
+
+// 16 sub-bins per octave for |sim| in [2^-16, 2): bits 62..48 of the double, offset so that
+// 2^-16 maps to bin 0; smaller values share bin 0, values >= 1 clamp to the top bin.
+__device__ __forceinline__ int sim_bin(unsigned long long key_bits) {
+    const int hi = int((key_bits & 0x7FFFFFFFFFFFFFFFull) >> 48);       // 11 exponent bits + 4 mantissa bits
+    const int base = (1023 - 16) << 4;
+    return max(0, min(SEL_BINS - 1, hi - base));
+}
+
+template <int LOG2_SLOTS>
+__device__ void warp_row(const xmap_sim_args &a, const WarpTab &T, unsigned char *sel, int row) {
+    const int lane = threadIdx.x & 31;
     const RowCtx c = make_ctx(a, row);
     const int lo = a.csc_ptr[row], hi = a.csc_ptr[row + 1];
-    long long w = a.row_work[row];
-    int log2n = 6;
+    const long long w = a.row_work[row];
+    int log2n = 5;
     while (log2n < LOG2_SLOTS && (1LL << log2n) < 2 * w) ++log2n;
     const int nslots = 1 << log2n;
     const unsigned mask = nslots - 1;
     const int shift = 32 - log2n;
-    for (int s = tid; s < nslots; s += THREADS) { h_key[s] = 0u; h_cnt[s] = 0u; h_lo[s] = 0u; h_hi[s] = 0u; }
-    __syncthreads();
-    PHASE_MARK(0);
+    for (int s = lane; s < nslots; s += 32) { T.key[s] = 0u; T.cnt[s] = 0u; T.inner[s] = 0ull; }
+    __syncwarp();
 
     auto add = [&](bool valid, int j, unsigned agree, long long fx) {
-        if (!valid) return;
-        const unsigned key = (unsigned)j + 1u;
-        unsigned slot = ((unsigned)j * 2654435761u) >> shift;
-        for (int probe = 0; probe < nslots; ++probe) {
-            unsigned cur = *(volatile unsigned *)&h_key[slot];
-            if (cur != key) {
-                if (cur == 0u) cur = atomicCAS(&h_key[slot], 0u, key);
-                if (cur != 0u && cur != key) { slot = (slot + 1) & mask; continue; }
+        if (valid) {
+            const unsigned key = (unsigned)j + 1u;
+            unsigned slot = ((unsigned)j * 2654435761u) >> shift;
+            bool ok = false;
+            for (int probe = 0; probe < nslots; ++probe) {
+                unsigned cur = *(volatile unsigned *)&T.key[slot];
+                if (cur != key) {
+                    if (cur == 0u) cur = atomicCAS(&T.key[slot], 0u, key);
+                    if (cur != 0u && cur != key) { slot = (slot + 1) & mask; continue; }
+                }
+                ok = true;
+                break;
             }
-            atomicAdd(&h_cnt[slot], (1u << 16) | agree);
-            const unsigned lo32 = (unsigned)(unsigned long long)fx, hi32 = (unsigned)((unsigned long long)fx >> 32);
-            const unsigned old = atomicAdd(&h_lo[slot], lo32);
-            const unsigned carry = (old + lo32 < old) ? 1u : 0u;
-            if (hi32 + carry) atomicAdd(&h_hi[slot], hi32 + carry);
-            return;
+            if (ok) {
+                T.cnt[slot] += (1u << 16) | agree;
+                T.inner[slot] += (unsigned long long)fx;
+            } else {
+                atomicExch(a.error_flag, 1);
+            }
         }
-        atomicExch(a.error_flag, 1);
+        __syncwarp();
     };
-    accumulate_raters(a, row, c.cls_i, lo, hi, tid >> 5, THREADS >> 5, add);
-    __syncthreads();
-    PHASE_MARK(1);
+    accumulate_raters(a, row, c.cls_i, lo, hi, 0, 1, add);
 
-    // ---- compaction of the occupied slots (so the epilogue runs at full lane utilisation) ----
-    unsigned short *ent = reinterpret_cast<unsigned short *>(&S + 1);
-    __shared__ int s_nent, s_kept, s_label;
-    if (tid == 0) { s_nent = 0; s_kept = 0; s_label = 0; }
-    __syncthreads();
-    for (int base = 0; base < nslots; base += THREADS) {
-        const int e = base + tid;
-        const bool occ = (e < nslots) && (h_key[e] != 0u);
+    // compaction of the occupied slots
+    int n_ent = 0;
+    for (int s0 = 0; s0 < nslots; s0 += 32) {
+        const int s = s0 + lane;
+        const bool occ = T.key[s] != 0u;
         const unsigned m = __ballot_sync(0xffffffffu, occ);
-        if (m) {
-            int pos = 0;
-            const int leader = __ffs(m) - 1;
-            if ((tid & 31) == leader) pos = atomicAdd(&s_nent, __popc(m));
-            pos = __shfl_sync(0xffffffffu, pos, leader);
-            if (occ) ent[pos + __popc(m & ((1u << (tid & 31)) - 1u))] = (unsigned short)e;
-        }
+        if (occ) T.ent[n_ent + __popc(m & ((1u << lane) - 1u))] = (unsigned short)s;
+        n_ent += __popc(m);
     }
-    __syncthreads();
-    const int n_ent = s_nent;
-    PHASE_MARK(2);
-    // ---- one evaluation per pair; the similarity replaces the accumulator in place ----
-    {
-        int lk = 0, ll = 0;
-        for (int q = tid; q < n_ent; q += THREADS) {
-            const int e = ent[q];
-            const unsigned key = h_key[e];
-            const unsigned cn = h_cnt[e];
-            double sim; int label;
-            const long long fx = (long long)(((unsigned long long)h_hi[e] << 32) | h_lo[e]);
-            const bool keep = eval_pair(a, c, int(key - 1u), int(cn >> 16), int(cn & 0xFFFFu), fx, sim, label);
-            const unsigned long long sb = keep ? (unsigned long long)__double_as_longlong(sim) : 0ull;
-            h_lo[e] = (unsigned)sb; h_hi[e] = (unsigned)(sb >> 32);
-            h_key[e] = key | (label ? 0x80000000u : 0u);
-            if (keep) { ++lk; ll |= label; }
-        }
+    __syncwarp();
+    // one evaluation per pair; the similarity replaces the accumulator in place
+    int lk = 0, ll = 0;
+    for (int q = lane; q < n_ent; q += 32) {
+        const int e = T.ent[q];
+        const unsigned key = T.key[e], cn = T.cnt[e];
+        double sim; int label;
+        const bool keep = eval_pair(a, c, int(key - 1u), int(cn >> 16), int(cn & 0xFFFFu), (long long)T.inner[e],
+                                    sim, label);
+        T.inner[e] = keep ? (unsigned long long)__double_as_longlong(sim) : 0ull;
+        T.key[e] = key | (label ? 0x80000000u : 0u);
+        if (keep) { ++lk; ll |= label; }
+    }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            lk += __shfl_xor_sync(0xffffffffu, lk, off);
-            ll |= __shfl_xor_sync(0xffffffffu, ll, off);
-        }
-        if ((tid & 31) == 0) {
-            if (lk) atomicAdd(&s_kept, lk);
-            if (ll) atomicOr(&s_label, 1);
-        }
+    for (int off = 16; off > 0; off >>= 1) {
+        lk += __shfl_xor_sync(0xffffffffu, lk, off);
+        ll |= __shfl_xor_sync(0xffffffffu, ll, off);
     }
-    __syncthreads();
-    PHASE_MARK(3);
-    auto get = [&](int q, int &j, int &n, int &mutu, double &sim, int &label, bool) -> int {
-        const int e = ent[q];
-        const unsigned long long sb = ((unsigned long long)h_hi[e] << 32) | h_lo[e];
-        if (sb == 0ull) return 1;
-        sim = __longlong_as_double((long long)sb);
-        const unsigned key = h_key[e];
-        j = int((key & 0x7FFFFFFFu) - 1u);
-        label = int(key >> 31);
-        const unsigned cn = h_cnt[e];
-        n = int(cn >> 16); mutu = int(cn & 0xFFFFu);
-        return 2;
-    };
-    finalize_row<THREADS, 4 * THREADS>(a, c, n_ent, get, S, PreCounts{1, n_ent, s_kept, s_label});
-    PHASE_MARK(4);
+    __syncwarp();
+
+    if (a.mode == 2) {  // emit every kept pair (materialised sim RDD, assist.py:75-77)
+        const int64_t base = a.emit_ptr[row];
+        int written = 0;
+        for (int q0 = 0; q0 < n_ent; q0 += 32) {
+            const int q = q0 + lane;
+            unsigned long long sb = 0ull;
+            int e = 0;
+            if (q < n_ent) { e = T.ent[q]; sb = T.inner[e]; }
+            const unsigned m = __ballot_sync(0xffffffffu, sb != 0ull);
+            if (sb != 0ull) {
+                const int64_t o = base + written + __popc(m & ((1u << lane) - 1u));
+                const unsigned cn = T.cnt[e];
+                a.emit_j[o] = int((T.key[e] & 0x7FFFFFFFu) - 1u);
+                a.emit_sim[o] = __longlong_as_double((long long)sb);
+                a.emit_mutu[o] = int(cn & 0xFFFFu); a.emit_n[o] = int(cn >> 16);
+            }
+            written += __popc(m);
+        }
+        __syncwarp();
+        return;
+    }
+    const bool bb = (a.mode == 0) && (ll != 0);          // bridge item: a kept cross-domain pair (assist.py:84-86)
+    if (a.mode == 0 && lane == 0) {
+        a.row_flags[row] = bb ? 1 : 0;
+        a.row_npairs[row] = n_ent;
+        a.row_nkept[row] = lk;
+    }
+    // list of every kept candidate (extender.py:30-43)
+    for (int q = lane; q < n_ent; q += 32) {
+        const int e = T.ent[q];
+        int lst = -1;
+        if (T.inner[e] != 0ull) {
+            const int j = int((T.key[e] & 0x7FFFFFFFu) - 1u);
+            if (a.mode == 1) lst = (a.bb_in[j] != 0) ? 0 : -1;
+            else if (bb) lst = ((a.contains[j] >> c.dom_i) & 1) ? 1 : 0;
+            else lst = 1;
+        }
+        T.lst[e] = (signed char)lst;
+    }
+    __syncwarp();
+    // ---- top-K per list: histogram threshold, then K rounds over the few survivors ----
+    // bin(|sim|) = 16 sub-bins per octave over [2^-16, 1]; everything smaller shares bin 0.
+    const int K = a.k;
+    for (int list = 0; list < 2; ++list) {
+        if (list == 1 && a.mode != 0) continue;           // pass 2 only writes slot 0
+        const bool use = (list == 0) ? ((a.mode == 1) || bb) : true;
+        int got = 0;
+        const size_t o = ((size_t)row * 2 + list) * K;
+        if (use) {
+            unsigned *hist = reinterpret_cast<unsigned *>(sel);
+            for (int b = lane; b < SEL_BINS; b += 32) hist[b] = 0u;
+            __syncwarp();
+            int n_list = 0;
+            for (int q = lane; q < n_ent; q += 32) {
+                const int e = T.ent[q];
+                if (T.lst[e] != list) continue;
+                atomicAdd(&hist[sim_bin(T.inner[e])], 1u);
+                ++n_list;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) n_list += __shfl_xor_sync(0xffffffffu, n_list, off);
+            __syncwarp();
+            // smallest bin b* such that #(bin >= b*) >= min(K, n_list): scan from the top
+            const int want = min(K, n_list);
+            int bstar = 0, above = 0;                      // `above` = #(bin > b*)
+            {
+                int run = 0;
+                bool found = false;
+                for (int hi = SEL_BINS - 32; hi >= 0 && !found; hi -= 32) {
+                    const unsigned v = hist[hi + lane];
+                    // suffix sums within the 32 bins, highest lane = highest bin
+                    unsigned suf = v;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const unsigned t = __shfl_down_sync(0xffffffffu, suf, off);
+                        if (lane + off < 32) suf += t;
+                    }
+                    const unsigned hit = __ballot_sync(0xffffffffu, run + (int)suf >= want);
+                    if (hit && want > 0) {
+                        const int l = 31 - __clz(hit);        // highest lane (bin) reaching `want`
+                        bstar = hi + l;
+                        const int suf_l = __shfl_sync(0xffffffffu, (int)suf, l);
+                        const int v_l = __shfl_sync(0xffffffffu, (int)v, l);
+                        above = run + suf_l - v_l;
+                        found = true;
+                    } else {
+                        run += (int)__shfl_sync(0xffffffffu, suf, 0);
+                    }
+                }
+            }
+            __syncwarp();
+            // survivors: every candidate above b* plus the candidates inside b*
+            unsigned long long *bkey = reinterpret_cast<unsigned long long *>(sel);
+            int *bent = reinterpret_cast<int *>(bkey + SEL_BUF);
+            int nb = 0;                                    // warp-uniform
+            bool overflow = false;
+            for (int q0 = 0; q0 < n_ent && want > 0; q0 += 32) {
+                const int q = q0 + lane;
+                bool take = false;
+                int e = 0;
+                unsigned long long key = 0ull;
+                if (q < n_ent) {
+                    e = T.ent[q];
+                    if (T.lst[e] == list) {
+                        key = T.inner[e] & 0x7FFFFFFFFFFFFFFFull;
+                        take = sim_bin(key) >= bstar;
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, take);
+                if (nb + __popc(m) > SEL_BUF) { overflow = true; break; }
+                if (take) {
+                    const int pos = nb + __popc(m & ((1u << lane) - 1u));
+                    bkey[pos] = key; bent[pos] = e;
+                }
+                nb += __popc(m);
+            }
+            __syncwarp();
+            (void)above;
+            if (!overflow) {
+                unsigned long long last_k = ~0ull; int last_t = -1;
+                for (int rr = 0; rr < want; ++rr) {
+                    unsigned long long bk = 0; int bt = 0x7FFFFFFF, bp = -1;
+                    for (int q = lane; q < nb; q += 32) {
+                        const unsigned long long kk = bkey[q];
+                        const int e = bent[q];
+                        const int tt = int((T.key[e] & 0x7FFFFFFFu) - 1u);
+                        if (rr > 0 && !better(last_k, last_t, kk, tt)) continue;
+                        if (bp < 0 || better(kk, tt, bk, bt)) { bk = kk; bt = tt; bp = e; }
+                    }
+                    warp_argbest(bk, bt, bp);
+                    if (bp < 0) break;
+                    if (lane == 0) {
+                        const unsigned cn = T.cnt[bp];
+                        a.tab_idx[o + rr] = bt;
+                        a.tab_sim[o + rr] = __longlong_as_double((long long)T.inner[bp]);
+                        a.tab_mutu[o + rr] = int(cn & 0xFFFFu); a.tab_n[o + rr] = int(cn >> 16);
+                    }
+                    last_k = bk; last_t = bt;
+                    got = rr + 1;
+                }
+            } else {
+                // many equal similarities in the threshold bin: plain K rounds over all entries
+                unsigned long long last_k = ~0ull; int last_t = -1;
+                for (int rr = 0; rr < want; ++rr) {
+                    unsigned long long bk = 0; int bt = 0x7FFFFFFF, bp = -1;
+                    for (int q = lane; q < n_ent; q += 32) {
+                        const int e = T.ent[q];
+                        if (T.lst[e] != list) continue;
+                        const unsigned long long kk = T.inner[e] & 0x7FFFFFFFFFFFFFFFull;
+                        const int tt = int((T.key[e] & 0x7FFFFFFFu) - 1u);
+                        if (rr > 0 && !better(last_k, last_t, kk, tt)) continue;
+                        if (bp < 0 || better(kk, tt, bk, bt)) { bk = kk; bt = tt; bp = e; }
+                    }
+                    warp_argbest(bk, bt, bp);
+                    if (bp < 0) break;
+                    if (lane == 0) {
+                        const unsigned cn = T.cnt[bp];
+                        a.tab_idx[o + rr] = bt;
+                        a.tab_sim[o + rr] = __longlong_as_double((long long)T.inner[bp]);
+                        a.tab_mutu[o + rr] = int(cn & 0xFFFFu); a.tab_n[o + rr] = int(cn >> 16);
+                    }
+                    last_k = bk; last_t = bt;
+                    got = rr + 1;
+                }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) a.tab_len[(size_t)row * 2 + list] = got;
+    }
+    __syncwarp();
+}
+
+// shared-memory tables: WARPS rows per CTA, rows assigned statically (sorted by descending work)
+template <int LOG2_SLOTS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) sim_warp_smem_kernel(xmap_sim_args a, const int32_t *__restrict__ rows,
+                                                                   int n_rows) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int r = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    unsigned char *mine = smem_raw + (threadIdx.x >> 5) * (warp_tab_bytes(1 << LOG2_SLOTS) + SEL_BYTES);
+    const WarpTab T = carve_tab(mine, 1 << LOG2_SLOTS);
+    warp_row<LOG2_SLOTS>(a, T, mine + warp_tab_bytes(1 << LOG2_SLOTS), rows[r]);
+}
+
+// global (L2) tables: persistent warps, rows fetched from a counter
+template <int LOG2_SLOTS>
+__global__ void __launch_bounds__(128) sim_warp_gmem_kernel(xmap_sim_args a, const int32_t *__restrict__ rows,
+                                                            int n_rows, unsigned char *__restrict__ workspace,
+                                                            int32_t *__restrict__ counter) {
+    __shared__ __align__(16) unsigned char s_sel[4][SEL_BYTES];
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const WarpTab T = carve_tab(workspace + (size_t)gw * warp_tab_bytes(1 << LOG2_SLOTS), 1 << LOG2_SLOTS);
+    while (true) {
+        int r = 0;
+        if (lane == 0) r = atomicAdd(counter, 1);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r >= n_rows) break;
+        warp_row<LOG2_SLOTS>(a, T, s_sel[threadIdx.x >> 5], rows[r]);
+    }
 }
 
 // --------------------------------------------------------------------------
@@ -721,15 +956,18 @@ static size_t big_scratch_layout(int n_rows, long long capacity, char *base, Big
     return off;
 }
 
-template <int LOG2_SLOTS, int THREADS>
-static int launch_hash(const xmap_sim_args &a, const int32_t *rows, int n_rows, cudaStream_t st) {
-    size_t smem = (size_t)(1 << LOG2_SLOTS) * 16 + sizeof(Scratch<THREADS, 4 * THREADS>) + (size_t)(1 << LOG2_SLOTS) * 2;
-    auto kern = sim_hash_kernel<LOG2_SLOTS, THREADS>;
+template <int LOG2_SLOTS, int WARPS>
+static int launch_warp_smem(const xmap_sim_args &a, const int32_t *rows, int n_rows, cudaStream_t st) {
+    const size_t smem = WARPS * (warp_tab_bytes(1 << LOG2_SLOTS) + SEL_BYTES);
+    auto kern = sim_warp_smem_kernel<LOG2_SLOTS, WARPS>;
     XMAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<n_rows, THREADS, smem, st>>>(a, rows, n_rows);
+    kern<<<(n_rows + WARPS - 1) / WARPS, WARPS * 32, smem, st>>>(a, rows, n_rows);
     XMAP_LAUNCH_CHECK();
     return 0;
 }
+
+constexpr int GMEM_LOG2_SLOTS = 13;
+constexpr int GMEM_CTAS_PER_SM = 12;      // x 4 warps = 48 persistent warps per SM
 
 static int check_args(const xmap_sim_args &a) {
     if (a.k < 1 || a.k > KMAX) return fail_msg("xmap_sim: k out of range [1, XMAP_KMAX]");
@@ -744,14 +982,35 @@ static int check_args(const xmap_sim_args &a) {
 
 using namespace xmap;
 
-extern "C" int xmap_sim_rows_smem(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
-                                  int32_t tier, void *stream_) {
+extern "C" size_t xmap_sim_rows_workspace_bytes(int32_t tier) {
+    if (tier != 3) return 0;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return (size_t)sms * GMEM_CTAS_PER_SM * 4 * warp_tab_bytes(1 << GMEM_LOG2_SLOTS) + 256;
+}
+
+extern "C" int xmap_sim_rows(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows, int32_t tier,
+                             void *workspace, size_t workspace_bytes, void *stream_) {
     if (int rc = check_args(*args_h)) return rc;
     if (n_rows <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream_;
-    if (tier == 0) return launch_hash<11, 256>(*args_h, rows, n_rows, st);
-    if (tier == 1) return launch_hash<13, 512>(*args_h, rows, n_rows, st);
-    return fail_msg("xmap_sim_rows_smem: bad tier");
+    if (tier == 0) return launch_warp_smem<9, 4>(*args_h, rows, n_rows, st);
+    if (tier == 1) return launch_warp_smem<10, 2>(*args_h, rows, n_rows, st);
+    if (tier == 2) return launch_warp_smem<11, 1>(*args_h, rows, n_rows, st);
+    if (tier == 3) {
+        if (workspace_bytes < xmap_sim_rows_workspace_bytes(3)) return fail_msg("xmap_sim_rows: workspace too small");
+        int dev = 0, sms = 148;
+        XMAP_CUDA(cudaGetDevice(&dev));
+        XMAP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        int32_t *counter = reinterpret_cast<int32_t *>(workspace);
+        XMAP_CUDA(cudaMemsetAsync(counter, 0, sizeof(int32_t), st));
+        sim_warp_gmem_kernel<GMEM_LOG2_SLOTS><<<sms * GMEM_CTAS_PER_SM, 128, 0, st>>>(
+            *args_h, rows, n_rows, reinterpret_cast<unsigned char *>(workspace) + 256, counter);
+        XMAP_LAUNCH_CHECK();
+        return 0;
+    }
+    return fail_msg("xmap_sim_rows: bad tier");
 }
 
 extern "C" int xmap_sim_big_accumulate(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
@@ -801,15 +1060,3 @@ extern "C" int xmap_sim_big_finalize(const xmap_sim_args *args_h, const int32_t 
     XMAP_LAUNCH_CHECK();
     return 0;
 }
-
-#ifdef XMAP_PHASE_TIMING
-extern "C" int xmap_debug_phase_cycles(unsigned long long *out_h, int reset) {
-    XMAP_CUDA(cudaDeviceSynchronize());
-    XMAP_CUDA(cudaMemcpyFromSymbol(out_h, xmap::g_phase, sizeof(unsigned long long) * 8));
-    if (reset) {
-        unsigned long long z[8] = {0};
-        XMAP_CUDA(cudaMemcpyToSymbol(xmap::g_phase, z, sizeof(z)));
-    }
-    return 0;
-}
-#endif

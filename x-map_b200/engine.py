@@ -144,6 +144,7 @@ class SimEngine:
         self.tab_n = torch.zeros((I, 2, k), dtype=torch.int32, device=dev)
         self.tab_len = torch.zeros((I, 2), dtype=torch.int32, device=dev)
         self._big_ws = None
+        self._tier_ws = None
 
     # -- argument block ----------------------------------------------------
     def _args(self, mode, bb_in=None, emit=None):
@@ -168,7 +169,7 @@ class SimEngine:
 
     # -- planning ----------------------------------------------------------
     def plan(self, rows=None):
-        """Split rows by cost: two shared-memory tiers and the heavy tier.
+        """Split rows by cost: four warp-per-row tiers (by table size) and the heavy tier.
         Each tier is ordered by descending work so long rows start first."""
         w = self.lay.row_work
         if rows is None:
@@ -178,11 +179,12 @@ class SimEngine:
         wr = w[rows.long()]
         order = torch.argsort(wr, descending=True, stable=True)
         rows, wr = rows[order], wr[order]
-        has = wr > 0
-        t0 = rows[has & (wr <= N.TIER0_MAXWORK)]
-        t1 = rows[(wr > N.TIER0_MAXWORK) & (wr <= N.TIER1_MAXWORK)]
-        big = rows[wr > N.TIER1_MAXWORK]
-        return t0.contiguous(), t1.contiguous(), big.contiguous()
+        tiers, lo = [], 0
+        for hi in N.TIER_MAXWORK:
+            tiers.append(rows[(wr > lo) & (wr <= hi)].contiguous())
+            lo = hi
+        big = rows[wr > lo].contiguous()
+        return tiers, big
 
     def _big_batches(self, big):
         """Cut the heavy rows (already sorted by descending work) into batches bounded by the
@@ -221,14 +223,20 @@ class SimEngine:
             self._big_ws = ws
         return ws
 
-    def _run_rows(self, args, t0, t1, big):
+    def _run_rows(self, args, tiers, big):
         L = N.lib()
         st = _stream_ptr()
-        if t0.numel():
-            N.check(L.xmap_sim_rows_smem(args, N.ptr(t0), t0.numel(), 0, st), "xmap_sim_rows_smem[0]")
-            self.launches += 1
-        if t1.numel():
-            N.check(L.xmap_sim_rows_smem(args, N.ptr(t1), t1.numel(), 1, st), "xmap_sim_rows_smem[1]")
+        for tier, rows in enumerate(tiers):
+            if not rows.numel():
+                continue
+            ws = None
+            need = L.xmap_sim_rows_workspace_bytes(tier)
+            if need:
+                if self._tier_ws is None or self._tier_ws.numel() < need:
+                    self._tier_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+                ws = self._tier_ws
+            N.check(L.xmap_sim_rows(args, N.ptr(rows), rows.numel(), tier, N.ptr(ws), need, st),
+                    "xmap_sim_rows[%d]" % tier)
             self.launches += 1
         if big.numel():
             lay = self.lay
@@ -258,9 +266,9 @@ class SimEngine:
     # -- passes ------------------------------------------------------------
     def pass1(self, rows=None):
         """Similarity rows + BB flags + (BB_BB, BB_NB) / NB_NN tables for `rows`."""
-        t0, t1, big = self.plan(rows)
-        self._run_rows(self._args(0), t0, t1, big)
-        return dict(tier0=int(t0.numel()), tier1=int(t1.numel()), big=int(big.numel()))
+        tiers, big = self.plan(rows)
+        self._run_rows(self._args(0), tiers, big)
+        return dict(tiers=[int(t.numel()) for t in tiers], big=int(big.numel()))
 
     def pass2(self, bb_all, rows=None):
         """NB_BB tables for the non-bridge rows among `rows` (needs every item's BB flag)."""
@@ -268,9 +276,9 @@ class SimEngine:
             rows = torch.arange(self.lay.n_items, dtype=torch.int32, device=self.device)
         rl = rows.long()
         nb = rows[(self.row_flags[rl] == 0) & (self.row_nkept[rl] > 0)]
-        t0, t1, big = self.plan(nb)
-        self._run_rows(self._args(1, bb_in=bb_all.to(torch.uint8).contiguous()), t0, t1, big)
-        return dict(tier0=int(t0.numel()), tier1=int(t1.numel()), big=int(big.numel()))
+        tiers, big = self.plan(nb)
+        self._run_rows(self._args(1, bb_in=bb_all.to(torch.uint8).contiguous()), tiers, big)
+        return dict(tiers=[int(t.numel()) for t in tiers], big=int(big.numel()))
 
     def run(self, rows=None):
         """Single-GPU convenience: pass 1, pass 2, error check."""
@@ -303,8 +311,8 @@ class SimEngine:
                     mutu=torch.empty(total, dtype=torch.int32, device=dev),
                     n=torch.empty(total, dtype=torch.int32, device=dev),
                     cursor=torch.zeros(I, dtype=torch.int32, device=dev))
-        t0, t1, big = self.plan(rows)
-        self._run_rows(self._args(2, emit=emit), t0, t1, big)
+        tiers, big = self.plan(rows)
+        self._run_rows(self._args(2, emit=emit), tiers, big)
         self._check_error()
         i = torch.repeat_interleave(torch.arange(I, device=dev), nk)
         key = i * I + emit["j"].long()
