@@ -145,6 +145,7 @@ class SimEngine:
         self.tab_len = torch.zeros((I, 2), dtype=torch.int32, device=dev)
         self._big_ws = None
         self._tier_ws = None
+        self.profile = None        # dict kind -> [(start_event, end_event)] when enabled
 
     # -- argument block ----------------------------------------------------
     def _args(self, mode, bb_in=None, emit=None):
@@ -223,6 +224,27 @@ class SimEngine:
             self._big_ws = ws
         return ws
 
+    def enable_profile(self):
+        """Record a CUDA event pair around every kernel group (read with profile_ms())."""
+        self.profile = {}
+
+    def _timed(self, kind, fn):
+        if self.profile is None:
+            return fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        self.profile.setdefault(kind, []).append((a, b))
+        return r
+
+    def profile_ms(self):
+        """{kind: (launch groups, total ms)}; synchronises."""
+        torch.cuda.synchronize()
+        out = {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (self.profile or {}).items()}
+        self.profile = {}
+        return out
+
     def _run_rows(self, args, tiers, big):
         L = N.lib()
         st = _stream_ptr()
@@ -235,8 +257,9 @@ class SimEngine:
                 if self._tier_ws is None or self._tier_ws.numel() < need:
                     self._tier_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
                 ws = self._tier_ws
-            N.check(L.xmap_sim_rows(args, N.ptr(rows), rows.numel(), tier, N.ptr(ws), need, st),
-                    "xmap_sim_rows[%d]" % tier)
+            self._timed("warp_tier%d" % tier, lambda: N.check(
+                L.xmap_sim_rows(args, N.ptr(rows), rows.numel(), tier, N.ptr(ws), need, st),
+                "xmap_sim_rows[%d]" % tier))
             self.launches += 1
         if big.numel():
             lay = self.lay
@@ -249,14 +272,14 @@ class SimEngine:
                 grp_off = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=self.device)
                 grp_off[1:] = torch.cumsum((c + RATER_GROUP - 1) // RATER_GROUP, 0)
                 ws["counter"].zero_()
-                N.check(L.xmap_sim_big_accumulate(
+                self._timed("big_accumulate", lambda: N.check(L.xmap_sim_big_accumulate(
                     args, N.ptr(rows), rows.numel(), N.ptr(grp_off), N.ptr(ws["table"]),
                     N.ptr(ws["touched"]), N.ptr(ws["touched_n"]), N.ptr(ws["counter"]), st),
-                    "xmap_sim_big_accumulate")
-                N.check(L.xmap_sim_big_finalize(
+                    "xmap_sim_big_accumulate"))
+                self._timed("big_epilogue", lambda: N.check(L.xmap_sim_big_finalize(
                     args, N.ptr(rows), rows.numel(), N.ptr(ws["table"]), N.ptr(ws["touched"]),
                     N.ptr(ws["touched_n"]), capacity, N.ptr(ws["scratch"]), ws["scratch"].numel(), st),
-                    "xmap_sim_big_finalize")
+                    "xmap_sim_big_finalize"))
                 self.launches += 4
 
     def _check_error(self):
