@@ -122,11 +122,13 @@ typedef struct xmap_sim_args {
  *   tier 1: row_work <= 700   (1024 slots, shared memory)
  *   tier 2: row_work <= 1400  (2048 slots, shared memory)
  *   tier 3: row_work <= 5600  (8192 slots in a per-warp slice of `workspace`, persistent warps)
+ *   tier 4: row_work <= 22000 (32768 slots, likewise)
  * workspace >= xmap_sim_rows_workspace_bytes(tier) (0 for the shared-memory tiers). */
 #define XMAP_SIM_TIER0_MAXWORK 350
 #define XMAP_SIM_TIER1_MAXWORK 700
 #define XMAP_SIM_TIER2_MAXWORK 1400
 #define XMAP_SIM_TIER3_MAXWORK 5600
+#define XMAP_SIM_TIER4_MAXWORK 22000
 size_t xmap_sim_rows_workspace_bytes(int32_t tier);
 int xmap_sim_rows(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows, int32_t tier,
                   void *workspace, size_t workspace_bytes, void *stream);

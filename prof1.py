@@ -20,10 +20,10 @@ empty = torch.zeros(0, dtype=torch.int32, device=dev)
 a0 = eng._args(0)
 for rep in range(2):
     ts = []
-    for i in range(4):
-        sel = [tiers[q] if q == i else empty for q in range(4)]
+    for i in range(len(tiers)):
+        sel = [tiers[q] if q == i else empty for q in range(len(tiers))]
         _, t = T(eng._run_rows, a0, sel, empty); ts.append(round(t,2))
-    _, tc = T(eng._run_rows, a0, [empty]*4, big)
+    _, tc = T(eng._run_rows, a0, [empty]*len(tiers), big)
     print("pass1 tiers ms", ts, "big %.2f ms" % tc)
 for rep in range(2):
     _, t1 = T(eng.pass1); _, t2 = T(eng.pass2, eng.row_flags)

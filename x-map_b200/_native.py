@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libxmap_b200.so")
 
 KMAX = 64
 METHODS = {"adjust_cosine": 0, "cosine": 1}
-TIER_MAXWORK = (350, 700, 1400, 5600)     # XMAP_SIM_TIER{0..3}_MAXWORK
+TIER_MAXWORK = (350, 700, 1400, 5600, 22000)     # XMAP_SIM_TIER{0..4}_MAXWORK
 
 _p = C.c_void_p
 

@@ -367,25 +367,18 @@ __device__ void finalize_row(const xmap_sim_args &a, const RowCtx &c, int n_entr
 // a per-warp slice of a global workspace (L2) for 8192 slots (row_work <= 5600), where warps are
 // persistent and fetch rows from a counter.
 // --------------------------------------------------------------------------
-struct WarpTab {
-    unsigned long long *inner;   // fixed-point inner product, then the similarity bits (0 = filtered)
-    unsigned *key;               // item + 1 (label in bit 31 after the epilogue)
-    unsigned *cnt;               // n << 16 | mutu
-    unsigned short *ent;         // compacted occupied slots
-    signed char *lst;            // list of the candidate, -1 = none / taken
+// One 16-byte slot per column: AoS so a global-memory table costs one 32-byte sector per product.
+//   accumulate phase : key = item + 1, cnt = n << 16 | mutu, inner = fixed-point inner product
+//   after compaction : the occupied slots sit contiguously at the front of the same array, and the
+//                      epilogue overwrites inner with the similarity bits (0 = filtered) and tags key
+//                      with the label (bit 31) and the candidate's list (bits 28-29: 0 none, 1, 2)
+struct __align__(16) Slot {
+    unsigned key, cnt;
+    unsigned long long inner;
 };
+constexpr unsigned SLOT_ITEM_MASK = 0x01FFFFFFu;     // item + 1 <= 2^24
 
-__host__ __device__ constexpr size_t warp_tab_bytes(int slots) { return (((size_t)slots * (8 + 4 + 4 + 2 + 1) + 15) / 16) * 16; }
-
-__device__ __forceinline__ WarpTab carve_tab(unsigned char *base, int slots) {
-    WarpTab T;
-    T.inner = reinterpret_cast<unsigned long long *>(base);
-    T.key = reinterpret_cast<unsigned *>(T.inner + slots);
-    T.cnt = T.key + slots;
-    T.ent = reinterpret_cast<unsigned short *>(T.cnt + slots);
-    T.lst = reinterpret_cast<signed char *>(T.ent + slots);
-    return T;
-}
+__host__ __device__ constexpr size_t warp_tab_bytes(int slots) { return (size_t)slots * sizeof(Slot); }
 
 constexpr int SEL_BINS = 256;
 constexpr int SEL_BUF = 192;                 // survivors buffer (aliases the histogram): 192 * 12 B
@@ -400,7 +393,7 @@ __device__ __forceinline__ int sim_bin(unsigned long long key_bits) {
 }
 
 template <int LOG2_SLOTS>
-__device__ void warp_row(const xmap_sim_args &a, const WarpTab &T, unsigned char *sel, int row) {
+__device__ void warp_row(const xmap_sim_args &a, Slot *__restrict__ S, unsigned char *sel, int row) {
     const int lane = threadIdx.x & 31;
     const RowCtx c = make_ctx(a, row);
     const int lo = a.csc_ptr[row], hi = a.csc_ptr[row + 1];
@@ -410,7 +403,7 @@ __device__ void warp_row(const xmap_sim_args &a, const WarpTab &T, unsigned char
     const int nslots = 1 << log2n;
     const unsigned mask = nslots - 1;
     const int shift = 32 - log2n;
-    for (int s = lane; s < nslots; s += 32) { T.key[s] = 0u; T.cnt[s] = 0u; T.inner[s] = 0ull; }
+    for (int s = lane; s < nslots; s += 32) S[s] = Slot{0u, 0u, 0ull};
     __syncwarp();
 
     auto add = [&](bool valid, int j, unsigned agree, long long fx) {
@@ -419,17 +412,17 @@ __device__ void warp_row(const xmap_sim_args &a, const WarpTab &T, unsigned char
             unsigned slot = ((unsigned)j * 2654435761u) >> shift;
             bool ok = false;
             for (int probe = 0; probe < nslots; ++probe) {
-                unsigned cur = *(volatile unsigned *)&T.key[slot];
+                unsigned cur = *(volatile unsigned *)&S[slot].key;
                 if (cur != key) {
-                    if (cur == 0u) cur = atomicCAS(&T.key[slot], 0u, key);
+                    if (cur == 0u) cur = atomicCAS(&S[slot].key, 0u, key);
                     if (cur != 0u && cur != key) { slot = (slot + 1) & mask; continue; }
                 }
                 ok = true;
                 break;
             }
             if (ok) {
-                T.cnt[slot] += (1u << 16) | agree;
-                T.inner[slot] += (unsigned long long)fx;
+                S[slot].cnt += (1u << 16) | agree;
+                S[slot].inner += (unsigned long long)fx;
             } else {
                 atomicExch(a.error_flag, 1);
             }
@@ -438,26 +431,28 @@ __device__ void warp_row(const xmap_sim_args &a, const WarpTab &T, unsigned char
     };
     accumulate_raters(a, row, c.cls_i, lo, hi, 0, 1, add);
 
-    // compaction of the occupied slots
+    // in-place compaction: a chunk of 32 slots is read into registers before anything is written,
+    // and the write positions never run ahead of the chunk being read
     int n_ent = 0;
     for (int s0 = 0; s0 < nslots; s0 += 32) {
-        const int s = s0 + lane;
-        const bool occ = T.key[s] != 0u;
+        const Slot v = S[s0 + lane];
+        const bool occ = v.key != 0u;
         const unsigned m = __ballot_sync(0xffffffffu, occ);
-        if (occ) T.ent[n_ent + __popc(m & ((1u << lane) - 1u))] = (unsigned short)s;
+        __syncwarp();
+        if (occ) S[n_ent + __popc(m & ((1u << lane) - 1u))] = v;
         n_ent += __popc(m);
+        __syncwarp();
     }
-    __syncwarp();
-    // one evaluation per pair; the similarity replaces the accumulator in place
+    // one evaluation per pair; the similarity replaces the accumulator
     int lk = 0, ll = 0;
     for (int q = lane; q < n_ent; q += 32) {
-        const int e = T.ent[q];
-        const unsigned key = T.key[e], cn = T.cnt[e];
+        Slot v = S[q];
         double sim; int label;
-        const bool keep = eval_pair(a, c, int(key - 1u), int(cn >> 16), int(cn & 0xFFFFu), (long long)T.inner[e],
+        const bool keep = eval_pair(a, c, int(v.key - 1u), int(v.cnt >> 16), int(v.cnt & 0xFFFFu), (long long)v.inner,
                                     sim, label);
-        T.inner[e] = keep ? (unsigned long long)__double_as_longlong(sim) : 0ull;
-        T.key[e] = key | (label ? 0x80000000u : 0u);
+        v.inner = keep ? (unsigned long long)__double_as_longlong(sim) : 0ull;
+        v.key |= (label ? 0x80000000u : 0u);
+        S[q] = v;
         if (keep) { ++lk; ll |= label; }
     }
 #pragma unroll
@@ -472,16 +467,14 @@ __device__ void warp_row(const xmap_sim_args &a, const WarpTab &T, unsigned char
         int written = 0;
         for (int q0 = 0; q0 < n_ent; q0 += 32) {
             const int q = q0 + lane;
-            unsigned long long sb = 0ull;
-            int e = 0;
-            if (q < n_ent) { e = T.ent[q]; sb = T.inner[e]; }
-            const unsigned m = __ballot_sync(0xffffffffu, sb != 0ull);
-            if (sb != 0ull) {
+            Slot v = Slot{0u, 0u, 0ull};
+            if (q < n_ent) v = S[q];
+            const unsigned m = __ballot_sync(0xffffffffu, v.inner != 0ull);
+            if (v.inner != 0ull) {
                 const int64_t o = base + written + __popc(m & ((1u << lane) - 1u));
-                const unsigned cn = T.cnt[e];
-                a.emit_j[o] = int((T.key[e] & 0x7FFFFFFFu) - 1u);
-                a.emit_sim[o] = __longlong_as_double((long long)sb);
-                a.emit_mutu[o] = int(cn & 0xFFFFu); a.emit_n[o] = int(cn >> 16);
+                a.emit_j[o] = int((v.key & SLOT_ITEM_MASK) - 1u);
+                a.emit_sim[o] = __longlong_as_double((long long)v.inner);
+                a.emit_mutu[o] = int(v.cnt & 0xFFFFu); a.emit_n[o] = int(v.cnt >> 16);
             }
             written += __popc(m);
         }
@@ -494,25 +487,25 @@ __device__ void warp_row(const xmap_sim_args &a, const WarpTab &T, unsigned char
         a.row_npairs[row] = n_ent;
         a.row_nkept[row] = lk;
     }
-    // list of every kept candidate (extender.py:30-43)
+    // list of every kept candidate (extender.py:30-43), tagged into the key
     for (int q = lane; q < n_ent; q += 32) {
-        const int e = T.ent[q];
-        int lst = -1;
-        if (T.inner[e] != 0ull) {
-            const int j = int((T.key[e] & 0x7FFFFFFFu) - 1u);
-            if (a.mode == 1) lst = (a.bb_in[j] != 0) ? 0 : -1;
-            else if (bb) lst = ((a.contains[j] >> c.dom_i) & 1) ? 1 : 0;
-            else lst = 1;
+        const Slot v = S[q];
+        unsigned tag = 0u;
+        if (v.inner != 0ull) {
+            const int j = int((v.key & SLOT_ITEM_MASK) - 1u);
+            if (a.mode == 1) tag = (a.bb_in[j] != 0) ? 1u : 0u;
+            else if (bb) tag = ((a.contains[j] >> c.dom_i) & 1) ? 2u : 1u;
+            else tag = 2u;
         }
-        T.lst[e] = (signed char)lst;
+        S[q].key = v.key | (tag << 28);
     }
     __syncwarp();
     // ---- top-K per list: histogram threshold, then K rounds over the few survivors ----
-    // bin(|sim|) = 16 sub-bins per octave over [2^-16, 1]; everything smaller shares bin 0.
     const int K = a.k;
     for (int list = 0; list < 2; ++list) {
         if (list == 1 && a.mode != 0) continue;           // pass 2 only writes slot 0
         const bool use = (list == 0) ? ((a.mode == 1) || bb) : true;
+        const unsigned tagv = (unsigned)(list + 1);
         int got = 0;
         const size_t o = ((size_t)row * 2 + list) * K;
         if (use) {
@@ -521,24 +514,23 @@ __device__ void warp_row(const xmap_sim_args &a, const WarpTab &T, unsigned char
             __syncwarp();
             int n_list = 0;
             for (int q = lane; q < n_ent; q += 32) {
-                const int e = T.ent[q];
-                if (T.lst[e] != list) continue;
-                atomicAdd(&hist[sim_bin(T.inner[e])], 1u);
+                const Slot v = S[q];
+                if (((v.key >> 28) & 3u) != tagv) continue;
+                atomicAdd(&hist[sim_bin(v.inner)], 1u);
                 ++n_list;
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) n_list += __shfl_xor_sync(0xffffffffu, n_list, off);
             __syncwarp();
-            // smallest bin b* such that #(bin >= b*) >= min(K, n_list): scan from the top
+            // largest bin b* such that #(bin >= b*) >= min(K, n_list): scan from the top
             const int want = min(K, n_list);
-            int bstar = 0, above = 0;                      // `above` = #(bin > b*)
+            int bstar = 0;
             {
                 int run = 0;
                 bool found = false;
-                for (int hi = SEL_BINS - 32; hi >= 0 && !found; hi -= 32) {
-                    const unsigned v = hist[hi + lane];
-                    // suffix sums within the 32 bins, highest lane = highest bin
-                    unsigned suf = v;
+                for (int hb = SEL_BINS - 32; hb >= 0 && !found; hb -= 32) {
+                    const unsigned v = hist[hb + lane];
+                    unsigned suf = v;                      // suffix sums, highest lane = highest bin
 #pragma unroll
                     for (int off = 1; off < 32; off <<= 1) {
                         const unsigned t = __shfl_down_sync(0xffffffffu, suf, off);
@@ -546,11 +538,7 @@ __device__ void warp_row(const xmap_sim_args &a, const WarpTab &T, unsigned char
                     }
                     const unsigned hit = __ballot_sync(0xffffffffu, run + (int)suf >= want);
                     if (hit && want > 0) {
-                        const int l = 31 - __clz(hit);        // highest lane (bin) reaching `want`
-                        bstar = hi + l;
-                        const int suf_l = __shfl_sync(0xffffffffu, (int)suf, l);
-                        const int v_l = __shfl_sync(0xffffffffu, (int)v, l);
-                        above = run + suf_l - v_l;
+                        bstar = hb + (31 - __clz(hit));
                         found = true;
                     } else {
                         run += (int)__shfl_sync(0xffffffffu, suf, 0);
@@ -558,7 +546,7 @@ __device__ void warp_row(const xmap_sim_args &a, const WarpTab &T, unsigned char
                 }
             }
             __syncwarp();
-            // survivors: every candidate above b* plus the candidates inside b*
+            // survivors: every candidate of the list whose bin is >= b*
             unsigned long long *bkey = reinterpret_cast<unsigned long long *>(sel);
             int *bent = reinterpret_cast<int *>(bkey + SEL_BUF);
             int nb = 0;                                    // warp-uniform
@@ -566,12 +554,11 @@ __device__ void warp_row(const xmap_sim_args &a, const WarpTab &T, unsigned char
             for (int q0 = 0; q0 < n_ent && want > 0; q0 += 32) {
                 const int q = q0 + lane;
                 bool take = false;
-                int e = 0;
                 unsigned long long key = 0ull;
                 if (q < n_ent) {
-                    e = T.ent[q];
-                    if (T.lst[e] == list) {
-                        key = T.inner[e] & 0x7FFFFFFFFFFFFFFFull;
+                    const Slot v = S[q];
+                    if (((v.key >> 28) & 3u) == tagv) {
+                        key = v.inner & 0x7FFFFFFFFFFFFFFFull;
                         take = sim_bin(key) >= bstar;
                     }
                 }
@@ -579,58 +566,42 @@ __device__ void warp_row(const xmap_sim_args &a, const WarpTab &T, unsigned char
                 if (nb + __popc(m) > SEL_BUF) { overflow = true; break; }
                 if (take) {
                     const int pos = nb + __popc(m & ((1u << lane) - 1u));
-                    bkey[pos] = key; bent[pos] = e;
+                    bkey[pos] = key; bent[pos] = q;
                 }
                 nb += __popc(m);
             }
             __syncwarp();
-            (void)above;
-            if (!overflow) {
-                unsigned long long last_k = ~0ull; int last_t = -1;
-                for (int rr = 0; rr < want; ++rr) {
-                    unsigned long long bk = 0; int bt = 0x7FFFFFFF, bp = -1;
+            unsigned long long last_k = ~0ull; int last_t = -1;
+            for (int rr = 0; rr < want; ++rr) {
+                unsigned long long bk = 0; int bt = 0x7FFFFFFF, bp = -1;
+                if (!overflow) {
                     for (int q = lane; q < nb; q += 32) {
                         const unsigned long long kk = bkey[q];
                         const int e = bent[q];
-                        const int tt = int((T.key[e] & 0x7FFFFFFFu) - 1u);
+                        const int tt = int((S[e].key & SLOT_ITEM_MASK) - 1u);
                         if (rr > 0 && !better(last_k, last_t, kk, tt)) continue;
                         if (bp < 0 || better(kk, tt, bk, bt)) { bk = kk; bt = tt; bp = e; }
                     }
-                    warp_argbest(bk, bt, bp);
-                    if (bp < 0) break;
-                    if (lane == 0) {
-                        const unsigned cn = T.cnt[bp];
-                        a.tab_idx[o + rr] = bt;
-                        a.tab_sim[o + rr] = __longlong_as_double((long long)T.inner[bp]);
-                        a.tab_mutu[o + rr] = int(cn & 0xFFFFu); a.tab_n[o + rr] = int(cn >> 16);
-                    }
-                    last_k = bk; last_t = bt;
-                    got = rr + 1;
-                }
-            } else {
-                // many equal similarities in the threshold bin: plain K rounds over all entries
-                unsigned long long last_k = ~0ull; int last_t = -1;
-                for (int rr = 0; rr < want; ++rr) {
-                    unsigned long long bk = 0; int bt = 0x7FFFFFFF, bp = -1;
+                } else {   // many equal similarities in the threshold bin: rounds over all entries
                     for (int q = lane; q < n_ent; q += 32) {
-                        const int e = T.ent[q];
-                        if (T.lst[e] != list) continue;
-                        const unsigned long long kk = T.inner[e] & 0x7FFFFFFFFFFFFFFFull;
-                        const int tt = int((T.key[e] & 0x7FFFFFFFu) - 1u);
+                        const Slot v = S[q];
+                        if (((v.key >> 28) & 3u) != tagv) continue;
+                        const unsigned long long kk = v.inner & 0x7FFFFFFFFFFFFFFFull;
+                        const int tt = int((v.key & SLOT_ITEM_MASK) - 1u);
                         if (rr > 0 && !better(last_k, last_t, kk, tt)) continue;
-                        if (bp < 0 || better(kk, tt, bk, bt)) { bk = kk; bt = tt; bp = e; }
+                        if (bp < 0 || better(kk, tt, bk, bt)) { bk = kk; bt = tt; bp = q; }
                     }
-                    warp_argbest(bk, bt, bp);
-                    if (bp < 0) break;
-                    if (lane == 0) {
-                        const unsigned cn = T.cnt[bp];
-                        a.tab_idx[o + rr] = bt;
-                        a.tab_sim[o + rr] = __longlong_as_double((long long)T.inner[bp]);
-                        a.tab_mutu[o + rr] = int(cn & 0xFFFFu); a.tab_n[o + rr] = int(cn >> 16);
-                    }
-                    last_k = bk; last_t = bt;
-                    got = rr + 1;
                 }
+                warp_argbest(bk, bt, bp);
+                if (bp < 0) break;
+                if (lane == 0) {
+                    const Slot v = S[bp];
+                    a.tab_idx[o + rr] = bt;
+                    a.tab_sim[o + rr] = __longlong_as_double((long long)v.inner);
+                    a.tab_mutu[o + rr] = int(v.cnt & 0xFFFFu); a.tab_n[o + rr] = int(v.cnt >> 16);
+                }
+                last_k = bk; last_t = bt;
+                got = rr + 1;
             }
             __syncwarp();
         }
@@ -647,8 +618,7 @@ __global__ void __launch_bounds__(WARPS * 32) sim_warp_smem_kernel(xmap_sim_args
     const int r = blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (r >= n_rows) return;
     unsigned char *mine = smem_raw + (threadIdx.x >> 5) * (warp_tab_bytes(1 << LOG2_SLOTS) + SEL_BYTES);
-    const WarpTab T = carve_tab(mine, 1 << LOG2_SLOTS);
-    warp_row<LOG2_SLOTS>(a, T, mine + warp_tab_bytes(1 << LOG2_SLOTS), rows[r]);
+    warp_row<LOG2_SLOTS>(a, reinterpret_cast<Slot *>(mine), mine + warp_tab_bytes(1 << LOG2_SLOTS), rows[r]);
 }
 
 // global (L2) tables: persistent warps, rows fetched from a counter
@@ -659,7 +629,7 @@ __global__ void __launch_bounds__(128) sim_warp_gmem_kernel(xmap_sim_args a, con
     __shared__ __align__(16) unsigned char s_sel[4][SEL_BYTES];
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const WarpTab T = carve_tab(workspace + (size_t)gw * warp_tab_bytes(1 << LOG2_SLOTS), 1 << LOG2_SLOTS);
+    Slot *T = reinterpret_cast<Slot *>(workspace + (size_t)gw * warp_tab_bytes(1 << LOG2_SLOTS));
     while (true) {
         int r = 0;
         if (lane == 0) r = atomicAdd(counter, 1);
@@ -966,7 +936,6 @@ static int launch_warp_smem(const xmap_sim_args &a, const int32_t *rows, int n_r
     return 0;
 }
 
-constexpr int GMEM_LOG2_SLOTS = 13;
 constexpr int GMEM_CTAS_PER_SM = 12;      // x 4 warps = 48 persistent warps per SM
 
 static int check_args(const xmap_sim_args &a) {
@@ -982,12 +951,14 @@ static int check_args(const xmap_sim_args &a) {
 
 using namespace xmap;
 
+static int gmem_log2_slots(int tier) { return tier == 3 ? 13 : (tier == 4 ? 15 : 0); }
+
 extern "C" size_t xmap_sim_rows_workspace_bytes(int32_t tier) {
-    if (tier != 3) return 0;
+    if (tier != 3 && tier != 4) return 0;
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-    return (size_t)sms * GMEM_CTAS_PER_SM * 4 * warp_tab_bytes(1 << GMEM_LOG2_SLOTS) + 256;
+    return (size_t)sms * GMEM_CTAS_PER_SM * 4 * warp_tab_bytes(1 << gmem_log2_slots(tier)) + 256;
 }
 
 extern "C" int xmap_sim_rows(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows, int32_t tier,
@@ -998,15 +969,19 @@ extern "C" int xmap_sim_rows(const xmap_sim_args *args_h, const int32_t *rows, i
     if (tier == 0) return launch_warp_smem<9, 4>(*args_h, rows, n_rows, st);
     if (tier == 1) return launch_warp_smem<10, 2>(*args_h, rows, n_rows, st);
     if (tier == 2) return launch_warp_smem<11, 1>(*args_h, rows, n_rows, st);
-    if (tier == 3) {
-        if (workspace_bytes < xmap_sim_rows_workspace_bytes(3)) return fail_msg("xmap_sim_rows: workspace too small");
+    if (tier == 3 || tier == 4) {
+        if (workspace_bytes < xmap_sim_rows_workspace_bytes(tier)) return fail_msg("xmap_sim_rows: workspace too small");
         int dev = 0, sms = 148;
         XMAP_CUDA(cudaGetDevice(&dev));
         XMAP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         int32_t *counter = reinterpret_cast<int32_t *>(workspace);
         XMAP_CUDA(cudaMemsetAsync(counter, 0, sizeof(int32_t), st));
-        sim_warp_gmem_kernel<GMEM_LOG2_SLOTS><<<sms * GMEM_CTAS_PER_SM, 128, 0, st>>>(
-            *args_h, rows, n_rows, reinterpret_cast<unsigned char *>(workspace) + 256, counter);
+        if (tier == 3)
+            sim_warp_gmem_kernel<13><<<sms * GMEM_CTAS_PER_SM, 128, 0, st>>>(
+                *args_h, rows, n_rows, reinterpret_cast<unsigned char *>(workspace) + 256, counter);
+        else
+            sim_warp_gmem_kernel<15><<<sms * GMEM_CTAS_PER_SM, 128, 0, st>>>(
+                *args_h, rows, n_rows, reinterpret_cast<unsigned char *>(workspace) + 256, counter);
         XMAP_LAUNCH_CHECK();
         return 0;
     }

@@ -255,6 +255,7 @@ class SimEngine:
             need = L.xmap_sim_rows_workspace_bytes(tier)
             if need:
                 if self._tier_ws is None or self._tier_ws.numel() < need:
+                    self._tier_ws = None
                     self._tier_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
                 ws = self._tier_ws
             self._timed("warp_tier%d" % tier, lambda: N.check(
