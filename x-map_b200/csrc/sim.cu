@@ -443,22 +443,40 @@ __device__ void warp_row(const xmap_sim_args &a, Slot *__restrict__ S, unsigned 
         n_ent += __popc(m);
         __syncwarp();
     }
-    // one evaluation per pair; the similarity replaces the accumulator
-    int lk = 0, ll = 0;
+    // One pass over the compacted entries: similarity (replaces the accumulator), filter, label,
+    // the candidate's class, and a 256-bin histogram of |sim| per class.  Classes: mode 0 ->
+    // 1 = other-domain ("cross"), 2 = same-domain; mode 1 -> 1 = neighbour is a bridge item.
+    unsigned *hist = reinterpret_cast<unsigned *>(sel);          // [2][SEL_BINS]
+    for (int b = lane; b < 2 * SEL_BINS; b += 32) hist[b] = 0u;
+    __syncwarp();
+    int lk = 0, ll = 0, n1 = 0, n2 = 0;
     for (int q = lane; q < n_ent; q += 32) {
         Slot v = S[q];
         double sim; int label;
-        const bool keep = eval_pair(a, c, int(v.key - 1u), int(v.cnt >> 16), int(v.cnt & 0xFFFFu), (long long)v.inner,
-                                    sim, label);
-        v.inner = keep ? (unsigned long long)__double_as_longlong(sim) : 0ull;
-        v.key |= (label ? 0x80000000u : 0u);
+        const int j = int(v.key - 1u);
+        const bool keep = eval_pair(a, c, j, int(v.cnt >> 16), int(v.cnt & 0xFFFFu), (long long)v.inner, sim, label);
+        unsigned cls = 0u;
+        if (keep) {
+            ++lk; ll |= label;
+            if (a.mode == 1) cls = (a.bb_in[j] != 0) ? 1u : 0u;
+            else cls = ((a.contains[j] >> c.dom_i) & 1) ? 2u : 1u;
+            v.inner = (unsigned long long)__double_as_longlong(sim);
+            if (cls) {
+                atomicAdd(&hist[(cls - 1u) * SEL_BINS + sim_bin(v.inner)], 1u);
+                if (cls == 1u) ++n1; else ++n2;
+            }
+        } else {
+            v.inner = 0ull;
+        }
+        v.key |= (label ? 0x80000000u : 0u) | (cls << 28);
         S[q] = v;
-        if (keep) { ++lk; ll |= label; }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         lk += __shfl_xor_sync(0xffffffffu, lk, off);
         ll |= __shfl_xor_sync(0xffffffffu, ll, off);
+        n1 += __shfl_xor_sync(0xffffffffu, n1, off);
+        n2 += __shfl_xor_sync(0xffffffffu, n2, off);
     }
     __syncwarp();
 
@@ -487,79 +505,56 @@ __device__ void warp_row(const xmap_sim_args &a, Slot *__restrict__ S, unsigned 
         a.row_npairs[row] = n_ent;
         a.row_nkept[row] = lk;
     }
-    // list of every kept candidate (extender.py:30-43), tagged into the key
-    for (int q = lane; q < n_ent; q += 32) {
-        const Slot v = S[q];
-        unsigned tag = 0u;
-        if (v.inner != 0ull) {
-            const int j = int((v.key & SLOT_ITEM_MASK) - 1u);
-            if (a.mode == 1) tag = (a.bb_in[j] != 0) ? 1u : 0u;
-            else if (bb) tag = ((a.contains[j] >> c.dom_i) & 1) ? 2u : 1u;
-            else tag = 2u;
-        }
-        S[q].key = v.key | (tag << 28);
-    }
-    __syncwarp();
-    // ---- top-K per list: histogram threshold, then K rounds over the few survivors ----
+    // Lists (extender.py:30-43):  BB row: slot 0 = class 1, slot 1 = class 2;
+    // NB row (pass 1): slot 1 = every kept neighbour (classes 1 and 2); pass 2: slot 0 = class 1.
     const int K = a.k;
+    int bstar[2], want[2];
+    unsigned cmask[2];                                    // classes that belong to the list
+    for (int list = 0; list < 2; ++list) {
+        bool use; int n_list;
+        if (a.mode == 1) { use = (list == 0); cmask[list] = 2u; n_list = n1; }             // bit c = class c
+        else if (bb) { use = true; cmask[list] = (list == 0) ? 2u : 4u; n_list = (list == 0) ? n1 : n2; }
+        else { use = (list == 1); cmask[list] = 6u; n_list = n1 + n2; }
+        want[list] = use ? min(K, n_list) : 0;
+        bstar[list] = 0;
+        if (want[list] == 0) continue;
+        // largest bin b* such that #(bin >= b*) >= want: scan the (summed) histogram from the top
+        int run = 0;
+        bool found = false;
+        for (int hb = SEL_BINS - 32; hb >= 0 && !found; hb -= 32) {
+            unsigned v = 0u;
+            if (cmask[list] & 2u) v += hist[hb + lane];
+            if (cmask[list] & 4u) v += hist[SEL_BINS + hb + lane];
+            unsigned suf = v;                              // suffix sums, highest lane = highest bin
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned t = __shfl_down_sync(0xffffffffu, suf, off);
+                if (lane + off < 32) suf += t;
+            }
+            const unsigned hit = __ballot_sync(0xffffffffu, run + (int)suf >= want[list]);
+            if (hit) { bstar[list] = hb + (31 - __clz(hit)); found = true; }
+            else run += (int)__shfl_sync(0xffffffffu, suf, 0);
+        }
+    }
+    __syncwarp();                                          // the histogram is dead; its memory becomes the survivor buffer
     for (int list = 0; list < 2; ++list) {
         if (list == 1 && a.mode != 0) continue;           // pass 2 only writes slot 0
-        const bool use = (list == 0) ? ((a.mode == 1) || bb) : true;
-        const unsigned tagv = (unsigned)(list + 1);
         int got = 0;
         const size_t o = ((size_t)row * 2 + list) * K;
-        if (use) {
-            unsigned *hist = reinterpret_cast<unsigned *>(sel);
-            for (int b = lane; b < SEL_BINS; b += 32) hist[b] = 0u;
-            __syncwarp();
-            int n_list = 0;
-            for (int q = lane; q < n_ent; q += 32) {
-                const Slot v = S[q];
-                if (((v.key >> 28) & 3u) != tagv) continue;
-                atomicAdd(&hist[sim_bin(v.inner)], 1u);
-                ++n_list;
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) n_list += __shfl_xor_sync(0xffffffffu, n_list, off);
-            __syncwarp();
-            // largest bin b* such that #(bin >= b*) >= min(K, n_list): scan from the top
-            const int want = min(K, n_list);
-            int bstar = 0;
-            {
-                int run = 0;
-                bool found = false;
-                for (int hb = SEL_BINS - 32; hb >= 0 && !found; hb -= 32) {
-                    const unsigned v = hist[hb + lane];
-                    unsigned suf = v;                      // suffix sums, highest lane = highest bin
-#pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        const unsigned t = __shfl_down_sync(0xffffffffu, suf, off);
-                        if (lane + off < 32) suf += t;
-                    }
-                    const unsigned hit = __ballot_sync(0xffffffffu, run + (int)suf >= want);
-                    if (hit && want > 0) {
-                        bstar = hb + (31 - __clz(hit));
-                        found = true;
-                    } else {
-                        run += (int)__shfl_sync(0xffffffffu, suf, 0);
-                    }
-                }
-            }
-            __syncwarp();
-            // survivors: every candidate of the list whose bin is >= b*
+        if (want[list] > 0) {
             unsigned long long *bkey = reinterpret_cast<unsigned long long *>(sel);
             int *bent = reinterpret_cast<int *>(bkey + SEL_BUF);
             int nb = 0;                                    // warp-uniform
             bool overflow = false;
-            for (int q0 = 0; q0 < n_ent && want > 0; q0 += 32) {
+            for (int q0 = 0; q0 < n_ent; q0 += 32) {
                 const int q = q0 + lane;
                 bool take = false;
                 unsigned long long key = 0ull;
                 if (q < n_ent) {
                     const Slot v = S[q];
-                    if (((v.key >> 28) & 3u) == tagv) {
+                    if ((cmask[list] >> ((v.key >> 28) & 3u)) & 1u) {
                         key = v.inner & 0x7FFFFFFFFFFFFFFFull;
-                        take = sim_bin(key) >= bstar;
+                        take = sim_bin(key) >= bstar[list];
                     }
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, take);
@@ -572,7 +567,7 @@ __device__ void warp_row(const xmap_sim_args &a, Slot *__restrict__ S, unsigned 
             }
             __syncwarp();
             unsigned long long last_k = ~0ull; int last_t = -1;
-            for (int rr = 0; rr < want; ++rr) {
+            for (int rr = 0; rr < want[list]; ++rr) {
                 unsigned long long bk = 0; int bt = 0x7FFFFFFF, bp = -1;
                 if (!overflow) {
                     for (int q = lane; q < nb; q += 32) {
@@ -585,7 +580,7 @@ __device__ void warp_row(const xmap_sim_args &a, Slot *__restrict__ S, unsigned 
                 } else {   // many equal similarities in the threshold bin: rounds over all entries
                     for (int q = lane; q < n_ent; q += 32) {
                         const Slot v = S[q];
-                        if (((v.key >> 28) & 3u) != tagv) continue;
+                        if (!((cmask[list] >> ((v.key >> 28) & 3u)) & 1u)) continue;
                         const unsigned long long kk = v.inner & 0x7FFFFFFFFFFFFFFFull;
                         const int tt = int((v.key & SLOT_ITEM_MASK) - 1u);
                         if (rr > 0 && !better(last_k, last_t, kk, tt)) continue;
