@@ -38,6 +38,18 @@ def test_sim_all_tiers_vs_restatement(method):
     assert all(n > 0 for n in st["tiers"][:4]) and (st["tiers"][4] + st["big"]) > 0, st
 
 
+def test_heavy_rows_sparse_and_dense_modes():
+    """A wider catalogue: heavy rows below 2*n_items products go through first-touch lists, the
+    heaviest through the reduction-only dense mode; both against the restatement."""
+    import torch
+    case = PT.synth_case(30000, 12000, 500000, 0.05, seed=13)
+    out = PT.check_sim_against_restatement(case, "adjust_cosine", 50, 10)
+    w = out["lay"].row_work
+    big = w > 22000
+    assert int((big & (w < 2 * case["n_items"])).sum()) > 0 and int((w >= 2 * case["n_items"]).sum()) > 0
+    assert out["tabs"].stats["pass1"]["tiers"][4] > 0
+
+
 def test_heavy_rows_in_several_batches_and_chunks():
     """Tiny table budget -> the heavy tier runs in many batches; results must not change."""
     case = PT.synth_case(6000, 1200, 120000, 0.1, seed=5)

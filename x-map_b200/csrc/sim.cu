@@ -24,6 +24,12 @@ namespace xmap {
 
 constexpr int KMAX = XMAP_KMAX;
 
+// A row with at least 2 * n_items products touches a large share of the columns: it is accumulated
+// with fire-and-forget reductions only (no first-touch list, so no warp ever waits for an atomic to
+// return) and evaluated by a linear, coalesced scan of its dense table.
+__host__ __device__ __forceinline__ bool row_is_dense(long long row_work, int n_items) { return row_work >= 2LL * n_items; }
+
+
 
 // Candidate buffer of the per-row top-k selection.  A candidate belongs to exactly one of the
 // row's two lists; it is stored as a 128-bit sortable record:
@@ -42,7 +48,7 @@ struct Scratch {
     int t_j[2][KMAX], t_mutu[2][KMAX], t_n[2][KMAX];
     int t_len[2];
     int fin_len[2][THREADS / 32];
-    int ncand, n0, n_pairs, n_kept, any_label;
+    int ncand, n0;
 };
 
 constexpr unsigned long long LIST0_BIT = 1ull << 63;
@@ -254,106 +260,6 @@ __device__ void select_lists(Scratch<THREADS, CAP> &S, int K) {
     __syncthreads();
     if (tid == 0) { S.ncand = 0; S.n0 = 0; }
     __syncthreads();
-}
-
-struct PreCounts { int have, n_pairs, n_kept, any_label; };
-
-// Get(e, j, n, mutu, sim, label, last_sweep) -> 0: empty entry, 1: co-rated but filtered, 2: kept
-template <int THREADS, int CAP, class Get>
-__device__ void finalize_row(const xmap_sim_args &a, const RowCtx &c, int n_entries, Get get,
-                             Scratch<THREADS, CAP> &S, PreCounts pre) {
-    const int tid = threadIdx.x;
-    const int K = a.k;
-    const int row = c.row;
-    if (tid == 0) {
-        S.ncand = 0; S.n0 = 0; S.n_pairs = 0; S.n_kept = 0; S.any_label = 0;
-        S.t_len[0] = S.t_len[1] = 0; S.thr[0] = S.thr[1] = 0ull;
-    }
-    __syncthreads();
-
-    if (a.mode == 2) {  // emit every kept pair (materialised sim RDD, assist.py:75-77)
-        const int64_t base = a.emit_ptr[row];
-        for (int e = tid; e < n_entries; e += THREADS) {
-            int j, n, mutu, label; double sim;
-            if (get(e, j, n, mutu, sim, label, true) != 2) continue;
-            int pos = atomicAdd(&S.n_kept, 1);
-            a.emit_j[base + pos] = j; a.emit_sim[base + pos] = sim;
-            a.emit_mutu[base + pos] = mutu; a.emit_n[base + pos] = n;
-        }
-        return;
-    }
-
-    bool bb = false;
-    if (a.mode == 0) {  // counts + is this a bridge item (assist.py:84-86)
-        if (!pre.have) {
-            int lp = 0, lk = 0, ll = 0;
-            for (int e = tid; e < n_entries; e += THREADS) {
-                int j, n, mutu, label; double sim;
-                int st = get(e, j, n, mutu, sim, label, false);
-                if (st == 0) continue;
-                ++lp;
-                if (st == 2) { ++lk; ll |= label; }
-            }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                lp += __shfl_xor_sync(0xffffffffu, lp, off);
-                lk += __shfl_xor_sync(0xffffffffu, lk, off);
-                ll |= __shfl_xor_sync(0xffffffffu, ll, off);
-            }
-            if ((tid & 31) == 0) {
-                if (lp) atomicAdd(&S.n_pairs, lp);
-                if (lk) atomicAdd(&S.n_kept, lk);
-                if (ll) atomicOr(&S.any_label, 1);
-            }
-            __syncthreads();
-        } else if (tid == 0) {
-            S.n_pairs = pre.n_pairs; S.n_kept = pre.n_kept; S.any_label = pre.any_label;
-        }
-        __syncthreads();
-        bb = S.any_label != 0;
-        if (tid == 0) {
-            a.row_flags[row] = bb ? 1 : 0;
-            a.row_npairs[row] = S.n_pairs;
-            a.row_nkept[row] = S.n_kept;
-        }
-    }
-    // list definitions (extender.py:30-43); every candidate belongs to exactly one list
-    const bool use0 = (a.mode == 1) || bb;
-    const bool use1 = (a.mode == 0);
-    for (int base = 0; base < n_entries; base += THREADS) {
-        if (S.ncand + THREADS + 2 * KMAX > CAP) select_lists<THREADS, CAP>(S, K);
-        const int e = base + tid;
-        int j, n, mutu, label; double sim;
-        if (e < n_entries && get(e, j, n, mutu, sim, label, true) == 2) {
-            int lst;
-            if (a.mode == 1) lst = (a.bb_in[j] != 0) ? 0 : -1;
-            else if (bb) lst = ((a.contains[j] >> c.dom_i) & 1) ? 1 : 0;
-            else lst = 1;
-            const unsigned long long key = abs_key(sim);
-            if (lst >= 0 && S.thr[lst] && key < S.thr[lst]) lst = -1;
-            if (lst >= 0) {
-                const int p = atomicAdd(&S.ncand, 1);
-                if (lst == 0) atomicAdd(&S.n0, 1);
-                S.skey[p] = (lst == 0 ? LIST0_BIT : 0ull) | key;
-                S.spay[p] = (sim < 0.0 ? LIST0_BIT : 0ull) | ((unsigned long long)j << 16) | (unsigned)p;
-                S.c_mutu[p] = mutu; S.c_n[p] = n;
-            }
-        }
-        __syncthreads();
-    }
-    select_lists<THREADS, CAP>(S, K);
-    // write tables [n_items][2][K]
-    for (int slot = 0; slot < 2; ++slot) {
-        const bool wr = (slot == 0) ? (a.mode == 1 || a.mode == 0) : (a.mode == 0);
-        if (!wr) continue;
-        const int len = ((slot == 0) ? use0 : use1) ? S.t_len[slot] : 0;
-        const size_t o = ((size_t)row * 2 + slot) * K;
-        if (tid < len) {
-            a.tab_idx[o + tid] = S.t_j[slot][tid]; a.tab_sim[o + tid] = S.t_sim[slot][tid];
-            a.tab_mutu[o + tid] = S.t_mutu[slot][tid]; a.tab_n[o + tid] = S.t_n[slot][tid];
-        }
-        if (tid == 0) a.tab_len[(size_t)row * 2 + slot] = len;
-    }
 }
 
 // --------------------------------------------------------------------------
@@ -669,6 +575,17 @@ __global__ void __launch_bounds__(BIG_THREADS) sim_big_accum_kernel(
         ulonglong2 *T = table + (size_t)b * a.n_items;
         int32_t *tl = touched + (size_t)b * a.n_items;
         int32_t *tn = touched_n + b;
+        const bool dense = row_is_dense(a.row_work[row], a.n_items);
+        if (dense) {                                   // fire-and-forget: nothing to wait for
+            auto add_red = [&](bool valid, int j, unsigned agree, long long fx) {
+                if (valid) {
+                    atomicAdd(&T[j].x, (1ull << 32) | (unsigned long long)agree);
+                    atomicAdd(&T[j].y, (unsigned long long)fx);
+                }
+            };
+            accumulate_raters(a, row, cls_i, lo, hi, 0, 1, add_red);
+            continue;
+        }
         int nstage = 0;                                // warp-uniform
         auto flush = [&](int count) {                  // move `count` staged columns to the row's list
             int basep = 0;
@@ -710,6 +627,7 @@ struct BigScratch {
     long long *tile_off;    // [n_rows + 1] scan of per-row tile counts
     int *row_kept;          // [n_rows]
     int *row_label;         // [n_rows]
+    int *row_pairs;         // [n_rows] co-rated columns of the row
     int *tile_counter;      // [1]
     double *c_sim;          // [capacity] 0.0 = filtered / empty
     int *c_j, *c_mutu, *c_n;
@@ -717,11 +635,8 @@ struct BigScratch {
     long long capacity;
 };
 
-// A row whose touched list covers >= 1/8 of the columns is evaluated by a linear scan of its
-// dense table (coalesced) instead of through the list (random access).
-__device__ __forceinline__ bool row_is_dense(int touched, int n_items) { return (long long)touched * 8 >= n_items; }
-
-__global__ void big_scan_kernel(const int32_t *__restrict__ touched_n, int n_rows, int n_items, BigScratch sc,
+__global__ void big_scan_kernel(const int32_t *__restrict__ touched_n, const int32_t *__restrict__ rows,
+                                const int64_t *__restrict__ row_work, int n_rows, int n_items, BigScratch sc,
                                 int32_t *error_flag) {
     __shared__ long long s_ent[1024], s_tile[1024];
     const int tid = threadIdx.x;
@@ -730,8 +645,7 @@ __global__ void big_scan_kernel(const int32_t *__restrict__ touched_n, int n_row
     for (int q = 0; q < per; ++q) {
         int b = tid * per + q;
         if (b < n_rows) {
-            const int t = touched_n[b];
-            const long long len = row_is_dense(t, n_items) ? n_items : t;
+            const long long len = row_is_dense(row_work[rows[b]], n_items) ? n_items : touched_n[b];
             le += len; lt += (len + EVAL_TILE - 1) / EVAL_TILE;
         }
     }
@@ -752,11 +666,11 @@ __global__ void big_scan_kernel(const int32_t *__restrict__ touched_n, int n_row
     for (int q = 0; q < per; ++q) {
         int b = tid * per + q;
         if (b < n_rows) {
-            const int t = touched_n[b];
-            const long long len = row_is_dense(t, n_items) ? n_items : t;
+            const bool dense = row_is_dense(row_work[rows[b]], n_items);
+            const long long len = dense ? n_items : touched_n[b];
             sc.ent_off[b] = re; sc.tile_off[b] = rt;
             re += len; rt += (len + EVAL_TILE - 1) / EVAL_TILE;
-            sc.row_kept[b] = 0; sc.row_label[b] = 0;
+            sc.row_kept[b] = 0; sc.row_label[b] = 0; sc.row_pairs[b] = dense ? 0 : touched_n[b];
         }
     }
 }
@@ -768,14 +682,14 @@ __global__ void __launch_bounds__(256) big_eval_kernel(xmap_sim_args a, const in
                                                        ulonglong2 *__restrict__ table,
                                                        const int32_t *__restrict__ touched,
                                                        const int32_t *__restrict__ touched_n, BigScratch sc) {
-    __shared__ int s_tile, s_b, s_kept, s_label;
+    __shared__ int s_tile, s_b, s_kept, s_label, s_pairs;
     const int tid = threadIdx.x;
     if (sc.ent_off[n_rows] > sc.capacity) return;
     const long long n_tiles = sc.tile_off[n_rows];
     while (true) {
         if (tid == 0) {
             const int t = atomicAdd(sc.tile_counter, 1);
-            s_tile = t; s_kept = 0; s_label = 0;
+            s_tile = t; s_kept = 0; s_label = 0; s_pairs = 0;
             int lo = 0, hi = n_rows;                  // largest b with tile_off[b] <= t
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
@@ -789,16 +703,15 @@ __global__ void __launch_bounds__(256) big_eval_kernel(xmap_sim_args a, const in
         if (t >= n_tiles) break;
         const int row = rows[b];
         const RowCtx c = make_ctx(a, row);
-        const int tn = touched_n[b];
-        const bool dense = row_is_dense(tn, a.n_items);
-        const int len = dense ? a.n_items : tn;
+        const bool dense = row_is_dense(a.row_work[row], a.n_items);
+        const int len = dense ? a.n_items : touched_n[b];
         const int e0 = (int)(t - sc.tile_off[b]) * EVAL_TILE;
         const int e1 = min(e0 + EVAL_TILE, len);
         ulonglong2 *T = table + (size_t)b * a.n_items;
         const int32_t *tl = touched + (size_t)b * a.n_items;
         const long long goff = sc.ent_off[b];
         const bool cosine = (a.method == XMAP_METHOD_COSINE);
-        int lk = 0, ll = 0;
+        int lk = 0, ll = 0, lp = 0;
         for (int eb = e0 + tid; eb < e1; eb += 256 * EVAL_UNROLL) {
             int j[EVAL_UNROLL];
             ulonglong2 cell[EVAL_UNROLL];
@@ -833,6 +746,7 @@ __global__ void __launch_bounds__(256) big_eval_kernel(xmap_sim_args a, const in
                     if (a.mode != 2) sc.c_sim[g] = 0.0;
                     continue;
                 }
+                ++lp;
                 const int n = int(cell[u].x >> 32), mutu = int(cell[u].x & 0xFFFFFFFFull);
                 const int q = 62 - a.r2_bits - min(c.cls_i, ceil_log2_u32((uint32_t)cnt_j[u]));
                 const double inner = (double)(long long)cell[u].y * pow2d(-q);
@@ -858,43 +772,111 @@ __global__ void __launch_bounds__(256) big_eval_kernel(xmap_sim_args a, const in
         for (int off = 16; off > 0; off >>= 1) {
             lk += __shfl_xor_sync(0xffffffffu, lk, off);
             ll |= __shfl_xor_sync(0xffffffffu, ll, off);
+            lp += __shfl_xor_sync(0xffffffffu, lp, off);
         }
         if ((tid & 31) == 0) {
             if (lk) atomicAdd(&s_kept, lk);
             if (ll) atomicOr(&s_label, 1);
+            if (lp) atomicAdd(&s_pairs, lp);
         }
         __syncthreads();
         if (tid == 0) {
             if (s_kept) atomicAdd(&sc.row_kept[b], s_kept);
             if (s_label) atomicOr(&sc.row_label[b], 1);
+            if (dense && s_pairs) atomicAdd(&sc.row_pairs[b], s_pairs);
         }
         __syncthreads();
     }
 }
 
+constexpr int SEL_UNROLL = 4;                 // candidate records per thread per step
+constexpr int SEL_CAP = 8 * FIN_THREADS;      // candidate buffer of the heavy-row selection
+
+// One CTA per heavy row: stream the row's candidate records (coalesced, SEL_UNROLL independent
+// 8-byte loads per thread per step), drop everything below the current K-th best before touching
+// the rest of the record, and keep the running top-K per list with the register tournament.
 __global__ void __launch_bounds__(FIN_THREADS) big_select_kernel(xmap_sim_args a, const int32_t *__restrict__ rows,
                                                                  int n_rows, int32_t *__restrict__ touched_n,
                                                                  BigScratch sc) {
-    __shared__ Scratch<FIN_THREADS, 4 * FIN_THREADS> S;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using ScratchT = Scratch<FIN_THREADS, SEL_CAP>;
+    ScratchT &S = *reinterpret_cast<ScratchT *>(smem_raw);
+    const int tid = threadIdx.x;
     const int b = blockIdx.x;
     const int row = rows[b];
-    const long long total = sc.ent_off[n_rows];
-    if (total > sc.capacity) return;
+    if (sc.ent_off[n_rows] > sc.capacity) return;
     const long long off = sc.ent_off[b];
     const int n_entries = (int)(sc.ent_off[b + 1] - off);
-    const int n_touched = touched_n[b];
-    __syncthreads();
-    if (threadIdx.x == 0) touched_n[b] = 0;
+    const int n_pairs = sc.row_pairs[b];
+    if (tid == 0) touched_n[b] = 0;
     if (a.mode == 2) return;
     const RowCtx c = make_ctx(a, row);
-    auto get = [&](int e, int &j, int &n, int &mutu, double &sim, int &label, bool) -> int {
-        sim = sc.c_sim[off + e];
-        if (sim == 0.0) return 1;
-        j = sc.c_j[off + e]; mutu = sc.c_mutu[off + e]; n = sc.c_n[off + e]; label = sc.c_label[off + e];
-        return 2;
-    };
-    finalize_row<FIN_THREADS, 4 * FIN_THREADS>(a, c, n_entries, get, S,
-                              PreCounts{1, n_touched, sc.row_kept[b], sc.row_label[b]});
+    const int K = a.k;
+    if (tid == 0) {
+        S.ncand = 0; S.n0 = 0;
+        S.t_len[0] = S.t_len[1] = 0; S.thr[0] = S.thr[1] = 0ull;
+    }
+    __syncthreads();
+    bool bb = false;
+    if (a.mode == 0) {
+        bb = sc.row_label[b] != 0;                       // a kept cross-domain pair (assist.py:84-86)
+        if (tid == 0) {
+            a.row_flags[row] = bb ? 1 : 0;
+            a.row_npairs[row] = n_pairs;
+            a.row_nkept[row] = sc.row_kept[b];
+        }
+    }
+    const bool use0 = (a.mode == 1) || bb;               // list definitions: extender.py:30-43
+    const bool use1 = (a.mode == 0);
+    for (int base = 0; base < n_entries; base += FIN_THREADS * SEL_UNROLL) {
+        if (S.ncand + FIN_THREADS * SEL_UNROLL + 2 * KMAX > SEL_CAP) select_lists<FIN_THREADS, SEL_CAP>(S, K);
+        // the smallest threshold any list in use still accepts
+        unsigned long long floor_key = 0ull;
+        {
+            const unsigned long long f0 = use0 ? S.thr[0] : ~0ull, f1 = use1 ? S.thr[1] : ~0ull;
+            floor_key = (f0 < f1) ? f0 : f1;
+            if (floor_key == ~0ull) floor_key = 0ull;
+        }
+        double sv[SEL_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SEL_UNROLL; ++u) {
+            const int e = base + u * FIN_THREADS + tid;
+            sv[u] = (e < n_entries) ? sc.c_sim[off + e] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < SEL_UNROLL; ++u) {
+            if (sv[u] == 0.0) continue;
+            const unsigned long long key = abs_key(sv[u]);
+            if (key < floor_key) continue;
+            const long long g = off + base + u * FIN_THREADS + tid;
+            const int j = sc.c_j[g];
+            int lst;
+            if (a.mode == 1) lst = (a.bb_in[j] != 0) ? 0 : -1;
+            else if (bb) lst = ((a.contains[j] >> c.dom_i) & 1) ? 1 : 0;
+            else lst = 1;
+            if (lst >= 0 && S.thr[lst] && key < S.thr[lst]) lst = -1;
+            if (lst >= 0) {
+                const int p = atomicAdd(&S.ncand, 1);
+                if (lst == 0) atomicAdd(&S.n0, 1);
+                S.skey[p] = (lst == 0 ? LIST0_BIT : 0ull) | key;
+                S.spay[p] = (sv[u] < 0.0 ? LIST0_BIT : 0ull) | ((unsigned long long)j << 16) | (unsigned)p;
+                S.c_mutu[p] = sc.c_mutu[g]; S.c_n[p] = sc.c_n[g];
+            }
+        }
+        __syncthreads();
+    }
+    select_lists<FIN_THREADS, SEL_CAP>(S, K);
+    // write tables [n_items][2][K]
+    for (int slot = 0; slot < 2; ++slot) {
+        if (slot == 1 && a.mode != 0) continue;
+        const int len = ((slot == 0) ? use0 : use1) ? S.t_len[slot] : 0;
+        const size_t o = ((size_t)row * 2 + slot) * K;
+        if (tid < len) {
+            a.tab_idx[o + tid] = S.t_j[slot][tid]; a.tab_sim[o + tid] = S.t_sim[slot][tid];
+            a.tab_mutu[o + tid] = S.t_mutu[slot][tid]; a.tab_n[o + tid] = S.t_n[slot][tid];
+        }
+        if (tid == 0) a.tab_len[(size_t)row * 2 + slot] = len;
+    }
 }
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -906,6 +888,7 @@ static size_t big_scratch_layout(int n_rows, long long capacity, char *base, Big
     char *p_toff = take(sizeof(long long) * ((size_t)n_rows + 1));
     char *p_kept = take(sizeof(int) * (size_t)n_rows);
     char *p_lab = take(sizeof(int) * (size_t)n_rows);
+    char *p_pairs = take(sizeof(int) * (size_t)n_rows);
     char *p_cnt = take(256);
     char *p_sim = take(sizeof(double) * (size_t)capacity);
     char *p_j = take(sizeof(int) * (size_t)capacity);
@@ -913,7 +896,7 @@ static size_t big_scratch_layout(int n_rows, long long capacity, char *base, Big
     char *p_n = take(sizeof(int) * (size_t)capacity);
     char *p_l = take((size_t)capacity);
     if (sc) {
-        sc->ent_off = (long long *)p_off; sc->tile_off = (long long *)p_toff; sc->row_kept = (int *)p_kept; sc->row_label = (int *)p_lab;
+        sc->ent_off = (long long *)p_off; sc->tile_off = (long long *)p_toff; sc->row_kept = (int *)p_kept; sc->row_label = (int *)p_lab; sc->row_pairs = (int *)p_pairs;
         sc->tile_counter = (int *)p_cnt; sc->c_sim = (double *)p_sim; sc->c_j = (int *)p_j;
         sc->c_mutu = (int *)p_m; sc->c_n = (int *)p_n; sc->c_label = (unsigned char *)p_l;
         sc->capacity = capacity;
@@ -1018,7 +1001,8 @@ extern "C" int xmap_sim_big_finalize(const xmap_sim_args *args_h, const int32_t 
     int dev = 0, sms = 148;
     XMAP_CUDA(cudaGetDevice(&dev));
     XMAP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    big_scan_kernel<<<1, 1024, 0, st>>>(touched_n, n_rows, args_h->n_items, sc, args_h->error_flag);
+    big_scan_kernel<<<1, 1024, 0, st>>>(touched_n, rows, args_h->row_work, n_rows, args_h->n_items, sc,
+                                      args_h->error_flag);
     XMAP_LAUNCH_CHECK();
     int eval_per_sm = 3;
     XMAP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eval_per_sm, big_eval_kernel, 256, 0));
@@ -1026,7 +1010,9 @@ extern "C" int xmap_sim_big_finalize(const xmap_sim_args *args_h, const int32_t 
     big_eval_kernel<<<sms * eval_per_sm, 256, 0, st>>>(*args_h, rows, n_rows,
                                                       reinterpret_cast<ulonglong2 *>(table), touched, touched_n, sc);
     XMAP_LAUNCH_CHECK();
-    big_select_kernel<<<n_rows, FIN_THREADS, 0, st>>>(*args_h, rows, n_rows, touched_n, sc);
+    const size_t sel_smem = sizeof(Scratch<FIN_THREADS, SEL_CAP>);
+    XMAP_CUDA(cudaFuncSetAttribute(big_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+    big_select_kernel<<<n_rows, FIN_THREADS, sel_smem, st>>>(*args_h, rows, n_rows, touched_n, sc);
     XMAP_LAUNCH_CHECK();
     return 0;
 }

@@ -194,7 +194,7 @@ class SimEngine:
         per_row = I * 20 + 4
         b_max = int(max(1, self.table_budget // per_row))
         w = self.lay.row_work[big.long()]
-        cap = torch.where(w * 8 >= I, torch.full_like(w, I), w).cpu().tolist()
+        cap = torch.where(w >= 2 * I, torch.full_like(w, I), torch.clamp(w, max=I)).cpu().tolist()   # dense rows: I records
         batches, lo, acc = [], 0, 0
         for q, c in enumerate(cap):
             if q > lo and (q - lo >= b_max or acc + c > BIG_CAND_CAPACITY):
