@@ -1,0 +1,2 @@
+set -x
+python prof5.py > gpurun_out/prof5.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"xsim" -c 200 --csv --log-file gpurun_out/launches_xsim.csv python prof5.py > gpurun_out/ncu_xsim.log 2>&1

@@ -133,11 +133,19 @@ def gpu_lists(tabs):
             tabs.tab_sim.cpu().numpy(), tabs.tab_mutu.cpu().numpy(), tabs.tab_n.cpu().numpy())
 
 
-def compare_knn(tabs, bb, valid_nb, lists, fragile=frozenset(), ref_pairs=None):
+NEAR_TIE_RTOL = 1e-9     # |sim| values closer than this are a tie up to fp64 rounding noise
+
+
+def compare_knn(tabs, bb, valid_nb, lists, fragile=frozenset(), ref_pairs=None, ref_sim=None):
     """lists: dict name -> (ptr, nbr) ragged arrays in canonical order.
-    Neighbour lists must be identical, order included.  Only neighbours that are
-    fragile zeros (see compare_pairs) may be missing / extra."""
-    flags, tl, ti, _, _, _ = gpu_lists(tabs)
+    Neighbour lists must be identical, order included, with two tolerated divergences:
+      * neighbours that are fragile zeros (see compare_pairs) may be missing / extra;
+      * neighbours whose |sim| agree to NEAR_TIE_RTOL may be permuted or swapped at the cut:
+        mathematically tied similarities are ordered by ulp-level rounding noise in the fp64
+        reference and by item index in the order-free fixed-point kernels (ref_sim: callable
+        (item, neighbour) -> reference sim, needed to recognise them).
+    Returns the number of lists that differed only by near-ties."""
+    flags, tl, ti, ts, _, _ = gpu_lists(tabs)
     n_items = len(bb)
     gbb = flags.astype(bool)
     if not np.array_equal(gbb, bb):
@@ -147,7 +155,7 @@ def compare_knn(tabs, bb, valid_nb, lists, fragile=frozenset(), ref_pairs=None):
         for it in np.nonzero(gbb != bb)[0]:
             js = rj[(ri == it) & (rl == 1)]
             assert all((int(it) * n_items + int(j)) in fragile for j in js), "BB flag of item %d differs" % it
-    bad = 0
+    bad, near, examples = 0, 0, []
     for it in range(n_items):
         if gbb[it] != bb[it]:
             continue
@@ -170,8 +178,16 @@ def compare_knn(tabs, bb, valid_nb, lists, fragile=frozenset(), ref_pairs=None):
                 g2 = [int(j) for j in got if (it * n_items + int(j)) not in fragile]
                 if g2[:len(w2)] == w2:
                     continue
+            if ref_sim is not None and len(got) == len(want):
+                rs = np.abs(np.array([ref_sim(it, int(j)) for j in want]))
+                gs = np.abs(ts[it, slot, :tl[it, slot]])
+                if np.allclose(gs, rs, rtol=NEAR_TIE_RTOL, atol=0):
+                    near += 1
+                    continue
+                examples.append((it, nm, got.tolist(), want.tolist(), gs.tolist(), rs.tolist()))
             bad += 1
-    assert bad == 0, "%d neighbour lists differ" % bad
+    assert bad == 0, "%d neighbour lists differ, e.g. %r" % (bad, examples[:2])
+    return near
 
 
 def restate_lists(knn, pairs):
@@ -197,9 +213,17 @@ def check_sim_against_restatement(case, method, num_atleast, k, table_budget=Non
                                  case["n_items"])
     assert int(tabs.row_npairs.sum().item()) == P["n_pairs_total"], "co-rated pair count differs"
     knn = RS.select_knn(P, case["n_items"], k, case["meta"]["dom_code"], case["meta"]["contains"])
-    compare_knn(tabs, knn["bb"], knn["valid_nb"], restate_lists(knn, P), fragile,
-                (P["i"], P["j"], P["label"]))
-    return dict(lay=lay, eng=eng, tabs=tabs, pairs=pairs, P=P, knn=knn, rel=rel, fragile=fragile)
+    n_items = case["n_items"]
+    pkey = P["i"].astype(np.int64) * n_items + P["j"]          # sorted by construction
+
+    def ref_sim(it, j):
+        q = np.searchsorted(pkey, it * n_items + j)
+        return P["sim"][q] if q < len(pkey) and pkey[q] == it * n_items + j else 0.0
+    near = compare_knn(tabs, knn["bb"], knn["valid_nb"], restate_lists(knn, P), fragile,
+                       (P["i"], P["j"], P["label"]), ref_sim)
+    n_lists = 2 * int(knn["bb"].sum() + knn["valid_nb"].sum())
+    assert near <= 0.005 * n_lists + 1, "%d of %d lists differ by near-ties" % (near, n_lists)
+    return dict(lay=lay, eng=eng, tabs=tabs, pairs=pairs, P=P, knn=knn, rel=rel, fragile=fragile, near_ties=near)
 
 
 def run_smoke():
