@@ -1,3 +1,3 @@
 set -x
-python -m pytest tests/test_gpu_extend.py tests/test_gpu_pipeline.py -x -q -m gpu 2>&1 | tail -25
-timeout 900 python bench.py --workload cfg2 --steps 2 --warmup 1 --no-cpu > gpurun_out/bench_cfg2.json 2> gpurun_out/bench_cfg2.err; tail -3 gpurun_out/bench_cfg2.err
+python -m pytest tests/test_gpu_extend.py tests/test_gpu_pipeline.py -x -q -m gpu 2>&1 | grep -vE "Warning|utcfrom|^\s*$" | tail -12
+python prof5.py > gpurun_out/prof5.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"xsim" -c 200 --csv --log-file gpurun_out/launches_xsim.csv python prof5.py > gpurun_out/ncu_xsim.log 2>&1

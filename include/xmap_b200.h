@@ -186,10 +186,12 @@ typedef struct xmap_xsim_args {
     const int64_t *rs_ptr;                    /* [n_s+1] */
     const int32_t *rs_end;
     const double *rs_e1, *rs_m1, *rs_f1, *rs_e2, *rs_m2, *rs_f2;
-    /* per-unit hash region: [hash_off[u], hash_off[u]+hash_size[u]) cells, size a power of two >= 32 */
+    /* per-unit hash region: [hash_off[u], hash_off[u]+hash_size[u]) 24-byte cells {u64 key, f64 num,
+     * f64 den}, size a power of two >= 32.  key = epoch << 32 | (end + 1): cells of another epoch are
+     * empty, so the workspace is zeroed once when allocated and every launch passes a fresh epoch >= 1. */
     const int64_t *hash_off; const int32_t *hash_size;
-    int32_t *hash_key;                        /* zero on entry */
-    double *hash_num; double *hash_den;
+    void *hash_cells;
+    uint32_t epoch;
     /* merge tree of the heavy starts: round r merges pairs [round_ptr_h[r], round_ptr_h[r+1]) */
     int32_t n_rounds; const int32_t *round_ptr_h;   /* HOST array, n_rounds + 1 entries */
     const int32_t *pair_dst, *pair_src;       /* unit indices; dst's table is sized for the union */

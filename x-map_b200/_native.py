@@ -41,7 +41,7 @@ class XsimArgs(C.Structure):
         ("par_ptr", _p), ("par_s", _p), ("par_joint", _p), ("par_e", _p), ("par_m", _p), ("par_f", _p),
         ("rs_ptr", _p), ("rs_end", _p),
         ("rs_e1", _p), ("rs_m1", _p), ("rs_f1", _p), ("rs_e2", _p), ("rs_m2", _p), ("rs_f2", _p),
-        ("hash_off", _p), ("hash_size", _p), ("hash_key", _p), ("hash_num", _p), ("hash_den", _p),
+        ("hash_off", _p), ("hash_size", _p), ("hash_cells", _p), ("epoch", C.c_uint32),
         ("n_rounds", C.c_int32), ("round_ptr_h", _p), ("pair_dst", _p), ("pair_src", _p),
         ("top_m", C.c_int32), ("mode", C.c_int32),
         ("out_count", _p),

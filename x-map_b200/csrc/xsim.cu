@@ -16,20 +16,33 @@ namespace xmap {
 
 constexpr int XS_THREADS = 256;
 
-// find-or-insert `key` (item + 1) in an open-addressing table; returns the slot or -1 (full).
-// Only one warp (accumulate) or one CTA (merge) ever writes a given table, so a plain CAS on the
-// key is enough; num/den of a fresh slot are initialised by the inserting thread.
-__device__ __forceinline__ int table_slot(int32_t *hk, double *hn, double *hd, int hsize, int shift, int key) {
+// 24-byte accumulator cell.  key = epoch << 32 | (end item + 1): a cell whose epoch differs from the
+// launch's epoch is empty, so the workspace never has to be cleared between launches (it is zeroed
+// once when allocated and every launch uses a fresh epoch).  Key and values share a 32-byte sector
+// in 3 of 4 cells, so a probe + update costs about one DRAM sector each way.
+struct XCell {
+    unsigned long long key;
+    double num, den;
+};
+
+// find-or-insert: returns the cell index or -1 (table full).  Only one warp (accumulate) or one
+// CTA (merge) ever writes a given table; the CAS resolves lanes racing for one empty cell, and the
+// thread whose CAS inserts the key initialises the values.
+__device__ __forceinline__ int table_slot(XCell *tab, int hsize, int shift, unsigned long long key, unsigned epoch) {
     const unsigned mask = (unsigned)hsize - 1u;
-    unsigned slot = ((unsigned)(key - 1) * 2654435761u) >> shift;
+    unsigned slot = (((unsigned)key - 1u) * 2654435761u) >> shift;
     for (int probe = 0; probe < hsize; ++probe) {
-        int cur = *(volatile int32_t *)&hk[slot];
+        unsigned long long cur = *(volatile unsigned long long *)&tab[slot].key;
         if (cur != key) {
-            if (cur == 0) {
-                cur = atomicCAS(&hk[slot], 0, key);
-                if (cur == 0) { hn[slot] = 0.0; hd[slot] = 0.0; }
+            if ((unsigned)(cur >> 32) != epoch) {          // empty (stale epoch): try to claim it
+                const unsigned long long old = atomicCAS(&tab[slot].key, cur, key);
+                if (old == cur) { tab[slot].num = 0.0; tab[slot].den = 0.0; return (int)slot; }
+                cur = old;
+                if (cur == key) return (int)slot;
+                if ((unsigned)(cur >> 32) != epoch) { --probe; continue; }   // changed under us but still empty: retry
             }
-            if (cur != 0 && cur != key) { slot = (slot + 1) & mask; continue; }
+            slot = (slot + 1) & mask;
+            continue;
         }
         return (int)slot;
     }
@@ -47,16 +60,15 @@ __global__ void __launch_bounds__(XS_THREADS) xsim_accum_kernel(xmap_xsim_args a
     const int x = (blockIdx.x * XS_THREADS + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (x >= a.n_units) return;
-    const int64_t hoff = a.hash_off[x];
     const int hsize = a.hash_size[x];
     if (hsize < 32 || (hsize & (hsize - 1)) != 0) {   // contract: power of two >= 32
         if (lane == 0) atomicExch(a.error_flag, 3);
         return;
     }
     const int shift = table_shift(hsize);
-    int32_t *hk = a.hash_key + hoff;
-    double *hn = a.hash_num + hoff;
-    double *hd = a.hash_den + hoff;
+    XCell *tab = reinterpret_cast<XCell *>(a.hash_cells) + a.hash_off[x];
+    const unsigned epoch = a.epoch;
+    const unsigned long long ekey = (unsigned long long)epoch << 32;
     long long combos = 0;
 
     for (int64_t lg = a.unit_leg_lo[x]; lg < a.unit_leg_hi[x]; ++lg) {
@@ -100,9 +112,9 @@ __global__ void __launch_bounds__(XS_THREADS) xsim_accum_kernel(xmap_xsim_args a
                     if (rem) { an = __dadd_rn(an, n2); ad = __dadd_rn(ad, d2); rem &= rem - 1u; }
                 }
                 if (leader) {
-                    const int slot = table_slot(hk, hn, hd, hsize, shift, y + 1);
+                    const int slot = table_slot(tab, hsize, shift, ekey | (unsigned)(y + 1), epoch);
                     if (slot < 0) atomicExch(a.error_flag, 2);
-                    else { hn[slot] = __dadd_rn(hn[slot], an); hd[slot] = __dadd_rn(hd[slot], ad); }
+                    else { tab[slot].num = __dadd_rn(tab[slot].num, an); tab[slot].den = __dadd_rn(tab[slot].den, ad); }
                 }
                 __syncwarp();
             }
@@ -121,77 +133,146 @@ __global__ void __launch_bounds__(XS_THREADS) xsim_merge_kernel(xmap_xsim_args a
     const int d = pair_dst[blockIdx.x], sx = pair_src[blockIdx.x];
     const int dsize = a.hash_size[d], ssize = a.hash_size[sx];
     const int dshift = table_shift(dsize);
-    int32_t *dk = a.hash_key + a.hash_off[d];
-    double *dn = a.hash_num + a.hash_off[d], *dd = a.hash_den + a.hash_off[d];
-    const int32_t *sk = a.hash_key + a.hash_off[sx];
-    const double *sn = a.hash_num + a.hash_off[sx], *sd = a.hash_den + a.hash_off[sx];
+    XCell *dt = reinterpret_cast<XCell *>(a.hash_cells) + a.hash_off[d];
+    const XCell *st = reinterpret_cast<const XCell *>(a.hash_cells) + a.hash_off[sx];
+    const unsigned epoch = a.epoch;
     for (int q = threadIdx.x; q < ssize; q += XS_THREADS) {
-        const int key = sk[q];
-        if (key == 0) continue;
-        const int slot = table_slot(dk, dn, dd, dsize, dshift, key);
+        const unsigned long long key = st[q].key;
+        if ((unsigned)(key >> 32) != epoch) continue;
+        const int slot = table_slot(dt, dsize, dshift, key, epoch);
         if (slot < 0) { atomicExch(a.error_flag, 2); continue; }
-        dn[slot] = __dadd_rn(dn[slot], sn[q]);
-        dd[slot] = __dadd_rn(dd[slot], sd[q]);
+        dt[slot].num = __dadd_rn(dt[slot].num, st[q].num);
+        dt[slot].den = __dadd_rn(dt[slot].den, st[q].den);
     }
 }
 
-// One warp per start: count the ends, pick the top-m, or emit every (end, xsim).
+constexpr int XF_BINS = 256;
+constexpr int XF_BUF = 224;                   // survivors; 224 * 12 B >= XF_BINS * 4 B
+
+// 16 sub-bins per octave for |xsim| in [2^-16, 2) (see sim_bin in sim.cu)
+__device__ __forceinline__ int xsim_bin(unsigned long long key_bits) {
+    const int hi = int((key_bits & 0x7FFFFFFFFFFFFFFFull) >> 48);
+    const int base = (1023 - 16) << 4;
+    return max(0, min(XF_BINS - 1, hi - base));
+}
+
+// One warp per start: count the ends and pick the top-m (two passes over the table: a histogram of
+// |xsim| to find the threshold bin, then the survivors), or emit every (end, xsim).
 __global__ void __launch_bounds__(XS_THREADS) xsim_finalize_kernel(xmap_xsim_args a) {
+    __shared__ __align__(16) unsigned char s_sel[XS_THREADS / 32][XF_BUF * 12];
     const int x = (blockIdx.x * XS_THREADS + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (x >= a.n_starts) return;
     const int u = a.start_unit[x];                    // the unit whose table holds the merged result
     const int hsize = a.hash_size[u];
-    const int32_t *hk = a.hash_key + a.hash_off[u];
-    const double *hn = a.hash_num + a.hash_off[u], *hd = a.hash_den + a.hash_off[u];
+    const XCell *tab = reinterpret_cast<const XCell *>(a.hash_cells) + a.hash_off[u];
+    const unsigned epoch = a.epoch;
 
     if (a.mode == 2) {  // emit every (end, xsim) of this start
         int64_t base = a.emit_ptr[x];
         int written = 0;
         for (int s0 = 0; s0 < hsize; s0 += 32) {
-            const int s = s0 + lane;
-            const int key = (s < hsize) ? hk[s] : 0;
-            const unsigned m = __ballot_sync(0xffffffffu, key != 0);
-            if (key != 0) {
+            const XCell c = tab[s0 + lane];
+            const bool occ = (unsigned)(c.key >> 32) == epoch;
+            const unsigned m = __ballot_sync(0xffffffffu, occ);
+            if (occ) {
                 const int64_t p = base + written + __popc(m & ((1u << lane) - 1u));
-                a.emit_end[p] = key - 1;
-                a.emit_xsim[p] = __ddiv_rn(hn[s], hd[s]);
+                a.emit_end[p] = int((unsigned)c.key) - 1;
+                a.emit_xsim[p] = __ddiv_rn(c.num, c.den);
             }
             written += __popc(m);
         }
         return;
     }
 
-    // count + top-m by |xsim| desc, ties to the smaller end index (generator.py:85,109)
+    // pass 1: count + histogram of |xsim|
+    unsigned *hist = reinterpret_cast<unsigned *>(s_sel[threadIdx.x >> 5]);
+    for (int b = lane; b < XF_BINS; b += 32) hist[b] = 0u;
+    __syncwarp();
     int cnt = 0;
-    for (int s = lane; s < hsize; s += 32) cnt += (hk[s] != 0);
+    for (int s = lane; s < hsize; s += 32) {
+        const XCell c = tab[s];
+        if ((unsigned)(c.key >> 32) != epoch) continue;
+        ++cnt;
+        atomicAdd(&hist[xsim_bin((unsigned long long)__double_as_longlong(__ddiv_rn(c.num, c.den)))], 1u);
+    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    __syncwarp();
     if (lane == 0) a.out_count[x] = cnt;
     const int M = min(a.top_m, cnt);
+    int bstar = 0;
+    {
+        int run = 0;
+        bool found = false;
+        for (int hb = XF_BINS - 32; hb >= 0 && !found && M > 0; hb -= 32) {
+            unsigned suf = hist[hb + lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned t = __shfl_down_sync(0xffffffffu, suf, off);
+                if (lane + off < 32) suf += t;
+            }
+            const unsigned hit = __ballot_sync(0xffffffffu, run + (int)suf >= M);
+            if (hit) { bstar = hb + (31 - __clz(hit)); found = true; }
+            else run += (int)__shfl_sync(0xffffffffu, suf, 0);
+        }
+    }
+    __syncwarp();
+    // pass 2: survivors (bin >= b*), or, if one bin holds too many equal values, plain rounds
+    unsigned long long *bkey = reinterpret_cast<unsigned long long *>(s_sel[threadIdx.x >> 5]);
+    int *bslot = reinterpret_cast<int *>(bkey + XF_BUF);
+    int nb = 0;
+    bool overflow = false;
+    for (int s0 = 0; s0 < hsize && M > 0; s0 += 32) {
+        const XCell c = tab[s0 + lane];
+        bool take = false;
+        unsigned long long kk = 0ull;
+        if ((unsigned)(c.key >> 32) == epoch) {
+            kk = abs_key(__ddiv_rn(c.num, c.den));
+            take = xsim_bin(kk) >= bstar;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, take);
+        if (nb + __popc(m) > XF_BUF) { overflow = true; break; }
+        if (take) {
+            const int pos = nb + __popc(m & ((1u << lane) - 1u));
+            bkey[pos] = kk; bslot[pos] = s0 + lane;
+        }
+        nb += __popc(m);
+    }
+    __syncwarp();
     unsigned long long last_k = ~0ull;
-    int last_t = -1;
+    int last_t = -1, got = 0;
     for (int r = 0; r < M; ++r) {
         unsigned long long bk = 0;
         int bt = 0x7FFFFFFF, bp = -1;
-        for (int s = lane; s < hsize; s += 32) {
-            const int key = hk[s];
-            if (key == 0) continue;
-            const unsigned long long kk = abs_key(__ddiv_rn(hn[s], hd[s]));
-            const int tt = key - 1;
-            // strictly after the previous winner in the total order
-            if (r > 0 && !better(last_k, last_t, kk, tt)) continue;
-            if (bp < 0 || better(kk, tt, bk, bt)) { bk = kk; bt = tt; bp = s; }
+        if (!overflow) {
+            for (int q = lane; q < nb; q += 32) {
+                const unsigned long long kk = bkey[q];
+                const int sl = bslot[q];
+                const int tt = int((unsigned)tab[sl].key) - 1;
+                if (r > 0 && !better(last_k, last_t, kk, tt)) continue;
+                if (bp < 0 || better(kk, tt, bk, bt)) { bk = kk; bt = tt; bp = sl; }
+            }
+        } else {
+            for (int s = lane; s < hsize; s += 32) {
+                const XCell c = tab[s];
+                if ((unsigned)(c.key >> 32) != epoch) continue;
+                const unsigned long long kk = abs_key(__ddiv_rn(c.num, c.den));
+                const int tt = int((unsigned)c.key) - 1;
+                if (r > 0 && !better(last_k, last_t, kk, tt)) continue;    // strictly after the previous winner
+                if (bp < 0 || better(kk, tt, bk, bt)) { bk = kk; bt = tt; bp = s; }
+            }
         }
         warp_argbest(bk, bt, bp);
         if (bp < 0) break;
         if (lane == 0) {
             a.top_end[(size_t)x * a.top_m + r] = bt;
-            a.top_xsim[(size_t)x * a.top_m + r] = __ddiv_rn(hn[bp], hd[bp]);
+            a.top_xsim[(size_t)x * a.top_m + r] = __ddiv_rn(tab[bp].num, tab[bp].den);
         }
         last_k = bk; last_t = bt;
+        got = r + 1;
     }
-    if (lane == 0) a.top_len[x] = M;
+    if (lane == 0) a.top_len[x] = got;
 }
 
 }  // namespace xmap

@@ -296,14 +296,26 @@ class XsimEngine:
         base_u = self.u0[self.unit_start] if n_units else g
         sub_ub = P[base_u + hi] - P[base_u + g] if n_units else unit_ub
         end_cap = int(torch.unique(p.rs_end).numel()) if p.rs_end.numel() else 1
-        self.hsize = torch.clamp(_pow2_at_least(2 * torch.clamp(sub_ub, max=end_cap)), min=32)
+        # distinct ends <= min(paths, reachable ends): a table of >= 1.25x that bound never fills up
+        # (worst-case load 0.8; typical load ~0.25 because several paths share an end)
+        self.hsize = torch.clamp(_pow2_at_least((5 * torch.clamp(sub_ub, max=end_cap) + 3) // 4), min=32)
         self.start_bytes = torch.zeros(n, dtype=i64, device=dev)
         if n_units:
-            self.start_bytes.index_add_(0, self.unit_start, self.hsize * 20)
+            self.start_bytes.index_add_(0, self.unit_start, self.hsize * 24)
         self.order = torch.argsort(p.ub, descending=True, stable=True)
         self.n_units = n_units
+        self._cells = None
+        self.epoch = 0
 
     # ------------------------------------------------------------------
+    def _workspace(self, n_cells):
+        """Persistent cell workspace (24 B cells), zeroed once; launches are told apart by epoch."""
+        need = n_cells * 3
+        if self._cells is None or self._cells.numel() < need:
+            self._cells = None
+            self._cells = torch.zeros(need, dtype=torch.int64, device=self.device)
+        return self._cells
+
     def _batches(self):
         order = self.order
         if order.numel() == 0:
@@ -330,9 +342,7 @@ class XsimEngine:
         hs = self.hsize[units]
         hoff = torch.cumsum(hs, 0) - hs
         total = int(hs.sum().item())
-        hkey = torch.zeros(total, dtype=torch.int32, device=dev)
-        hnum = torch.empty(total, dtype=torch.float64, device=dev)
-        hden = torch.empty(total, dtype=torch.float64, device=dev)
+        cells = self._workspace(total)
         # merge tree
         g = self.unit_g[units]
         Gu = torch.repeat_interleave(G, G)
@@ -368,7 +378,9 @@ class XsimEngine:
         a.rs_ptr = P(p.rs_ptr); a.rs_end = P(p.rs_end)
         (a.rs_e1, a.rs_m1, a.rs_f1, a.rs_e2, a.rs_m2, a.rs_f2) = [P(v) for v in p.rs_vals]
         a.hash_off = P(hoff); a.hash_size = P(hs.to(torch.int32))
-        a.hash_key, a.hash_num, a.hash_den = P(hkey), P(hnum), P(hden)
+        a.hash_cells = N.ptr(cells)
+        self.epoch += 1
+        a.epoch = self.epoch
         a.n_rounds = len(rounds) - 1
         a.round_ptr_h = C.cast(round_ptr, C.c_void_p)
         a.pair_dst, a.pair_src = P(pair_dst), P(pair_src)
