@@ -39,7 +39,7 @@ WORKLOADS = {
 METRIC = "item_pair_sims_per_sec"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
 # (profiles/), keyed by kernel group; None until captured.
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {"big_accumulate": 7.08e9}   # mean of the 3 captured launches (8.29, 8.22, 4.72 GB), profiles/r1_ncu_full_cfg2.csv
 
 
 def make_workload(name):
@@ -70,34 +70,55 @@ def workload_label(wl, method):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region."""
+    """SM clock + throttle reasons during the timed region (NVML; nvidia-smi as a fallback)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.sm, self.reasons, self.sm_max, self.stop_flag = index, [], set(), None, False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _nvml_sample(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+                          ("sw_power_cap", 0x4)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _smi_sample(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
+        f = [x.strip() for x in out.split(",")]
+        self.sm.append(float(f[0])); self.sm_max = float(f[1])
+        for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[2:6]):
+            if v.lower().startswith("active"):
+                self.reasons.add(name)
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self._nvml_sample() if self.nvml else self._smi_sample()
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.005 if self.nvml else 0.1)
 
     def summary(self):
         self.stop_flag = True
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def measured_peaks():
@@ -118,24 +139,26 @@ def _cpu_block(args):
     return P["n_pairs_total"], len(P["i"]), time.perf_counter() - t0
 
 
-def _sample(wl, lo_user, n_u):
-    m = (wl["user"] >= lo_user) & (wl["user"] < lo_user + n_u)
-    user, item = wl["user"][m].astype(np.int64) - lo_user, wl["item"][m].astype(np.int64)
+def _sample(wl, phase, stride):
+    """Every `stride`-th user starting at `phase` (a uniform sample of light and heavy users),
+    with users and items renumbered densely."""
+    m = (wl["user"] % stride) == phase
+    user, item = wl["user"][m].astype(np.int64) // stride, wl["item"][m].astype(np.int64)
+    n_u = int(user.max()) + 1 if len(user) else 1
     present = np.unique(item)
     imap = np.full(wl["n_items"], -1, dtype=np.int64); imap[present] = np.arange(len(present))
     return (user, imap[item], wl["rating"][m].astype(np.float64), n_u, len(present),
             wl["meta"]["prefix_code"][present]), int(m.sum())
 
 
-def cpu_baseline(wl, method="adjust_cosine", num_atleast=50, target_ratings=300_000, cores=1):
+def cpu_baseline(wl, method="adjust_cosine", num_atleast=50, target_ratings=250_000, cores=1):
     """oracle/restate.py (numpy/scipy restatement of baselinerSim.py:17-216) on a bounded sample of
-    the workload: `cores` disjoint slices of users of ~target_ratings ratings each, one process per
-    slice (the reference's per-task arithmetic is single-threaded)."""
-    frac = min(1.0 / cores, target_ratings / max(1, wl["nnz"]))
-    n_u = max(1, int(wl["n_users"] * frac))
+    the workload: `cores` disjoint strided user samples of ~target_ratings ratings each, one process
+    per sample (the reference's per-task arithmetic is single-threaded)."""
+    stride = max(cores, int(round(wl["nnz"] / max(1, target_ratings))))
     jobs, nr = [], 0
     for c in range(cores):
-        args, r = _sample(wl, c * n_u, n_u)
+        args, r = _sample(wl, c, stride)
         jobs.append(args + (method, num_atleast)); nr += r
     t0 = time.perf_counter()
     if cores == 1:
@@ -147,9 +170,9 @@ def cpu_baseline(wl, method="adjust_cosine", num_atleast=50, target_ratings=300_
     dt = time.perf_counter() - t0
     n_pairs = sum(r[0] for r in res)
     return {"value": n_pairs / dt, "unit": "item pairs/s", "cores": cores, "kind": "port",
-            "sample": "%d slice(s) of %d users of %s (%d ratings, %d co-rated pairs, %.1f s wall): "
+            "sample": "%d sample(s), every %d-th user of %s (%d ratings, %d co-rated pairs, %.1f s wall): "
                       "oracle/restate.py, the numpy/scipy restatement of the reference arithmetic "
-                      "(no Spark/JVM/shuffle serialisation)" % (cores, n_u, wl["name"], nr, n_pairs, dt)}
+                      "(no Spark/JVM/shuffle serialisation)" % (cores, stride, wl["name"], nr, n_pairs, dt)}
 
 
 def run_reference_arm(args):
@@ -164,7 +187,7 @@ def run_reference_arm(args):
     cores = min(os.cpu_count() or 1, 32)
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        cb = cpu_baseline(wl, method=args.method, target_ratings=120_000, cores=cores)
+        cb = cpu_baseline(wl, method=args.method, target_ratings=150_000, cores=cores)
         if s >= args.warmup:
             vals.append(cb["value"]); secs.append(time.perf_counter() - t0)
     v = float(np.mean(vals))
