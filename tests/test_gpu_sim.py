@@ -61,6 +61,28 @@ def test_heavy_rows_in_several_batches_and_chunks():
     assert np.array_equal(a["tabs"].tab_idx.cpu().numpy(), b["tabs"].tab_idx.cpu().numpy())
 
 
+@pytest.mark.parametrize("k", [1, 50, 64])
+def test_topk_sizes(k):
+    """k = 50 is BASELINE.json's large-scale configuration; 64 is the library maximum."""
+    case = PT.synth_case(5000, 800, 80000, 0.1, seed=17)
+    PT.check_sim_against_restatement(case, "cosine", 20, k)
+
+
+def test_rejects_bad_arguments():
+    import torch
+    from xmap_b200 import engine as E
+    case = PT.synth_case(300, 60, 2000, 0.2, seed=2)
+    lay = E.build_layout(case["user"], case["item"], case["rating"], case["n_users"], case["n_items"])
+    meta = PT.to_device_meta(case["meta"])
+    with pytest.raises(ValueError):
+        E.SimEngine(lay, meta, "pearson", 50, 10)
+    with pytest.raises(ValueError):
+        E.SimEngine(lay, meta, "cosine", 50, 65)
+    with pytest.raises(ValueError):
+        from xmap_b200.encode import check_ratings_f32
+        check_ratings_f32([3.1400000001])
+
+
 def test_symmetry_and_properties():
     case = PT.synth_case(3000, 500, 40000, 0.2, seed=8)
     lay, eng, tabs, pairs = PT.run_gpu_sim(case["user"], case["item"], case["rating"], case["n_users"],

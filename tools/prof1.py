@@ -1,4 +1,4 @@
-import sys, time, json; sys.path.insert(0,".")
+import sys, time, json; sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 import numpy as np, torch
 import bench
 from xmap_b200 import engine as E, _native as N
