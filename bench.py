@@ -39,7 +39,7 @@ WORKLOADS = {
 METRIC = "item_pair_sims_per_sec"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
 # (profiles/), keyed by kernel group; None until captured.
-NCU_TRAFFIC = {"big_accumulate": 7.08e9}   # mean of the 3 captured launches (8.29, 8.22, 4.72 GB), profiles/r1_ncu_full_cfg2.csv
+NCU_TRAFFIC = {}
 
 
 def make_workload(name):
@@ -249,7 +249,7 @@ def main():
     # resident layout for the device-timed metric
     lay = E.build_layout(h_user, h_item, h_rating, wl["n_users"], wl["n_items"], device=dev)
     eng = E.SimEngine(lay, meta, args.method, 50, k)
-    shard = MG.RowShard(lay.row_work, rank, world)
+    shard = MG.RowShard(eng.tri_work, rank, world)
 
     def sim_step(engine):
         return MG.similarity_step(engine, shard)
@@ -277,7 +277,7 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms.mean())
     launches = (eng.launches - l0)
-    P_total = int(tabs.row_npairs.sum().item())
+    P_total = tabs.n_pairs_total
     P_kept = int(tabs.row_nkept.sum().item())
     value = P_total / (ms_step * 1e-3)
 
@@ -285,7 +285,7 @@ def main():
     def e2e_step():
         lay2 = E.build_layout(h_user, h_item, h_rating, wl["n_users"], wl["n_items"], device=dev)
         eng2 = E.SimEngine(lay2, meta, args.method, 50, k)
-        t = MG.similarity_step(eng2, MG.RowShard(lay2.row_work, rank, world))
+        t = MG.similarity_step(eng2, MG.RowShard(eng2.tri_work, rank, world))
         out = [t.row_flags.cpu(), t.tab_len.cpu(), t.tab_idx.cpu(), t.tab_sim.cpu(), t.tab_mutu.cpu(),
                t.tab_n.cpu()]
         torch.cuda.synchronize()
@@ -327,16 +327,34 @@ def main():
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
-        alg_bytes = 8.0 * (wl["W"] + wl["nnz"]) + 12.0 * wl["nnz"] + 80.0 * k * wl["n_items"]
-        stage_gbs = alg_bytes / (ms_step * 1e-3) / 1e9          # whole similarity stage (both passes)
-        # dominant kernel: the one with the largest CUDA-event time over the timed steps
-        kinds = {kk: (n, ms) for kk, (n, ms) in prof.items()}
+        # the stage evaluates every unordered pair once: W/2 products of 8 B, one pass over the CSC
+        # (16 B per rating: entry + suffix extent), 2 x 16 B records written and read back per kept pair,
+        # and the tables out
+        alg_bytes = 8.0 * (wl["W"] / 2) + 16.0 * wl["nnz"] + 32.0 * P_kept + 80.0 * k * wl["n_items"]
+        stage_gbs = alg_bytes / (ms_step * 1e-3) / 1e9
+        # kernels: the accumulate launches are one kernel function per group width
+        launches_plan, _ = eng.plan(None if world == 1 else shard.rows(dev))
+        fam_ms, fam_n, fam_bytes = {}, {}, {}
+        for kk, (n, ms_k) in prof.items():
+            if kk.startswith("accumulate"):
+                fam = "tri_warp_kernel" if kk.endswith("_t32") else ("tri_gmem_kernel" if "_g" in kk else "tri_cta_kernel")
+            elif kk == "select_warp":
+                fam = "select_warp_kernel"
+            elif kk == "select_cta":
+                fam = "select_cta_kernel"
+            else:
+                fam = kk
+            fam_ms[fam] = fam_ms.get(fam, 0.0) + ms_k
+            fam_n[fam] = fam_n.get(fam, 0) + n
+        for r, cells_cap, threads, in_gmem in launches_plan:
+            fam = "tri_gmem_kernel" if in_gmem else ("tri_warp_kernel" if threads == 32 else "tri_cta_kernel")
+            fam_bytes[fam] = fam_bytes.get(fam, 0.0) + 8.0 * float(eng.tri_work[r.long()].sum().item())
+        long_rows = tabs.row_nkept > 2048
+        fam_bytes["select_cta_kernel"] = 16.0 * float(tabs.row_nkept[long_rows].sum().item())
+        fam_bytes["select_warp_kernel"] = 16.0 * float(tabs.row_nkept[~long_rows].sum().item())
+        kinds = {kk: (fam_n[kk], fam_ms[kk]) for kk in fam_ms}
         dom = max(kinds, key=lambda kk: kinds[kk][1])
-        tiers, big = eng.plan(None if world == 1 else shard.rows(dev))
-        work = {"warp_tier%d" % i: int(lay.row_work[t.long()].sum().item()) for i, t in enumerate(tiers)}
-        work["big_accumulate"] = int(lay.row_work[big.long()].sum().item())
-        work["big_epilogue"] = 0
-        dom_bytes_step = 8.0 * work.get(dom, 0)                 # 8 B CSR entry per co-rating product
+        dom_bytes_step = fam_bytes.get(dom, 0.0)
         dom_ms_step = kinds[dom][1] / args.steps
         achieved = dom_bytes_step / (dom_ms_step * 1e-3) / 1e9 if dom_ms_step > 0 else 0.0
         line = {
@@ -346,7 +364,7 @@ def main():
             "config": {"workload": workload_label(wl, args.method),
                        "pairs_evaluated": P_total, "pairs_kept": P_kept,
                        "l2_policy": "inputs (CSR+CSC+tables) larger than L2; no explicit flush",
-                       "parallelism": "item row-blocks x%d, ratings replicated" % world},
+                       "parallelism": "item row-blocks x%d, ratings replicated, neighbour records exchanged" % world},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "item pairs/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": float(e2e_s) * 1e3},
@@ -358,8 +376,10 @@ def main():
                          "kernel_share_of_step": dom_ms_step / ms_step,
                          "per_kernel_ms_per_step": {kk: v[1] / args.steps for kk, v in kinds.items()},
                          "stage_algorithmic_gbs": stage_gbs, "stage_frac": stage_gbs / peaks["hbm_gbs"],
-                         "note": "achieved = 8 B per co-rating product of the rows the kernel owns / its CUDA-event "
-                                 "time; stage figure = (8*(W+nnz) + 12*nnz + 80*k*I) / step time"},
+                         "per_launch_ms_per_step": {kk: v[1] / args.steps for kk, v in prof.items()},
+                         "note": "achieved = algorithmic bytes of the kernel (8 B per co-rating product for the "
+                                 "accumulate kernels, 16 B per neighbour record for the selection kernels) / its "
+                                 "CUDA-event time; stage figure = (8*W/2 + 16*nnz + 32*P_kept + 80*k*I) / step time"},
             "pipeline": pipe,
         }
         if not args.no_cpu:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define XMAP_B200_ABI_VERSION 1
+#define XMAP_B200_ABI_VERSION 2
 #define XMAP_KMAX 64                 /* largest supported top-k (extend_among_topk) */
 #define XMAP_METHOD_ADJUST_COSINE 0  /* baselinerSim.py:144-174 */
 #define XMAP_METHOD_COSINE 1         /* baselinerSim.py:115-142 */
@@ -65,95 +65,107 @@ int xmap_build_layout(const int32_t *user, const int32_t *item, const float *rat
                       void *workspace, size_t workspace_bytes, void *stream);
 
 /* Per output row i of R^T R: w[i] = sum over raters u of i of degree(u), the
- * number of co-rating products the row costs (W + nnz in total).
- * Used to plan which kernel handles which row. */
+ * number of co-rating products the full row would cost (W + nnz in
+ * total).  Bounds the length of a row's neighbour-record list and balances the
+ * multi-GPU row blocks. */
 int xmap_row_work(const int32_t *csr_ptr, const int32_t *csc_ptr, const uint64_t *csc_ent,
                   int32_t n_items, int64_t *row_work, void *stream);
 
+/* Triangular layout of the similarity stage.  Items are ranked by ascending
+ * popularity, ord[i] = rank of (count(i), i) (computed by the caller: one sort of
+ * n_items keys).  Every unordered pair {i, j} is evaluated ONCE, by the row of
+ * the less popular item, so row i only needs, for each of its raters u, the part
+ * of u's ratings that lies on more popular items.  With the user's ratings
+ * sorted by ord that part is a suffix:
+ *   tcsr_ent[k]  = { ord(item) | cls(item)<<24 | ge_avg<<29 , float bits of rating }
+ *                  same extents as csr_ptr, entries ascending by ord;
+ *   csc_aux[e]   = { pos, len }: CSC entry e = (i, u) sits at tcsr position pos, and
+ *                  the len entries after it are u's ratings of items more popular than i;
+ *   tri_work[i]  = sum of len over the raters of i = products row i evaluates
+ *                  (sum over i = W / 2);
+ *   ostat[o]     = 16 bytes per ord o: { double den; uint32 item; uint32 prefix<<8 | cls }
+ *                  den = norm2 (cosine) or adjusted norm2 (adjust_cosine) of the item,
+ *                  baselinerSim.py:131-132,164-165.
+ * workspace >= xmap_tri_workspace_bytes(nnz). */
+size_t xmap_tri_workspace_bytes(int64_t nnz);
+int xmap_build_tri_layout(const int32_t *csr_ptr, const uint64_t *csr_ent,
+                          const int32_t *csc_ptr, const uint64_t *csc_ent,
+                          const double *item_stats, const int32_t *prefix_code, const int32_t *ord,
+                          int32_t n_users, int32_t n_items, int64_t nnz, int32_t method,
+                          uint64_t *tcsr_ent, uint64_t *csc_aux, void *ostat, int64_t *tri_work,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------
- * (2) Similarity rows + fused epilogue + fused per-row top-k selection.
+ * (2) Similarity (triangular sparse R^T R) + fused epilogue, then per-row
+ * top-k selection.
  * Replaces: produce_pairwise_items + reduceByKey + calculate_*_sim +
  * retrieve_path_info + filter + detect_domain (baselinerSim.py:84-216),
  * get_item_sim (:218-233), the BB-item SQL (assist.py:82-87) and
  * ExtendSim.find_knn_items (extender.py:16-44).
  *
- * For every requested row i the kernels accumulate, over all users who rated
- * both i and j: n_ij, the mutuality count, and the inner product (fixed-point,
- * order-independent), then compute sim / mutu and apply the reference's filter
- * (sim != 0 and mutu != 0) and cross-domain label, and select neighbours.
+ * xmap_sim_accumulate: for every requested row i and every more popular item j
+ * co-rated with i, accumulates over the common raters n_ij, the mutuality count
+ * and the inner product (64-bit fixed point, order-independent), computes
+ * sim / mutu, applies the reference's filter (sim != 0 and mutu != 0) and
+ * appends one 16-byte neighbour record to the list of row i AND to the list of
+ * row j (sim(i,j) == sim(j,i) bitwise, so the pair is never evaluated twice):
+ *   rec[rec_ptr[r] + p] = { bits of sim (f64) , other_item | n<<24 | mutu<<44 }
+ *   p = atomic cursor rec_cnt[r]; order within a list is unspecified.
+ * The lists are the materialised return value of baseliner_calculate_sim_pipeline
+ * (assist.py:66-77).  bb[r] is set to 1 for both ends of a kept cross-domain pair
+ * (label by 2-character prefix, baselinerSim.py:191; the BB set of assist.py:84-86).
+ * row_npairs[i] += co-rated columns row i evaluated (pre-filter).
+ * rec_cnt, bb, row_npairs must be zero on entry of the first call of a stage.
  *
- * mode 0 (pass 1): writes row_flags bit0 = "i is a bridge (BB) item",
- *     row_npairs = #co-rated j, row_nkept = #kept j, and
- *       BB row : table slot 0 = BB_BB (top-k other-domain), slot 1 = BB_NB
- *       NB row : table slot 1 = NB_NN (top-k of all kept neighbours)
- * mode 1 (pass 2, NB rows only, needs bb_in = flags of ALL items):
- *       NB row : table slot 0 = NB_BB (top-k neighbours that are BB)
- * mode 2 (emit): appends every kept (j, sim, mutu, n) of row i at
- *     emit_ptr[i] .. (order within a row unspecified) -- the materialised
- *     return value of baseliner_calculate_sim_pipeline (assist.py:66-77).
- * Tables are [n_items][2][k]; ordering = |sim| descending, ties to the smaller
- * item index (SURVEY.md App. A.6 rule 3).
+ * A row's accumulator lives in shared memory: a direct-indexed table when the
+ * row has few more-popular columns (the popular rows), otherwise an open-
+ * addressing hash of ceil(4/3 * tri_work) cells; 32-bit shared-memory atomics.
+ *   threads_per_row = 32  : one warp per row, 4 rows per CTA (no CTA barrier)
+ *   threads_per_row > 32  : one CTA of that many threads per row
+ *   cells_cap             : table capacity (16-byte cells) of every row in `rows`
+ *   gtab != NULL          : tables in global memory instead (rows too large for shared
+ *                           memory); gtab holds gtab_ctas * cells_cap cells.
  * ------------------------------------------------------------------------- */
 typedef struct xmap_sim_args {
     /* layout */
-    const int32_t *csr_ptr; const uint64_t *csr_ent;
-    const int32_t *csc_ptr; const uint64_t *csc_ent;
-    const double *user_mu; const double *item_stats;
+    const int32_t *csc_ptr; const uint64_t *csc_ent; const uint64_t *csc_aux;
+    const uint64_t *tcsr_ent; const double *user_mu;
+    const void *ostat; const int32_t *ord; const int64_t *tri_work;
     /* per-item codes (host-computed from the id strings) */
-    const int32_t *prefix_code;    /* iid[:2]  -- baselinerSim.py:191 */
     const uint8_t *dom_code;       /* iid[-2:] -- extender.py:29     */
     const uint8_t *contains;       /* bit d: label d is a substring of iid -- extender.py:32,34 */
-    const uint8_t *bb_in;          /* mode 1 only */
-    const int64_t *row_work;       /* from xmap_row_work; sizes the per-row hash */
     int32_t n_items; int32_t method; int32_t num_atleast; int32_t k;
     int32_t r2_bits;               /* ceil(log2(max |product|)) for the fixed-point scale */
-    int32_t mode;
-    /* outputs */
-    uint8_t *row_flags; int32_t *row_npairs; int32_t *row_nkept;
+    int32_t pad0;
+    /* neighbour-record lists */
+    const int64_t *rec_ptr;        /* [n_items + 1] list extents (capacity) */
+    int32_t *rec_cnt;              /* [n_items] cursors = list lengths */
+    void *rec;                     /* 16-byte records */
+    uint8_t *bb;                   /* [n_items] bridge-item flags */
+    int32_t *row_npairs;           /* [n_items] */
+    /* selection output: tables [n_items][2][k] */
     int32_t *tab_idx; double *tab_sim; int32_t *tab_mutu; int32_t *tab_n; int32_t *tab_len;
-    /* emit (mode 2) */
-    const int64_t *emit_ptr; int32_t *emit_j; double *emit_sim; int32_t *emit_mutu; int32_t *emit_n;
-    int32_t *emit_cursor;          /* [n_items] zero-initialised */
-    int32_t *error_flag;           /* device int, set nonzero on table overflow */
+    int32_t *error_flag;           /* device int: 1 table overflow, 2 list capacity, 3 count range */
 } xmap_sim_args;
 
-/* Rows whose products fit one hash table: ONE WARP per row, private table, no barriers.
- *   tier 0: row_work <= 350   (512 slots, shared memory)
- *   tier 1: row_work <= 700   (1024 slots, shared memory)
- *   tier 2: row_work <= 1400  (2048 slots, shared memory)
- *   tier 3: row_work <= 5600  (8192 slots in a per-warp slice of `workspace`, persistent warps)
- *   tier 4: row_work <= 22000 (32768 slots, likewise)
- * workspace >= xmap_sim_rows_workspace_bytes(tier) (0 for the shared-memory tiers). */
-#define XMAP_SIM_TIER0_MAXWORK 350
-#define XMAP_SIM_TIER1_MAXWORK 700
-#define XMAP_SIM_TIER2_MAXWORK 1400
-#define XMAP_SIM_TIER3_MAXWORK 5600
-#define XMAP_SIM_TIER4_MAXWORK 22000
-size_t xmap_sim_rows_workspace_bytes(int32_t tier);
-int xmap_sim_rows(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows, int32_t tier,
-                  void *workspace, size_t workspace_bytes, void *stream);
+#define XMAP_SIM_MAX_SMEM_CELLS 14336     /* 224 KB of 16-byte cells */
+/* cells a row needs: min(#more popular items, ceil(4/3 * tri_work)), at least 32 */
+int64_t xmap_sim_row_cells(int64_t tri_work, int32_t n_more_popular);
+int xmap_sim_accumulate(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
+                        int32_t cells_cap, int32_t threads_per_row,
+                        void *gtab, int32_t gtab_ctas, void *stream);
 
-/* Heavy rows: each row is cut into chunks of raters; chunks accumulate into a
- * dense per-row table in HBM/L2 with 64-bit integer atomics (order-free, so
- * the result does not depend on the chunking or the GPU count), then one CTA
- * per row runs the same epilogue + selection.
- *   table   : [n_slots][n_items] 16-byte cells, zero on entry, zero on exit
- *   touched : [n_slots][n_items] int32 scratch; touched_n: [n_slots] zero on entry/exit
- *   row rows[b] uses table slot b; work is fetched by warps in groups of 128 raters, row-major.
- *   A dense-scanned row (touched >= n_items/8) takes n_items candidate records in the epilogue. */
-int xmap_sim_big_accumulate(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
-                            const int64_t *grp_off /* [n_rows+1] scan of ceil(raters/128) */,
-                            uint64_t *table, int32_t *touched, int32_t *touched_n,
-                            int32_t *work_counter /* device int, zero on entry */, void *stream);
-/* Epilogue of the heavy rows in three launches: scan of touched_n, a grid-wide evaluation of
- * every touched cell (similarity, filter, label -> compact candidate records; clears the
- * table), and one CTA per row for the top-k selection over its candidate records.
- * `capacity` = upper bound on the batch's touched cells (sum over rows of min(row_work, n_items));
- * scratch >= xmap_sim_big_scratch_bytes(n_rows, capacity).  Mode 2 needs emit_cursor zeroed. */
-size_t xmap_sim_big_scratch_bytes(int32_t n_rows, int64_t capacity);
-int xmap_sim_big_finalize(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
-                          uint64_t *table, int32_t *touched, int32_t *touched_n,
-                          int64_t capacity, void *scratch, size_t scratch_bytes, void *stream);
+/* Per-row top-k selection over the neighbour-record lists (extender.py:16-44), after
+ * every rank's records are in place and bb holds the flags of ALL items:
+ *   BB row : table slot 0 = BB_BB (top-k other-domain), slot 1 = BB_NB (top-k same-domain)
+ *   NB row : table slot 0 = NB_BB (top-k neighbours that are BB), slot 1 = NB_NN (top-k of all)
+ * Ordering = |sim| descending, ties to the smaller item index (SURVEY.md App. A.6 rule 3).
+ * long_rows = 0: one warp per row, rows with more than XMAP_SELECT_LONG records are skipped;
+ * long_rows = 1: one CTA per row, only rows with more than XMAP_SELECT_LONG records are done.
+ * rows == NULL means all rows 0 .. n_rows-1. */
+#define XMAP_SELECT_LONG 2048
+int xmap_sim_select(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
+                    int32_t long_rows, void *stream);
 
 /* ---------------------------------------------------------------------------
  * (3) X-SIM extension: masked path composition with fused aggregation.

@@ -1,4 +1,4 @@
-"""Run under torchrun on >= 2 GPUs: the sharded similarity stage (NCCL all-gathers) must be
+"""Run under torchrun on >= 2 GPUs: the sharded similarity stage (NCCL record all-to-all, flag all-reduce, table all-gathers) must be
 bit-identical to the single-GPU result.  (Not collected by pytest; the exchange logic itself is
 covered on CPU by tests/test_multi_gloo.py.)"""
 import os
@@ -23,7 +23,7 @@ def main():
     lay = E.build_layout(case["user"], case["item"], case["rating"], case["n_users"], case["n_items"], device=dev)
     ref = E.SimEngine(lay, meta, "adjust_cosine", 50, 10).run()
     eng = E.SimEngine(lay, meta, "adjust_cosine", 50, 10)
-    tabs = MG.similarity_step(eng, MG.RowShard(lay.row_work, rank, world))
+    tabs = MG.similarity_step(eng, MG.RowShard(eng.tri_work, rank, world))
     eng._check_error()
     ok = all(torch.equal(getattr(ref, f), getattr(tabs, f)) for f in
              ("row_flags", "row_npairs", "row_nkept", "tab_len", "tab_idx", "tab_sim", "tab_mutu", "tab_n"))

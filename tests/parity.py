@@ -65,11 +65,11 @@ def synth_case(n_users, n_items, n_draws, overlap, seed, half=False):
 
 
 def run_gpu_sim(user, item, rating, n_users, n_items, meta, method, num_atleast, k, emit=True,
-                table_budget=None):
+                max_smem_cells=None):
     import torch
     from xmap_b200 import engine as E
     lay = E.build_layout(user, item, rating, n_users, n_items)
-    kw = {} if table_budget is None else dict(table_budget=table_budget)
+    kw = {} if max_smem_cells is None else dict(max_smem_cells=max_smem_cells)
     eng = E.SimEngine(lay, to_device_meta(meta), method, num_atleast, k, **kw)
     tabs = eng.run()
     pairs = eng.emit_pairs() if emit else None
@@ -201,17 +201,17 @@ def restate_lists(knn, pairs):
     return out
 
 
-def check_sim_against_restatement(case, method, num_atleast, k, table_budget=None):
+def check_sim_against_restatement(case, method, num_atleast, k, max_smem_cells=None):
     from oracle import restate as RS
     lay, eng, tabs, pairs = run_gpu_sim(case["user"], case["item"], case["rating"], case["n_users"],
                                         case["n_items"], case["meta"], method, num_atleast, k,
-                                        table_budget=table_budget)
+                                        max_smem_cells=max_smem_cells)
     P = RS.sim_pairs(case["user"], case["item"], case["rating"], case["n_users"], case["n_items"],
                      case["meta"]["prefix_code"], method, num_atleast)
     compare_layout(lay, P["stats"])
     rel, fragile = compare_pairs(pairs, P["i"], P["j"], P["sim"], P["mutu"], P["frac"], P["label"],
                                  case["n_items"])
-    assert int(tabs.row_npairs.sum().item()) == P["n_pairs_total"], "co-rated pair count differs"
+    assert tabs.n_pairs_total == P["n_pairs_total"], "co-rated pair count differs"
     knn = RS.select_knn(P, case["n_items"], k, case["meta"]["dom_code"], case["meta"]["contains"])
     n_items = case["n_items"]
     pkey = P["i"].astype(np.int64) * n_items + P["j"]          # sorted by construction

@@ -29,36 +29,57 @@ def test_sim_matches_reference_golden(name):
     PT.compare_knn(tabs, g["bb"], g["valid_nb"], lists)
 
 
+def _kinds(out):
+    return [k for k, _ in out["tabs"].stats["accumulate"]]
+
+
 @pytest.mark.parametrize("method", ["adjust_cosine", "cosine"])
 def test_sim_all_tiers_vs_restatement(method):
-    """Large enough that the warp tiers (0-3 here; tier 4 needs bigger rows) and the heavy (dense table) path run."""
+    """Large enough that warp-per-row and CTA-per-row launches of several table sizes run, with both
+    hashed and direct-indexed tables, and that the long-list selection kernel is exercised."""
     case = PT.synth_case(20000, 3000, 400000, 0.05, seed=11, half=(method == "cosine"))
     out = PT.check_sim_against_restatement(case, method, 50, 10)
-    st = out["tabs"].stats["pass1"]
-    assert all(n > 0 for n in st["tiers"][:4]) and (st["tiers"][4] + st["big"]) > 0, st
+    kinds = _kinds(out)
+    assert any(k.endswith("_t32") for k in kinds) and any(not k.endswith("_t32") for k in kinds), kinds
+    assert len(kinds) >= 4, kinds
+    eng = out["eng"]
+    assert int((eng.rec_cnt > 2048).sum()) > 0            # long rows: select_cta_kernel
+    I = case["n_items"]
+    rtop = (I - 1 - eng.ord).long()
+    h = ((eng.tri_work * 4 + 2) // 3).clamp(min=32)
+    live = eng.tri_work > 0
+    assert int(((rtop <= h) & live).sum()) > 0 and int(((rtop > h) & live).sum()) > 0   # direct and hashed rows
 
 
-def test_heavy_rows_sparse_and_dense_modes():
-    """A wider catalogue: heavy rows below 2*n_items products go through first-touch lists, the
-    heaviest through the reduction-only dense mode; both against the restatement."""
-    import torch
+def test_wide_catalogue():
+    """A wider catalogue (more hashed rows, bigger tables), against the restatement."""
     case = PT.synth_case(30000, 12000, 500000, 0.05, seed=13)
     out = PT.check_sim_against_restatement(case, "adjust_cosine", 50, 10)
-    w = out["lay"].row_work
-    big = w > 22000
-    assert int((big & (w < 2 * case["n_items"])).sum()) > 0 and int((w >= 2 * case["n_items"]).sum()) > 0
-    assert out["tabs"].stats["pass1"]["tiers"][4] > 0
+    assert out["tabs"].n_pairs_total == out["P"]["n_pairs_total"]
 
 
-def test_heavy_rows_in_several_batches_and_chunks():
-    """Tiny table budget -> the heavy tier runs in many batches; results must not change."""
+def test_global_memory_tables_give_identical_results():
+    """Tiny shared-memory table limit -> most rows run with their table in global memory (the
+    fallback for rows that exceed shared memory); results must not change."""
     case = PT.synth_case(6000, 1200, 120000, 0.1, seed=5)
     a = PT.check_sim_against_restatement(case, "adjust_cosine", 50, 7)
-    per_row = case["n_items"] * 20 + 4
-    b = PT.check_sim_against_restatement(case, "adjust_cosine", 50, 7, table_budget=3 * per_row)
+    b = PT.check_sim_against_restatement(case, "adjust_cosine", 50, 7, max_smem_cells=64)
+    assert any("accumulate_g" in k for k in _kinds(b)) and not any("accumulate_g" in k for k in _kinds(a))
     for k in ("i", "j", "sim", "mutu", "n"):
         assert np.array_equal(a["pairs"][k].cpu().numpy(), b["pairs"][k].cpu().numpy()), k
-    assert np.array_equal(a["tabs"].tab_idx.cpu().numpy(), b["tabs"].tab_idx.cpu().numpy())
+    for t in ("tab_idx", "tab_sim", "tab_len", "row_flags"):
+        assert np.array_equal(getattr(a["tabs"], t).cpu().numpy(), getattr(b["tabs"], t).cpu().numpy()), t
+
+
+def test_rerun_is_idempotent():
+    """Running the stage twice on the same engine gives the same tables (cursors / flags reset)."""
+    case = PT.synth_case(3000, 500, 40000, 0.2, seed=9)
+    lay, eng, tabs, pairs = PT.run_gpu_sim(case["user"], case["item"], case["rating"], case["n_users"],
+                                           case["n_items"], case["meta"], "adjust_cosine", 50, 10)
+    first = {t: getattr(tabs, t).clone() for t in ("tab_idx", "tab_sim", "tab_len", "row_flags", "row_nkept")}
+    tabs2 = eng.run()
+    for t, v in first.items():
+        assert bool((getattr(tabs2, t) == v).all()), t
 
 
 @pytest.mark.parametrize("k", [1, 50, 64])
@@ -109,11 +130,11 @@ def test_degenerate_inputs():
     # users with one rating each: no co-rated pair at all
     lay, eng, tabs, pairs = PT.run_gpu_sim(np.array([0, 1, 2]), np.array([0, 1, 2]), np.array([5., 3., 1.]),
                                            3, 3, meta, "cosine", 50, 5)
-    assert len(pairs["i"]) == 0 and int(tabs.row_npairs.sum()) == 0
+    assert len(pairs["i"]) == 0 and tabs.n_pairs_total == 0
     # everybody gives 4 stars: adjusted cosine inner products are exactly 0 -> all filtered
     u = np.repeat(np.arange(4), 3); it = np.tile(np.arange(3), 4)
     lay, eng, tabs, pairs = PT.run_gpu_sim(u, it, np.full(12, 4.0), 4, 3, meta, "adjust_cosine", 50, 5)
-    assert int(tabs.row_npairs.sum()) == 6 and len(pairs["i"]) == 0
+    assert tabs.n_pairs_total == 6 and len(pairs["i"]) == 0
     lay, eng, tabs, pairs = PT.run_gpu_sim(u, it, np.full(12, 4.0), 4, 3, meta, "cosine", 50, 5)
     assert len(pairs["i"]) == 6
     torch.cuda.synchronize()

@@ -1,4 +1,4 @@
-"""CPU, world_size 2, gloo: work-balanced row sharding and the table all-gather."""
+"""CPU, world_size 2, gloo: work-balanced row sharding, the neighbour-record exchange and the table all-gather."""
 import os
 import socket
 
@@ -50,6 +50,50 @@ def test_row_shard_and_allgather_world2():
     assert all(ok for _, ok, _ in res)
     loads = res[0][2]
     assert max(loads) / (sum(loads) / 2) < 1.25        # blocks balanced by work, not by row count
+
+
+def _exchange_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from xmap_b200.multi import RowShard, exchange_records
+    I = 257
+    g = torch.Generator().manual_seed(5)
+    cap = torch.randint(0, 9, (I,), generator=g) * world
+    ptr = torch.zeros(I + 1, dtype=torch.int64); ptr[1:] = torch.cumsum(cap, 0)
+    sh = RowShard(cap + 1, rank, world)
+    # rank r produced, for row i, (i * 7 + r) % (cap/world + 1) records tagged (i, r, position)
+    def produced(r):
+        return torch.minimum((torch.arange(I) * 7 + r) % 5, cap // world)
+    cnt = produced(rank).to(torch.int32)
+    rec = torch.full((int(ptr[-1]) + 1, 2), -1, dtype=torch.int64)
+    for i in range(I):
+        for p in range(int(cnt[i])):
+            rec[int(ptr[i]) + p, 0] = i * 1000 + rank * 100 + p
+            rec[int(ptr[i]) + p, 1] = rank
+    exchange_records(rec, ptr, cnt, sh)
+    ok = True
+    for i in range(I):
+        want = sorted(i * 1000 + r * 100 + p for r in range(world) for p in range(int(produced(r)[i]))) \
+            if sh.lo <= i < sh.hi else []
+        got = sorted(rec[int(ptr[i]):int(ptr[i]) + int(cnt[i]), 0].tolist())
+        ok = ok and got == want
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_record_exchange_world2():
+    from tests import parity  # noqa: F401
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
 
 
 def test_row_shard_single_rank_and_edge_cases():

@@ -12,23 +12,22 @@ LIB_PATH = os.path.join(_HERE, "libxmap_b200.so")
 
 KMAX = 64
 METHODS = {"adjust_cosine": 0, "cosine": 1}
-TIER_MAXWORK = (350, 700, 1400, 5600, 22000)     # XMAP_SIM_TIER{0..4}_MAXWORK
+SELECT_LONG = 2048            # XMAP_SELECT_LONG
+ABI_VERSION = 2
 
 _p = C.c_void_p
 
 
 class SimArgs(C.Structure):
     _fields_ = [
-        ("csr_ptr", _p), ("csr_ent", _p), ("csc_ptr", _p), ("csc_ent", _p),
-        ("user_mu", _p), ("item_stats", _p),
-        ("prefix_code", _p), ("dom_code", _p), ("contains", _p), ("bb_in", _p),
-        ("row_work", _p),
+        ("csc_ptr", _p), ("csc_ent", _p), ("csc_aux", _p), ("tcsr_ent", _p), ("user_mu", _p),
+        ("ostat", _p), ("ord", _p), ("tri_work", _p),
+        ("dom_code", _p), ("contains", _p),
         ("n_items", C.c_int32), ("method", C.c_int32), ("num_atleast", C.c_int32),
-        ("k", C.c_int32), ("r2_bits", C.c_int32), ("mode", C.c_int32),
-        ("row_flags", _p), ("row_npairs", _p), ("row_nkept", _p),
+        ("k", C.c_int32), ("r2_bits", C.c_int32), ("pad0", C.c_int32),
+        ("rec_ptr", _p), ("rec_cnt", _p), ("rec", _p), ("bb", _p), ("row_npairs", _p),
         ("tab_idx", _p), ("tab_sim", _p), ("tab_mutu", _p), ("tab_n", _p), ("tab_len", _p),
-        ("emit_ptr", _p), ("emit_j", _p), ("emit_sim", _p), ("emit_mutu", _p), ("emit_n", _p),
-        ("emit_cursor", _p), ("error_flag", _p),
+        ("error_flag", _p),
     ]
 
 
@@ -58,12 +57,12 @@ _SIGS = {
     "xmap_build_layout": (C.c_int, [_p, _p, _p, C.c_int64, C.c_int32, C.c_int32,
                                     _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "xmap_row_work": (C.c_int, [_p, _p, _p, C.c_int32, _p, _p]),
-    "xmap_sim_rows_workspace_bytes": (C.c_size_t, [C.c_int32]),
-    "xmap_sim_rows": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, C.c_int32, _p, C.c_size_t, _p]),
-    "xmap_sim_big_accumulate": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, _p, _p, _p, _p, _p, _p]),
-    "xmap_sim_big_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
-    "xmap_sim_big_finalize": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, _p, _p, _p,
-                                        C.c_int64, _p, C.c_size_t, _p]),
+    "xmap_tri_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "xmap_build_tri_layout": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, C.c_int32, C.c_int32, C.c_int64, C.c_int32,
+                                        _p, _p, _p, _p, _p, C.c_size_t, _p]),
+    "xmap_sim_row_cells": (C.c_int64, [C.c_int64, C.c_int32]),
+    "xmap_sim_accumulate": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, C.c_int32, C.c_int32, _p, C.c_int32, _p]),
+    "xmap_sim_select": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, C.c_int32, _p]),
     "xmap_xsim_extend": (C.c_int, [C.POINTER(XsimArgs), _p]),
     "xmap_choose_mapping": (C.c_int, [_p, _p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_double, C.c_int32, C.c_int32, _p, C.c_uint64, _p, _p]),
@@ -95,7 +94,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.xmap_abi_version() != 1:
+        if L.xmap_abi_version() != ABI_VERSION:
             raise NativeError("libxmap_b200.so ABI version mismatch")
         _lib = L
     return _lib

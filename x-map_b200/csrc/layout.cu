@@ -118,6 +118,71 @@ __global__ void row_work_kernel(const int32_t *__restrict__ csr_ptr, const int32
     if (lane == 0) work[i] = w;
 }
 
+// ---- triangular layout (see include/xmap_b200.h) ---------------------------------------------
+struct __align__(16) OStat {
+    double den;
+    uint32_t item;
+    uint32_t prefix_cls;      // prefix << 8 | cls
+};
+
+// key = user << 32 | ord(item), value = the CSR entry with the item replaced by its ord
+__global__ void tri_keys_kernel(const int32_t *__restrict__ csr_ptr, const uint64_t *__restrict__ csr_ent,
+                                const int32_t *__restrict__ ord, int32_t n_users, int64_t nnz,
+                                uint64_t *__restrict__ keys, uint64_t *__restrict__ vals) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= nnz) return;
+    int32_t lo = 0, hi = n_users;                       // largest u with csr_ptr[u] <= k
+    while (hi - lo > 1) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (__ldg(csr_ptr + mid) <= k) lo = mid; else hi = mid;
+    }
+    const uint64_t e = csr_ent[k];
+    const uint32_t w0 = (uint32_t)e;
+    const uint32_t o = (uint32_t)__ldg(ord + (w0 & ITEM_MASK));
+    keys[k] = ((uint64_t)(uint32_t)lo << 32) | o;
+    vals[k] = (e & 0xFFFFFFFF00000000ull) | (uint64_t)((w0 & ~ITEM_MASK) | o);
+}
+
+// One warp per item: position of (i, u) in u's ord-sorted row, suffix length, row work.
+__global__ void tri_aux_kernel(const int32_t *__restrict__ csr_ptr, const int32_t *__restrict__ csc_ptr,
+                               const uint64_t *__restrict__ csc_ent, const uint64_t *__restrict__ tcsr_ent,
+                               const int32_t *__restrict__ ord, int32_t n_items,
+                               uint64_t *__restrict__ csc_aux, int64_t *__restrict__ tri_work) {
+    int32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n_items) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t oi = (uint32_t)ord[i];
+    long long w = 0;
+    for (int32_t e = csc_ptr[i] + lane; e < csc_ptr[i + 1]; e += 32) {
+        const uint32_t u = (uint32_t)(csc_ent[e] & 0x7FFFFFFFu);
+        int32_t lo = csr_ptr[u], hi = csr_ptr[u + 1];
+        const int32_t end = hi;
+        while (hi - lo > 1) {                           // largest pos with ord(pos) <= oi
+            const int32_t mid = (lo + hi) >> 1;
+            if (((uint32_t)__ldg(tcsr_ent + mid) & ITEM_MASK) <= oi) lo = mid; else hi = mid;
+        }
+        const int32_t len = end - lo - 1;
+        csc_aux[e] = ((uint64_t)(uint32_t)len << 32) | (uint32_t)lo;
+        w += len;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) w += __shfl_xor_sync(0xffffffffu, w, off);
+    if (lane == 0) tri_work[i] = w;
+}
+
+__global__ void tri_ostat_kernel(const double *__restrict__ item_stats, const int32_t *__restrict__ prefix_code,
+                                 const int32_t *__restrict__ ord, int32_t n_items, int32_t method,
+                                 OStat *__restrict__ ostat) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const double *s = item_stats + 4 * (int64_t)i;
+    OStat o;
+    o.den = (method == XMAP_METHOD_COSINE) ? s[1] : s[2];
+    o.item = (uint32_t)i;
+    o.prefix_cls = ((uint32_t)prefix_code[i] << 8) | (uint32_t)ceil_log2_u32((uint32_t)s[3]);
+    ostat[ord[i]] = o;
+}
+
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct LayoutWs {
@@ -220,6 +285,48 @@ extern "C" int xmap_row_work(const int32_t *csr_ptr, const int32_t *csc_ptr, con
     if (n_items == 0) return 0;
     row_work_kernel<<<(unsigned)(((int64_t)n_items * 32 + T - 1) / T), T, 0, st>>>(csr_ptr, csc_ptr, csc_ent,
                                                                                   n_items, row_work);
+    XMAP_LAUNCH_CHECK();
+    return 0;
+}
+
+static size_t tri_ws(int64_t nnz, size_t *cub_bytes_out) {
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
+                                    (const uint64_t *)nullptr, (uint64_t *)nullptr, (int64_t)nnz, 0, 64);
+    if (cub_bytes_out) *cub_bytes_out = cub_bytes;
+    return 3 * align_up((size_t)nnz * 8) + align_up(cub_bytes) + 256;
+}
+
+extern "C" size_t xmap_tri_workspace_bytes(int64_t nnz) { return tri_ws(nnz, nullptr); }
+
+extern "C" int xmap_build_tri_layout(const int32_t *csr_ptr, const uint64_t *csr_ent,
+                                     const int32_t *csc_ptr, const uint64_t *csc_ent,
+                                     const double *item_stats, const int32_t *prefix_code, const int32_t *ord,
+                                     int32_t n_users, int32_t n_items, int64_t nnz, int32_t method,
+                                     uint64_t *tcsr_ent, uint64_t *csc_aux, void *ostat, int64_t *tri_work,
+                                     void *workspace, size_t workspace_bytes, void *stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int T = 256;
+    if (n_items > 0) {
+        tri_ostat_kernel<<<(n_items + T - 1) / T, T, 0, st>>>(item_stats, prefix_code, ord, n_items, method,
+                                                              reinterpret_cast<OStat *>(ostat));
+        XMAP_LAUNCH_CHECK();
+        XMAP_CUDA(cudaMemsetAsync(tri_work, 0, sizeof(int64_t) * (size_t)n_items, st));
+    }
+    if (nnz == 0) return 0;
+    size_t cub_bytes = 0;
+    if (workspace_bytes < tri_ws(nnz, &cub_bytes)) return fail_msg("xmap_build_tri_layout: workspace too small");
+    char *base = (char *)workspace;
+    const size_t seg = align_up((size_t)nnz * 8);
+    uint64_t *keys_a = (uint64_t *)base, *keys_b = (uint64_t *)(base + seg), *vals_a = (uint64_t *)(base + 2 * seg);
+    void *cub_ws = base + 3 * seg;
+    const unsigned gN = (unsigned)((nnz + T - 1) / T);
+    tri_keys_kernel<<<gN, T, 0, st>>>(csr_ptr, csr_ent, ord, n_users, nnz, keys_a, vals_a);
+    XMAP_LAUNCH_CHECK();
+    XMAP_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys_a, keys_b, vals_a, tcsr_ent, nnz, 0,
+                                              32 + bits_for(n_users), st));
+    tri_aux_kernel<<<(unsigned)(((int64_t)n_items * 32 + T - 1) / T), T, 0, st>>>(
+        csr_ptr, csc_ptr, csc_ent, tcsr_ent, ord, n_items, csc_aux, tri_work);
     XMAP_LAUNCH_CHECK();
     return 0;
 }

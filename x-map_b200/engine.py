@@ -14,9 +14,6 @@ import torch
 
 from . import _native as N
 
-RATER_GROUP = 128                # raters per unit of heavy-row work (matches sim.cu)
-BIG_TABLE_BUDGET = 8 << 30       # bytes of HBM for heavy-row tables per batch
-BIG_CAND_CAPACITY = 96 << 20     # candidate records (21 B each) per heavy-row batch
 
 
 def _stream_ptr():
@@ -102,12 +99,13 @@ def r2_bits_for(method, r_min, r_max):
 
 @dataclass
 class SimTables:
-    """Output of the similarity + selection stage for the rows this rank owns."""
+    """Output of the similarity + selection stage."""
     k: int
     n_items: int
-    row_flags: torch.Tensor       # uint8 [I]  bit0: bridge (BB) item
-    row_npairs: torch.Tensor      # int32 [I]  co-rated neighbours (pre-filter)
-    row_nkept: torch.Tensor       # int32 [I]  neighbours surviving the filter
+    row_flags: torch.Tensor       # uint8 [I]  1: bridge (BB) item
+    row_npairs: torch.Tensor      # int32 [I]  co-rated pairs (pre-filter) row i evaluated: the pairs (i, j)
+                                  #            with j more popular than i; 2 * sum = directed co-rated pairs
+    row_nkept: torch.Tensor       # int32 [I]  neighbours surviving the filter (= length of the record list)
     tab_idx: torch.Tensor         # int32 [I,2,k]
     tab_sim: torch.Tensor         # f64   [I,2,k]
     tab_mutu: torch.Tensor        # int32 [I,2,k]
@@ -116,12 +114,33 @@ class SimTables:
     launches: int = 0
     stats: dict = field(default_factory=dict)
 
+    @property
+    def n_pairs_total(self):
+        """Directed co-rated item pairs evaluated (P)."""
+        return 2 * int(self.row_npairs.sum().item())
+
+
+CELL_CLASSES = (256, 512, 1024, 2048, 4096, 8192, 14336)   # table capacities (16-byte cells) of the launches
+CELL_THREADS = (32, 32, 32, 128, 256, 512, 512)            # threads per row each capacity gets at least
+REC_BYTES = 16
+REC_CNT_LIMIT = 1 << 20                                     # n and mutu are 20-bit fields of a record
+
+
+def popularity_order(count):
+    """ord[i] = rank of (count(i), i) ascending; the most popular item gets the largest ord."""
+    I = int(count.numel())
+    key = count.long() * (1 << 24) + torch.arange(I, device=count.device)
+    perm = torch.argsort(key)
+    ord_ = torch.empty(I, dtype=torch.int32, device=count.device)
+    ord_[perm] = torch.arange(I, dtype=torch.int32, device=count.device)
+    return ord_
+
 
 class SimEngine:
     """Similarity + top-k selection over a Layout (C ABI section 2)."""
 
     def __init__(self, layout, meta, method="adjust_cosine", num_atleast=50, k=10,
-                 table_budget=BIG_TABLE_BUDGET):
+                 max_smem_cells=CELL_CLASSES[-1]):
         if method not in N.METHODS:
             raise ValueError("unknown similarity method %r" % (method,))
         if not (1 <= k <= N.KMAX):
@@ -130,99 +149,119 @@ class SimEngine:
         self.method, self.num_atleast, self.k = method, int(num_atleast), int(k)
         self.device = layout.csr_ptr.device
         self.r2_bits = r2_bits_for(method, layout.r_min, layout.r_max)
-        self.table_budget = table_budget
+        self.max_smem_cells = int(max_smem_cells)
         self.launches = 0
         I = layout.n_items
         dev = self.device
-        self.error_flag = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.row_flags = torch.zeros(I, dtype=torch.uint8, device=dev)
+        L = N.lib()
+        # ---- triangular layout -------------------------------------------------------------------
+        count = layout.item_stats[:, 3]
+        if I and float(count.max()) >= REC_CNT_LIMIT:
+            raise N.NativeError("an item has >= 2^20 ratings: neighbour records hold 20-bit co-rating counts")
+        self.ord = popularity_order(count)
+        self.tcsr_ent = torch.empty(layout.nnz, dtype=torch.int64, device=dev)
+        self.csc_aux = torch.empty(layout.nnz, dtype=torch.int64, device=dev)
+        self.ostat = torch.empty(max(I, 1) * 16, dtype=torch.uint8, device=dev)
+        self.tri_work = torch.zeros(I, dtype=torch.int64, device=dev)
+        ws_bytes = L.xmap_tri_workspace_bytes(layout.nnz)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        N.check(L.xmap_build_tri_layout(
+            N.ptr(layout.csr_ptr), N.ptr(layout.csr_ent), N.ptr(layout.csc_ptr), N.ptr(layout.csc_ent),
+            N.ptr(layout.item_stats), N.ptr(meta.prefix_code), N.ptr(self.ord),
+            layout.n_users, I, layout.nnz, N.METHODS[method],
+            N.ptr(self.tcsr_ent), N.ptr(self.csc_aux), N.ptr(self.ostat), N.ptr(self.tri_work),
+            N.ptr(ws), ws_bytes, _stream_ptr()), "xmap_build_tri_layout")
+        del ws
+        # ---- neighbour-record lists: capacity = co-rating products of the full row, at most I - 1 ----
+        cap = torch.clamp(layout.row_work - count.long(), min=0, max=max(I - 1, 0))
+        self.rec_ptr = torch.zeros(I + 1, dtype=torch.int64, device=dev)
+        self.rec_ptr[1:] = torch.cumsum(cap, 0)
+        self.rec_cap = cap
+        total = int(self.rec_ptr[-1].item()) if I else 0
+        free, _ = torch.cuda.mem_get_info(dev)
+        if total * REC_BYTES > free - (1 << 30):
+            raise N.NativeError("neighbour-record lists need %.1f GB, %.1f GB free" %
+                                (total * REC_BYTES / 1e9, free / 1e9))
+        self.rec = torch.empty((max(total, 1), 2), dtype=torch.int64, device=dev)
+        self.rec_cnt = torch.zeros(I, dtype=torch.int32, device=dev)
+        self.bb = torch.zeros(I, dtype=torch.uint8, device=dev)
         self.row_npairs = torch.zeros(I, dtype=torch.int32, device=dev)
-        self.row_nkept = torch.zeros(I, dtype=torch.int32, device=dev)
+        self.error_flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.tab_idx = torch.full((I, 2, k), -1, dtype=torch.int32, device=dev)
         self.tab_sim = torch.zeros((I, 2, k), dtype=torch.float64, device=dev)
         self.tab_mutu = torch.zeros((I, 2, k), dtype=torch.int32, device=dev)
         self.tab_n = torch.zeros((I, 2, k), dtype=torch.int32, device=dev)
         self.tab_len = torch.zeros((I, 2), dtype=torch.int32, device=dev)
-        self._big_ws = None
-        self._tier_ws = None
+        self._gtab = None
+        self._plans = {}
         self.profile = None        # dict kind -> [(start_event, end_event)] when enabled
 
     # -- argument block ----------------------------------------------------
-    def _args(self, mode, bb_in=None, emit=None):
+    def _args(self):
         lay, m = self.lay, self.meta
         a = N.SimArgs()
-        a.csr_ptr, a.csr_ent = N.ptr(lay.csr_ptr), N.ptr(lay.csr_ent)
-        a.csc_ptr, a.csc_ent = N.ptr(lay.csc_ptr), N.ptr(lay.csc_ent)
-        a.user_mu, a.item_stats = N.ptr(lay.user_mu), N.ptr(lay.item_stats)
-        a.prefix_code, a.dom_code, a.contains = N.ptr(m.prefix_code), N.ptr(m.dom_code), N.ptr(m.contains)
-        a.bb_in = N.ptr(bb_in)
-        a.row_work = N.ptr(lay.row_work)
+        a.csc_ptr, a.csc_ent, a.csc_aux = N.ptr(lay.csc_ptr), N.ptr(lay.csc_ent), N.ptr(self.csc_aux)
+        a.tcsr_ent, a.user_mu = N.ptr(self.tcsr_ent), N.ptr(lay.user_mu)
+        a.ostat, a.ord, a.tri_work = N.ptr(self.ostat), N.ptr(self.ord), N.ptr(self.tri_work)
+        a.dom_code, a.contains = N.ptr(m.dom_code), N.ptr(m.contains)
         a.n_items, a.method = lay.n_items, N.METHODS[self.method]
-        a.num_atleast, a.k, a.r2_bits, a.mode = self.num_atleast, self.k, self.r2_bits, mode
-        a.row_flags, a.row_npairs, a.row_nkept = N.ptr(self.row_flags), N.ptr(self.row_npairs), N.ptr(self.row_nkept)
+        a.num_atleast, a.k, a.r2_bits = self.num_atleast, self.k, self.r2_bits
+        a.rec_ptr, a.rec_cnt, a.rec = N.ptr(self.rec_ptr), N.ptr(self.rec_cnt), N.ptr(self.rec)
+        a.bb, a.row_npairs = N.ptr(self.bb), N.ptr(self.row_npairs)
         a.tab_idx, a.tab_sim = N.ptr(self.tab_idx), N.ptr(self.tab_sim)
         a.tab_mutu, a.tab_n, a.tab_len = N.ptr(self.tab_mutu), N.ptr(self.tab_n), N.ptr(self.tab_len)
-        if emit is not None:
-            a.emit_ptr, a.emit_j, a.emit_sim = N.ptr(emit["ptr"]), N.ptr(emit["j"]), N.ptr(emit["sim"])
-            a.emit_mutu, a.emit_n, a.emit_cursor = N.ptr(emit["mutu"]), N.ptr(emit["n"]), N.ptr(emit["cursor"])
         a.error_flag = N.ptr(self.error_flag)
         return a
 
     # -- planning ----------------------------------------------------------
     def plan(self, rows=None):
-        """Split rows by cost: four warp-per-row tiers (by table size) and the heavy tier.
-        Each tier is ordered by descending work so long rows start first."""
-        w = self.lay.row_work
+        """Group the rows by table capacity and threads per row (cached per row set).
+        Returns (launches, long_candidates): launches = [(rows sorted by descending work,
+        cells_cap, threads_per_row, in_global_memory)], long_candidates = rows whose record
+        list can exceed XMAP_SELECT_LONG."""
+        key = None if rows is None else (int(rows[0]) if rows.numel() else -1, int(rows.numel()))
+        if key in self._plans:
+            return self._plans[key]
+        dev, I = self.device, self.lay.n_items
         if rows is None:
-            rows = torch.arange(self.lay.n_items, dtype=torch.int32, device=self.device)
+            rows = torch.arange(I, dtype=torch.int32, device=dev)
         else:
-            rows = rows.to(self.device, dtype=torch.int32)
-        wr = w[rows.long()]
-        order = torch.argsort(wr, descending=True, stable=True)
-        rows, wr = rows[order], wr[order]
-        tiers, lo = [], 0
-        for hi in N.TIER_MAXWORK:
-            tiers.append(rows[(wr > lo) & (wr <= hi)].contiguous())
-            lo = hi
-        big = rows[wr > lo].contiguous()
-        return tiers, big
-
-    def _big_batches(self, big):
-        """Cut the heavy rows (already sorted by descending work) into batches bounded by the
-        table budget and by the candidate-record capacity.  One host sync per plan."""
-        I = self.lay.n_items
-        per_row = I * 20 + 4
-        b_max = int(max(1, self.table_budget // per_row))
-        w = self.lay.row_work[big.long()]
-        cap = torch.where(w >= 2 * I, torch.full_like(w, I), torch.clamp(w, max=I)).cpu().tolist()   # dense rows: I records
-        batches, lo, acc = [], 0, 0
-        for q, c in enumerate(cap):
-            if q > lo and (q - lo >= b_max or acc + c > BIG_CAND_CAPACITY):
-                batches.append((lo, q, acc)); lo, acc = q, 0
-            acc += c
-        if len(cap) > lo:
-            batches.append((lo, len(cap), acc))
-        return batches, b_max
-
-    def _big_workspace(self, n_rows, capacity):
-        I = self.lay.n_items
-        L = N.lib()
-        ws = self._big_ws
-        need = L.xmap_sim_big_scratch_bytes(n_rows, capacity)
-        if ws is None or ws["B"] < n_rows or ws["scratch"].numel() < need:
-            dev = self.device
-            B = max(n_rows, ws["B"] if ws else 0)
-            need = max(need, ws["scratch"].numel() if ws else 0)
-            ws = None
-            self._big_ws = None
-            ws = dict(B=B,
-                      table=torch.zeros(B * I * 2, dtype=torch.int64, device=dev),
-                      touched=torch.empty(B * I, dtype=torch.int32, device=dev),
-                      touched_n=torch.zeros(B, dtype=torch.int32, device=dev),
-                      counter=torch.zeros(1, dtype=torch.int32, device=dev),
-                      scratch=torch.empty(need, dtype=torch.uint8, device=dev))
-            self._big_ws = ws
-        return ws
+            rows = rows.to(dev, dtype=torch.int32)
+        rl = rows.long()
+        work = self.tri_work[rl]
+        rtop = (I - 1 - self.ord[rl]).long()
+        h = torch.clamp((work * 4 + 2) // 3, min=32)
+        cells = torch.where(rtop <= h, rtop, h)
+        classes = [c for c in CELL_CLASSES if c <= self.max_smem_cells] or [self.max_smem_cells]
+        if classes[-1] < self.max_smem_cells:
+            classes.append(self.max_smem_cells)
+        bounds = torch.tensor(classes, dtype=torch.int64, device=dev)
+        cls = torch.bucketize(cells, bounds)                       # len(classes) = global-memory fallback
+        t_cells = torch.tensor([CELL_THREADS[min(q, len(CELL_THREADS) - 1)] if classes[q] > 1024 or q >= 3 else 32
+                                for q in range(len(classes))] + [512], dtype=torch.int64, device=dev)[cls]
+        t_work = torch.full_like(work, 32)
+        t_work[work > 3072] = 128
+        t_work[work > 8192] = 256
+        t_work[work > 32768] = 512
+        threads = torch.maximum(t_cells, t_work)
+        live = work > 0
+        code = (cls * 2048 + threads)[live]
+        rows_l, work_l, cells_l = rows[live], work[live], cells[live]
+        launches = []
+        for c in torch.unique(code).tolist():
+            m = code == c
+            r, w = rows_l[m], work_l[m]
+            r = r[torch.argsort(w, descending=True, stable=True)].contiguous()
+            q, th = c // 2048, c % 2048
+            if q < len(classes):
+                launches.append((r, classes[q], th, False))
+            else:
+                launches.append((r, int(cells_l[m].max().item()), 512, True))
+        launches.sort(key=lambda t: (-t[2], -t[1]))                # big CTAs first
+        long_cand = rows[self.rec_cap[rl] > N.SELECT_LONG].contiguous()
+        out = (launches, long_cand)
+        self._plans[key] = out
+        return out
 
     def enable_profile(self):
         """Record a CUDA event pair around every kernel group (read with profile_ms())."""
@@ -245,105 +284,91 @@ class SimEngine:
         self.profile = {}
         return out
 
-    def _run_rows(self, args, tiers, big):
+    def _check_error(self):
+        e = int(self.error_flag.item())
+        if e != 0:
+            raise N.NativeError("similarity kernel error %d (1: table overflow, 2: record-list capacity, "
+                                "3: co-rating count out of range)" % e)
+
+    # -- stages ------------------------------------------------------------
+    def reset(self):
+        self.rec_cnt.zero_()
+        self.bb.zero_()
+        self.row_npairs.zero_()
+
+    def accumulate(self, rows=None):
+        """Triangular similarity rows -> neighbour records of both ends, BB flags (xmap_sim_accumulate)."""
         L = N.lib()
         st = _stream_ptr()
-        for tier, rows in enumerate(tiers):
-            if not rows.numel():
-                continue
-            ws = None
-            need = L.xmap_sim_rows_workspace_bytes(tier)
-            if need:
-                if self._tier_ws is None or self._tier_ws.numel() < need:
-                    self._tier_ws = None
-                    self._tier_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-                ws = self._tier_ws
-            self._timed("warp_tier%d" % tier, lambda: N.check(
-                L.xmap_sim_rows(args, N.ptr(rows), rows.numel(), tier, N.ptr(ws), need, st),
-                "xmap_sim_rows[%d]" % tier))
+        args = self._args()
+        launches, _ = self.plan(rows)
+        stats = []
+        for r, cells_cap, threads, in_gmem in launches:
+            gtab, ctas = None, 0
+            if in_gmem:
+                ctas = min(int(r.numel()), 296)
+                need = ctas * cells_cap * 16
+                if self._gtab is None or self._gtab.numel() < need:
+                    self._gtab = None
+                    self._gtab = torch.empty(need, dtype=torch.uint8, device=self.device)
+                gtab = self._gtab
+            kind = "accumulate_%s%d_t%d" % ("g" if in_gmem else "c", cells_cap, threads)
+            self._timed(kind, lambda: N.check(L.xmap_sim_accumulate(
+                args, N.ptr(r), r.numel(), cells_cap, threads, N.ptr(gtab), ctas, st), "xmap_sim_accumulate"))
             self.launches += 1
-        if big.numel():
-            lay = self.lay
-            batches, _ = self._big_batches(big)
-            ws = self._big_workspace(max(hi - lo for lo, hi, _ in batches), max(c for _, _, c in batches))
-            for lo_b, hi_b, capacity in batches:
-                rows = big[lo_b:hi_b].contiguous()
-                rl = rows.long()
-                c = (lay.csc_ptr[rl + 1] - lay.csc_ptr[rl]).long()
-                grp_off = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=self.device)
-                grp_off[1:] = torch.cumsum((c + RATER_GROUP - 1) // RATER_GROUP, 0)
-                ws["counter"].zero_()
-                self._timed("big_accumulate", lambda: N.check(L.xmap_sim_big_accumulate(
-                    args, N.ptr(rows), rows.numel(), N.ptr(grp_off), N.ptr(ws["table"]),
-                    N.ptr(ws["touched"]), N.ptr(ws["touched_n"]), N.ptr(ws["counter"]), st),
-                    "xmap_sim_big_accumulate"))
-                self._timed("big_epilogue", lambda: N.check(L.xmap_sim_big_finalize(
-                    args, N.ptr(rows), rows.numel(), N.ptr(ws["table"]), N.ptr(ws["touched"]),
-                    N.ptr(ws["touched_n"]), capacity, N.ptr(ws["scratch"]), ws["scratch"].numel(), st),
-                    "xmap_sim_big_finalize"))
-                self.launches += 4
+            stats.append((kind, int(r.numel())))
+        return stats
 
-    def _check_error(self):
-        if int(self.error_flag.item()) != 0:
-            raise N.NativeError("similarity kernel error %d (1: hash overflow, 4: candidate capacity)" % int(self.error_flag.item()))
-
-    # -- passes ------------------------------------------------------------
-    def pass1(self, rows=None):
-        """Similarity rows + BB flags + (BB_BB, BB_NB) / NB_NN tables for `rows`."""
-        tiers, big = self.plan(rows)
-        self._run_rows(self._args(0), tiers, big)
-        return dict(tiers=[int(t.numel()) for t in tiers], big=int(big.numel()))
-
-    def pass2(self, bb_all, rows=None):
-        """NB_BB tables for the non-bridge rows among `rows` (needs every item's BB flag)."""
-        if rows is None:
-            rows = torch.arange(self.lay.n_items, dtype=torch.int32, device=self.device)
-        rl = rows.long()
-        nb = rows[(self.row_flags[rl] == 0) & (self.row_nkept[rl] > 0)]
-        tiers, big = self.plan(nb)
-        self._run_rows(self._args(1, bb_in=bb_all.to(torch.uint8).contiguous()), tiers, big)
-        return dict(tiers=[int(t.numel()) for t in tiers], big=int(big.numel()))
+    def select(self, rows=None):
+        """Per-row top-k lists from the neighbour records (xmap_sim_select); needs every item's BB flag."""
+        L = N.lib()
+        st = _stream_ptr()
+        args = self._args()
+        _, long_cand = self.plan(rows)
+        n = self.lay.n_items if rows is None else int(rows.numel())
+        rp = None if rows is None else N.ptr(rows.to(self.device, dtype=torch.int32).contiguous())
+        self._timed("select_warp", lambda: N.check(L.xmap_sim_select(args, rp, n, 0, st), "xmap_sim_select"))
+        self.launches += 1
+        if long_cand.numel():
+            self._timed("select_cta", lambda: N.check(
+                L.xmap_sim_select(args, N.ptr(long_cand), long_cand.numel(), 1, st), "xmap_sim_select(long)"))
+            self.launches += 1
 
     def run(self, rows=None):
-        """Single-GPU convenience: pass 1, pass 2, error check."""
-        s1 = self.pass1(rows)
-        s2 = self.pass2(self.row_flags, rows)
+        """Single-GPU convenience: reset, accumulate, select, error check."""
+        self.reset()
+        stats = self.accumulate(rows)
+        self.select(rows)
         self._check_error()
-        return self.tables(dict(pass1=s1, pass2=s2))
+        return self.tables(dict(accumulate=stats))
 
     def tables(self, stats=None):
-        return SimTables(self.k, self.lay.n_items, self.row_flags, self.row_npairs, self.row_nkept,
+        return SimTables(self.k, self.lay.n_items, self.bb, self.row_npairs, self.rec_cnt,
                          self.tab_idx, self.tab_sim, self.tab_mutu, self.tab_n, self.tab_len,
                          self.launches, stats or {})
 
     def emit_pairs(self, rows=None):
-        """Materialise every kept directed pair (the return value of
-        baseliner_calculate_sim_pipeline, assist.py:66-77), sorted by (i, j).
-        Needs pass1 to have filled row_nkept."""
+        """Every kept directed pair (the return value of baseliner_calculate_sim_pipeline,
+        assist.py:66-77), sorted by (i, j): the neighbour-record lists themselves."""
         dev = self.device
         I = self.lay.n_items
-        if rows is None:
-            rows = torch.arange(I, dtype=torch.int32, device=dev)
-        nk = torch.zeros(I, dtype=torch.int64, device=dev)
-        nk[rows.long()] = self.row_nkept[rows.long()].long()
-        ptr = torch.zeros(I + 1, dtype=torch.int64, device=dev)
-        ptr[1:] = torch.cumsum(nk, 0)
-        total = int(ptr[-1].item())
-        emit = dict(ptr=ptr,
-                    j=torch.empty(total, dtype=torch.int32, device=dev),
-                    sim=torch.empty(total, dtype=torch.float64, device=dev),
-                    mutu=torch.empty(total, dtype=torch.int32, device=dev),
-                    n=torch.empty(total, dtype=torch.int32, device=dev),
-                    cursor=torch.zeros(I, dtype=torch.int32, device=dev))
-        tiers, big = self.plan(rows)
-        self._run_rows(self._args(2, emit=emit), tiers, big)
-        self._check_error()
-        i = torch.repeat_interleave(torch.arange(I, device=dev), nk)
-        key = i * I + emit["j"].long()
-        order = torch.argsort(key)
-        i, j = i[order], emit["j"][order].long()
-        sim, mutu, n = emit["sim"][order], emit["mutu"][order], emit["n"][order]
-        cnt = self.lay.item_stats[:, 3]
-        frac = mutu.double() / (cnt[i] + cnt[j] - n.double())
+        cnt = self.rec_cnt.long()
+        if rows is not None:
+            keep = torch.zeros(I, dtype=torch.bool, device=dev)
+            keep[rows.long()] = True
+            cnt = torch.where(keep, cnt, torch.zeros_like(cnt))
+        i = torch.repeat_interleave(torch.arange(I, device=dev), cnt)
+        first = torch.cumsum(cnt, 0) - cnt
+        src = self.rec_ptr[:-1][i] + (torch.arange(i.numel(), device=dev) - first[i])
+        r = self.rec[src]
+        pack = r[:, 1]
+        j = pack & 0xFFFFFF
+        n = ((pack >> 24) & 0xFFFFF).to(torch.int32)
+        mutu = ((pack >> 44) & 0xFFFFF).to(torch.int32)
+        sim = r[:, 0].contiguous().view(torch.float64)
+        order = torch.argsort(i * I + j)
+        i, j, sim, mutu, n = i[order], j[order], sim[order], mutu[order], n[order]
+        cnt_i = self.lay.item_stats[:, 3]
+        frac = mutu.double() / (cnt_i[i] + cnt_i[j] - n.double())
         label = (self.meta.prefix_code[i] != self.meta.prefix_code[j]).to(torch.int32)
         return dict(i=i, j=j, sim=sim, mutu=mutu, n=n, frac=frac, label=label)

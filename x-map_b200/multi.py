@@ -1,20 +1,23 @@
 """Multi-GPU sharding of the similarity + selection stage (one process per GPU).
 
-Row i of R^T R needs only CSC column i and the CSR rows it touches, so item
-rows are cut into contiguous blocks of equal *work* (sum of rater degrees, not
-row count), every rank keeps the whole ratings layout (replicated; the
-reference broadcasts its side tables the same way, assist.py:69,73) and the
-SpGEMM itself needs no communication.  Two exchanges remain, both all-gathers
-over NCCL (NVLink / NVSwitch):
+Item rows are cut into contiguous blocks of equal *work* (sum of rater degrees,
+not row count); every rank keeps the whole ratings layout (replicated; the
+reference broadcasts its side tables the same way, assist.py:69,73).  A rank
+evaluates the triangular similarity rows of its block, which produces neighbour
+records for BOTH ends of every pair -- the end it owns and the (more popular)
+end another rank may own.  So the path has one real exchange step, followed by
+the gathers the reference performs as collect + broadcast:
 
-  1. BB flags after pass 1  (replaces the SQL DISTINCT + collect + broadcast of
-     assist.py:82-87)  -- n_items bytes;
-  2. the neighbour tables after pass 2 (replaces the collectAsMap + broadcast of
-     assist.py:121-132) -- n_items * 2k * 20 bytes.
+  1. all-to-all of the neighbour records addressed to rows of other ranks
+     (replaces the reduceByKey shuffle of baselinerSim.py:210-211, 232-233);
+  2. max-all-reduce of the BB flags (the SQL DISTINCT + collect + broadcast of
+     assist.py:82-87) -- n_items bytes;
+  3. all-gather of the neighbour tables after selection (the collectAsMap +
+     broadcast of assist.py:121-132) -- n_items * 2k * 20 bytes.
 
-Because the accumulators are order-free integers the gathered result is
-bit-identical for any world size.  The exchange helpers are device-agnostic so
-they can be exercised with the gloo backend on CPU tensors.
+Because the accumulators are order-free integers and selection uses a total
+order, the result is bit-identical for any world size.  The exchange helpers are
+device-agnostic so they can be exercised with the gloo backend on CPU tensors.
 """
 import torch
 import torch.distributed as dist
@@ -64,14 +67,81 @@ def allgather_rows(t, shard, group=None):
     return t
 
 
+def _all_to_all(recv, send, group=None):
+    """dist.all_to_all where the backend has it (NCCL); point-to-point otherwise (gloo)."""
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all(recv, send, group=group)
+        return
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    recv[rank].copy_(send[rank])
+    ops = []
+    for s in range(world):
+        if s == rank:
+            continue
+        if send[s].numel():
+            ops.append(dist.P2POp(dist.isend, send[s], s, group))
+        if recv[s].numel():
+            ops.append(dist.P2POp(dist.irecv, recv[s], s, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def _list_slots(base, seg):
+    """Flat indices base[r] + 0 .. seg[r]-1 for every row r, rows concatenated."""
+    tot = int(seg.sum())
+    if tot == 0:
+        return torch.zeros(0, dtype=torch.int64, device=seg.device), 0
+    first = torch.cumsum(seg, 0) - seg
+    r = torch.repeat_interleave(torch.arange(seg.numel(), device=seg.device), seg)
+    return base[r] + (torch.arange(tot, device=seg.device) - first[r]), tot
+
+
+def exchange_records(rec, rec_ptr, rec_cnt, shard, group=None):
+    """rec [total, 2] int64 records, rec_ptr [I + 1] list extents, rec_cnt [I] list lengths.
+    On entry the lists hold the records THIS rank produced, for every row; on exit the lists of the
+    rows this rank owns hold the records of every rank and the other lists are empty."""
+    if shard.world == 1:
+        return
+    world, rank = shard.world, shard.rank
+    cnt = rec_cnt.long()
+    blocks = [(shard.bounds[s], shard.bounds[s + 1]) for s in range(world)]
+    send_cnt = [cnt[lo:hi].contiguous() for lo, hi in blocks]
+    own = shard.hi - shard.lo
+    recv_cnt = [torch.empty(own, dtype=torch.int64, device=rec.device) for _ in range(world)]
+    _all_to_all(recv_cnt, send_cnt, group)
+    send_buf = []
+    for s, (lo, hi) in enumerate(blocks):
+        if s == rank:
+            send_buf.append(rec.new_empty((0, 2)))
+            continue
+        src, _ = _list_slots(rec_ptr[lo:hi], send_cnt[s])
+        send_buf.append(rec[src])
+    recv_buf = [rec.new_empty((0 if s == rank else int(recv_cnt[s].sum()), 2)) for s in range(world)]
+    _all_to_all(recv_buf, send_buf, group)
+    cur = cnt[shard.lo:shard.hi].clone()
+    for s in range(world):
+        if s == rank:
+            continue
+        dst, tot = _list_slots(rec_ptr[shard.lo:shard.hi] + cur, recv_cnt[s])
+        if tot:
+            rec[dst] = recv_buf[s]
+        cur += recv_cnt[s]
+    rec_cnt.zero_()
+    rec_cnt[shard.lo:shard.hi] = cur.to(rec_cnt.dtype)
+
+
 def similarity_step(engine, shard, group=None):
-    """Pass 1 on the owned rows, all-gather BB flags, pass 2, all-gather the tables."""
+    """Triangular rows of the owned block -> record exchange -> BB flags -> selection -> gather."""
     rows = None if shard.world == 1 else shard.rows(engine.device)
-    s1 = engine.pass1(rows)
-    allgather_rows(engine.row_flags, shard, group)
-    s2 = engine.pass2(engine.row_flags, rows)
+    engine.reset()
+    stats = engine.accumulate(rows)
     if shard.world > 1:
-        for t in (engine.row_npairs, engine.row_nkept, engine.tab_len, engine.tab_idx, engine.tab_sim,
+        engine._timed("exchange", lambda: exchange_records(engine.rec, engine.rec_ptr, engine.rec_cnt, shard, group))
+        dist.all_reduce(engine.bb, op=dist.ReduceOp.MAX, group=group)
+    engine.select(rows)
+    if shard.world > 1:
+        for t in (engine.row_npairs, engine.rec_cnt, engine.tab_len, engine.tab_idx, engine.tab_sim,
                   engine.tab_mutu, engine.tab_n):
             allgather_rows(t, shard, group)
-    return engine.tables(dict(pass1=s1, pass2=s2, rows=(shard.lo, shard.hi)))
+    return engine.tables(dict(accumulate=stats, rows=(shard.lo, shard.hi)))
