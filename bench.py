@@ -349,7 +349,7 @@ def main():
         for r, cells_cap, threads, in_gmem in launches_plan:
             fam = "tri_gmem_kernel" if in_gmem else ("tri_warp_kernel" if threads == 32 else "tri_cta_kernel")
             fam_bytes[fam] = fam_bytes.get(fam, 0.0) + 8.0 * float(eng.tri_work[r.long()].sum().item())
-        long_rows = tabs.row_nkept > 2048
+        long_rows = tabs.row_nkept > 8192
         fam_bytes["select_cta_kernel"] = 16.0 * float(tabs.row_nkept[long_rows].sum().item())
         fam_bytes["select_warp_kernel"] = 16.0 * float(tabs.row_nkept[~long_rows].sum().item())
         kinds = {kk: (fam_n[kk], fam_ms[kk]) for kk in fam_ms}

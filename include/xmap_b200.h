@@ -79,8 +79,9 @@ int xmap_row_work(const int32_t *csr_ptr, const int32_t *csc_ptr, const uint64_t
  * sorted by ord that part is a suffix:
  *   tcsr_ent[k]  = { ord(item) | cls(item)<<24 | ge_avg<<29 , float bits of rating }
  *                  same extents as csr_ptr, entries ascending by ord;
- *   csc_aux[e]   = { pos, len }: CSC entry e = (i, u) sits at tcsr position pos, and
- *                  the len entries after it are u's ratings of items more popular than i;
+ *   csc_aux[e]   = 16 bytes { uint32 pos, uint32 len, double mu }: CSC entry e = (i, u) sits at
+ *                  tcsr position pos, the len entries after it are u's ratings of items more
+ *                  popular than i, and mu = user_mu[u] (0 for the cosine method);
  *   tri_work[i]  = sum of len over the raters of i = products row i evaluates
  *                  (sum over i = W / 2);
  *   ostat[o]     = 16 bytes per ord o: { double den; uint32 item; uint32 prefix<<8 | cls }
@@ -90,9 +91,9 @@ int xmap_row_work(const int32_t *csr_ptr, const int32_t *csc_ptr, const uint64_t
 size_t xmap_tri_workspace_bytes(int64_t nnz);
 int xmap_build_tri_layout(const int32_t *csr_ptr, const uint64_t *csr_ent,
                           const int32_t *csc_ptr, const uint64_t *csc_ent,
-                          const double *item_stats, const int32_t *prefix_code, const int32_t *ord,
-                          int32_t n_users, int32_t n_items, int64_t nnz, int32_t method,
-                          uint64_t *tcsr_ent, uint64_t *csc_aux, void *ostat, int64_t *tri_work,
+                          const double *user_mu, const double *item_stats, const int32_t *prefix_code,
+                          const int32_t *ord, int32_t n_users, int32_t n_items, int64_t nnz, int32_t method,
+                          uint64_t *tcsr_ent, void *csc_aux, void *ostat, int64_t *tri_work,
                           void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------
@@ -124,12 +125,12 @@ int xmap_build_tri_layout(const int32_t *csr_ptr, const uint64_t *csr_ent,
  *   threads_per_row > 32  : one CTA of that many threads per row
  *   cells_cap             : table capacity (16-byte cells) of every row in `rows`
  *   gtab != NULL          : tables in global memory instead (rows too large for shared
- *                           memory); gtab holds gtab_ctas * cells_cap cells.
+ *                           memory); gtab holds gtab_ctas * cells_cap * 20 bytes.
  * ------------------------------------------------------------------------- */
 typedef struct xmap_sim_args {
     /* layout */
-    const int32_t *csc_ptr; const uint64_t *csc_ent; const uint64_t *csc_aux;
-    const uint64_t *tcsr_ent; const double *user_mu;
+    const int32_t *csc_ptr; const uint64_t *csc_ent; const void *csc_aux;
+    const uint64_t *tcsr_ent;
     const void *ostat; const int32_t *ord; const int64_t *tri_work;
     /* per-item codes (host-computed from the id strings) */
     const uint8_t *dom_code;       /* iid[-2:] -- extender.py:29     */
@@ -148,7 +149,7 @@ typedef struct xmap_sim_args {
     int32_t *error_flag;           /* device int: 1 table overflow, 2 list capacity, 3 count range */
 } xmap_sim_args;
 
-#define XMAP_SIM_MAX_SMEM_CELLS 14336     /* 224 KB of 16-byte cells */
+#define XMAP_SIM_MAX_SMEM_CELLS 12288     /* 12288 x (16-byte cell + 2-byte slot index) = 216 KB */
 /* cells a row needs: min(#more popular items, ceil(4/3 * tri_work)), at least 32 */
 int64_t xmap_sim_row_cells(int64_t tri_work, int32_t n_more_popular);
 int xmap_sim_accumulate(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
@@ -163,7 +164,7 @@ int xmap_sim_accumulate(const xmap_sim_args *args_h, const int32_t *rows, int32_
  * long_rows = 0: one warp per row, rows with more than XMAP_SELECT_LONG records are skipped;
  * long_rows = 1: one CTA per row, only rows with more than XMAP_SELECT_LONG records are done.
  * rows == NULL means all rows 0 .. n_rows-1. */
-#define XMAP_SELECT_LONG 2048
+#define XMAP_SELECT_LONG 8192
 int xmap_sim_select(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
                     int32_t long_rows, void *stream);
 

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libxmap_b200.so")
 
 KMAX = 64
 METHODS = {"adjust_cosine": 0, "cosine": 1}
-SELECT_LONG = 2048            # XMAP_SELECT_LONG
+SELECT_LONG = 8192            # XMAP_SELECT_LONG
 ABI_VERSION = 2
 
 _p = C.c_void_p
@@ -20,7 +20,7 @@ _p = C.c_void_p
 
 class SimArgs(C.Structure):
     _fields_ = [
-        ("csc_ptr", _p), ("csc_ent", _p), ("csc_aux", _p), ("tcsr_ent", _p), ("user_mu", _p),
+        ("csc_ptr", _p), ("csc_ent", _p), ("csc_aux", _p), ("tcsr_ent", _p),
         ("ostat", _p), ("ord", _p), ("tri_work", _p),
         ("dom_code", _p), ("contains", _p),
         ("n_items", C.c_int32), ("method", C.c_int32), ("num_atleast", C.c_int32),
@@ -58,7 +58,7 @@ _SIGS = {
                                     _p, _p, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "xmap_row_work": (C.c_int, [_p, _p, _p, C.c_int32, _p, _p]),
     "xmap_tri_workspace_bytes": (C.c_size_t, [C.c_int64]),
-    "xmap_build_tri_layout": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, C.c_int32, C.c_int32, C.c_int64, C.c_int32,
+    "xmap_build_tri_layout": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, C.c_int32, C.c_int32, C.c_int64, C.c_int32,
                                         _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "xmap_sim_row_cells": (C.c_int64, [C.c_int64, C.c_int32]),
     "xmap_sim_accumulate": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, C.c_int32, C.c_int32, _p, C.c_int32, _p]),

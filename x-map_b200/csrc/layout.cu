@@ -146,8 +146,8 @@ __global__ void tri_keys_kernel(const int32_t *__restrict__ csr_ptr, const uint6
 // One warp per item: position of (i, u) in u's ord-sorted row, suffix length, row work.
 __global__ void tri_aux_kernel(const int32_t *__restrict__ csr_ptr, const int32_t *__restrict__ csc_ptr,
                                const uint64_t *__restrict__ csc_ent, const uint64_t *__restrict__ tcsr_ent,
-                               const int32_t *__restrict__ ord, int32_t n_items,
-                               uint64_t *__restrict__ csc_aux, int64_t *__restrict__ tri_work) {
+                               const double *__restrict__ user_mu, const int32_t *__restrict__ ord, int32_t n_items,
+                               int32_t method, uint4 *__restrict__ csc_aux, int64_t *__restrict__ tri_work) {
     int32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= n_items) return;
     const int lane = threadIdx.x & 31;
@@ -162,7 +162,8 @@ __global__ void tri_aux_kernel(const int32_t *__restrict__ csr_ptr, const int32_
             if (((uint32_t)__ldg(tcsr_ent + mid) & ITEM_MASK) <= oi) lo = mid; else hi = mid;
         }
         const int32_t len = end - lo - 1;
-        csc_aux[e] = ((uint64_t)(uint32_t)len << 32) | (uint32_t)lo;
+        const double mu = (method == XMAP_METHOD_ADJUST_COSINE) ? user_mu[u] : 0.0;
+        csc_aux[e] = make_uint4((uint32_t)lo, (uint32_t)len, (uint32_t)__double2loint(mu), (uint32_t)__double2hiint(mu));
         w += len;
     }
 #pragma unroll
@@ -301,9 +302,9 @@ extern "C" size_t xmap_tri_workspace_bytes(int64_t nnz) { return tri_ws(nnz, nul
 
 extern "C" int xmap_build_tri_layout(const int32_t *csr_ptr, const uint64_t *csr_ent,
                                      const int32_t *csc_ptr, const uint64_t *csc_ent,
-                                     const double *item_stats, const int32_t *prefix_code, const int32_t *ord,
-                                     int32_t n_users, int32_t n_items, int64_t nnz, int32_t method,
-                                     uint64_t *tcsr_ent, uint64_t *csc_aux, void *ostat, int64_t *tri_work,
+                                     const double *user_mu, const double *item_stats, const int32_t *prefix_code,
+                                     const int32_t *ord, int32_t n_users, int32_t n_items, int64_t nnz, int32_t method,
+                                     uint64_t *tcsr_ent, void *csc_aux, void *ostat, int64_t *tri_work,
                                      void *workspace, size_t workspace_bytes, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     const int T = 256;
@@ -326,7 +327,7 @@ extern "C" int xmap_build_tri_layout(const int32_t *csr_ptr, const uint64_t *csr
     XMAP_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys_a, keys_b, vals_a, tcsr_ent, nnz, 0,
                                               32 + bits_for(n_users), st));
     tri_aux_kernel<<<(unsigned)(((int64_t)n_items * 32 + T - 1) / T), T, 0, st>>>(
-        csr_ptr, csc_ptr, csc_ent, tcsr_ent, ord, n_items, csc_aux, tri_work);
+        csr_ptr, csc_ptr, csc_ent, tcsr_ent, user_mu, ord, n_items, method, reinterpret_cast<uint4 *>(csc_aux), tri_work);
     XMAP_LAUNCH_CHECK();
     return 0;
 }

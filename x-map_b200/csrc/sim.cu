@@ -75,12 +75,37 @@ __device__ __forceinline__ void group_sync() {
     if (CTA_ROW) __syncthreads(); else __syncwarp();
 }
 
-template <bool CTA_ROW>
-__device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, int cells_cap, int row) {
+// rater descriptor of one lane: suffix start | ge_i << 31, suffix length, centred rating, user mean
+struct RaterDesc {
+    unsigned start;
+    int len;
+    double ci, mu;
+};
+
+__device__ __forceinline__ RaterDesc load_rater(const xmap_sim_args &a, int e, int hi) {
+    RaterDesc d{0u, 0, 0.0, 0.0};
+    if (e < hi) {
+        const uint2 ce = ld_ent(a.csc_ent + e);
+        const uint4 ax = __ldg(reinterpret_cast<const uint4 *>(a.csc_aux) + e);      // {pos, len, mean of the rater}
+        d.mu = __hiloint2double((int)ax.w, (int)ax.z);
+        d.ci = (double)__uint_as_float(ce.y) - d.mu;
+        d.start = (ax.x + 1u) | (ce.x & 0x80000000u);      // bit 31 = (rating of i >= average of i)
+        d.len = (int)ax.y;
+    }
+    return d;
+}
+
+// Accumulate + epilogue of one row by a group of threads (one warp, or a whole CTA).
+//   T    : cells_cap accumulator cells;  occ : cells_cap slot indices (IDX = uint16 in shared memory)
+//   s_cnt: one int of group-shared scratch (CTA mode)
+template <bool CTA_ROW, class IDX>
+__device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__restrict__ occ_list, int *s_cnt,
+                        int cells_cap, int row) {
     const int lane = threadIdx.x & 31;
     const int gwarps = CTA_ROW ? (blockDim.x >> 5) : 1;
     const int gw = CTA_ROW ? (threadIdx.x >> 5) : 0;
     const int gthreads = gwarps * 32, gtid = gw * 32 + lane;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const OStat *__restrict__ ostat = reinterpret_cast<const OStat *>(a.ostat);
 
     const int oi = a.ord[row];
@@ -98,57 +123,62 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, int cells_
         return;
     }
     const int ncell = (int)ncell_ll;
-    {
-        uint4 *T4 = reinterpret_cast<uint4 *>(T);
-        for (int s = gtid; s < ncell; s += gthreads) T4[s] = make_uint4(0u, 0u, 0u, 0u);
-    }
+    uint4 *T4 = reinterpret_cast<uint4 *>(T);
+    for (int s = gtid; s < ncell; s += gthreads) T4[s] = make_uint4(0u, 0u, 0u, 0u);
+    if (CTA_ROW && gtid == 0) *s_cnt = 0;
     group_sync<CTA_ROW>();
 
     // ---- accumulate: batches of 32 raters per warp, products flattened over the lanes ----------
-    const bool adj = (a.method == XMAP_METHOD_ADJUST_COSINE);
     const int qbase = 62 - a.r2_bits;
     const int top_ord = a.n_items - 1;
-    for (int b0 = lo + gw * 32; b0 < hi; b0 += gwarps * 32) {
-        const int e = b0 + lane;
-        unsigned start = 0u;
-        int len = 0;
-        double ci = 0.0, mu = 0.0;
-        if (e < hi) {
-            const uint2 ce = ld_ent(a.csc_ent + e);
-            const uint2 ax = ld_ent(a.csc_aux + e);
-            if (adj) mu = __ldg(a.user_mu + (ce.x & 0x7FFFFFFFu));
-            ci = (double)__uint_as_float(ce.y) - mu;
-            start = (ax.x + 1u) | (ce.x & 0x80000000u);    // bit 31 = (rating of i >= average of i)
-            len = (int)ax.y;
-        }
-        int incl = len;
+    // Many raters: one batch per warp.  Few raters (fewer batches than warps): every warp walks every
+    // batch and takes every gwarps-th chunk of 32 products, so the whole group stays busy.
+    const bool coop = CTA_ROW && ((hi - lo + 31) >> 5) < gwarps;
+    const int bfirst = coop ? 0 : gw, bstride = coop ? 1 : gwarps;
+    const int cfirst = coop ? gw : 0, cstride = coop ? gwarps : 1;
+    constexpr int UC = 2;                                  // chunks in flight per warp
+    RaterDesc nxt = load_rater(a, lo + bfirst * 32 + lane, hi);
+    for (int b0 = lo + bfirst * 32; b0 < hi; b0 += bstride * 32) {
+        const RaterDesc cur = nxt;
+        nxt = load_rater(a, b0 + bstride * 32 + lane, hi);  // prefetch the next batch of this warp
+        int incl = cur.len;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, incl, off);
             if (lane >= off) incl += t;
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
-        const int excl = incl - len;
-        for (int t0 = 0; t0 < total; t0 += 32) {
-            const int t = t0 + lane;
-            int l = 0;                                     // smallest lane with incl > t
+        const int excl = incl - cur.len;
+        for (int t0 = cfirst * 32; t0 < total; t0 += cstride * 32 * UC) {
+            uint2 en[UC];
+            unsigned st_l[UC];
+            double ci_l[UC], mu_l[UC];
+            bool valid[UC];
 #pragma unroll
-            for (int step = 16; step >= 1; step >>= 1) {
-                const int v = __shfl_sync(0xffffffffu, incl, l + step - 1);
-                if (v <= t) l += step;
+            for (int u = 0; u < UC; ++u) {
+                const int t = t0 + u * cstride * 32 + lane;
+                int l = 0;                                 // smallest lane with incl > t
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const int v = __shfl_sync(0xffffffffu, incl, l + step - 1);
+                    if (v <= t) l += step;
+                }
+                st_l[u] = __shfl_sync(0xffffffffu, cur.start, l);
+                const int ex_l = __shfl_sync(0xffffffffu, excl, l);
+                ci_l[u] = __shfl_sync(0xffffffffu, cur.ci, l);
+                mu_l[u] = __shfl_sync(0xffffffffu, cur.mu, l);
+                valid[u] = t < total;
+                if (valid[u]) en[u] = ld_ent(a.tcsr_ent + ((st_l[u] & 0x7FFFFFFFu) + (unsigned)(t - ex_l)));
             }
-            const unsigned st_l = __shfl_sync(0xffffffffu, start, l);
-            const int ex_l = __shfl_sync(0xffffffffu, excl, l);
-            const double ci_l = __shfl_sync(0xffffffffu, ci, l);
-            const double mu_l = __shfl_sync(0xffffffffu, mu, l);
-            if (t < total) {
-                const uint2 en = ld_ent(a.tcsr_ent + ((st_l & 0x7FFFFFFFu) + (unsigned)(t - ex_l)));
-                const int oj = ent_item(en.x);
-                const double cj = (double)__uint_as_float(en.y) - mu_l;
-                const double p = __dmul_rn(ci_l, cj);
-                const int q = qbase - min(cls_i, ent_cls(en.x));
+#pragma unroll
+            for (int u = 0; u < UC; ++u) {
+                if (!valid[u]) continue;
+                const int oj = ent_item(en[u].x);
+                const double cj = (double)__uint_as_float(en[u].y) - mu_l[u];
+                const double p = __dmul_rn(ci_l[u], cj);
+                const int q = qbase - min(cls_i, ent_cls(en[u].x));
                 const long long fx = __double2ll_rn(p * pow2d(q));
-                const unsigned agree = ((unsigned)ent_ge(en.x) == (st_l >> 31)) ? 1u : 0u;
+                const unsigned agree = ((unsigned)ent_ge(en[u].x) == (st_l[u] >> 31)) ? 1u : 0u;
                 int slot;
                 bool ok = true;
                 if (direct) {
@@ -159,10 +189,10 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, int cells_
                     slot = (int)__umulhi((unsigned)oj * 2654435761u, (unsigned)ncell);
                     ok = false;
                     for (int probe = 0; probe < ncell; ++probe) {
-                        unsigned cur = *(volatile unsigned *)&T[slot].key;
-                        if (cur != key) {
-                            if (cur == 0u) cur = atomicCAS(&T[slot].key, 0u, key);
-                            if (cur != 0u && cur != key) { slot = (slot + 1 == ncell) ? 0 : slot + 1; continue; }
+                        unsigned c = *(volatile unsigned *)&T[slot].key;
+                        if (c != key) {
+                            if (c == 0u) c = atomicCAS(&T[slot].key, 0u, key);
+                            if (c != 0u && c != key) { slot = (slot + 1 == ncell) ? 0 : slot + 1; continue; }
                         }
                         ok = true;
                         break;
@@ -184,64 +214,128 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, int cells_
     }
     group_sync<CTA_ROW>();
 
-    // ---- epilogue: similarity, filter, label; append to both rows' record lists ------------------
-    // baselinerSim.py:163-173 / :125-141, :89, :95, :191, :207
-    Rec *__restrict__ rec = reinterpret_cast<Rec *>(a.rec);
-    const long long base_i = a.rec_ptr[row];
-    const int cap_i = (int)(a.rec_ptr[row + 1] - base_i);
-    int nent = 0;
-    for (int s0 = 0; s0 < ncell; s0 += gthreads) {
-        const int s = s0 + gtid;
-        bool keep = false;
-        double sim = 0.0;
-        unsigned jitem = 0u, n = 0u, mutu = 0u;
-        int label = 0;
+    // ---- index list of the occupied cells (order irrelevant) ---------------------------------------
+    int n_ent = 0;
+    for (int s0 = gw * 32; s0 < ncell; s0 += gthreads) {
+        const int s = s0 + lane;
+        bool occ = false;
         if (s < ncell) {
-            const uint4 cv = reinterpret_cast<const uint4 *>(T)[s];
-            int oj;
-            bool occ;
-            if (direct) { n = cv.x + cv.y; mutu = cv.x; occ = n != 0u; oj = top_ord - s; }
-            else { occ = cv.x != 0u; oj = (int)cv.x - 1; n = cv.y >> 16; mutu = cv.y & 0xFFFFu; }
-            if (occ) {
-                ++nent;
-                const OStat sj = ostat[oj];
-                const int q = qbase - min(cls_i, int(sj.prefix_cls & 0xFFu));
-                const long long fx = (long long)(((unsigned long long)cv.w << 32) | (unsigned long long)cv.z);
-                const double inner = (double)fx * pow2d(-q);
-                const double dd = __dmul_rn(si.den, sj.den);
-                const double cosv = (dd != 0.0) ? __ddiv_rn(inner, dd) : 0.0;
-                const int mn = min((int)n, a.num_atleast);
-                sim = __ddiv_rn(__dmul_rn(cosv, (double)mn), (double)a.num_atleast);
-                label = ((sj.prefix_cls >> 8) != prefix_i) ? 1 : 0;
-                jitem = sj.item;
-                keep = sim != 0.0 && mutu != 0u;
+            const uint2 kc = *reinterpret_cast<const uint2 *>(&T[s]);
+            occ = direct ? (kc.x | kc.y) != 0u : kc.x != 0u;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, occ);
+        if (m) {
+            int base = n_ent;
+            if (CTA_ROW) {
+                if (lane == 0) base = atomicAdd(s_cnt, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+            }
+            if (occ) occ_list[base + __popc(m & lt_mask)] = (IDX)s;
+            n_ent += __popc(m);
+        }
+    }
+    group_sync<CTA_ROW>();
+    if (CTA_ROW) n_ent = *s_cnt;
+    if (gtid == 0 && n_ent) a.row_npairs[row] += n_ent;     // this row's group is the only writer
+
+    // ---- epilogue pass 1: similarity, filter, label of every occupied cell, in place ---------------
+    // baselinerSim.py:163-173 / :125-141, :89, :95, :191, :207.  A kept cell becomes the 16-byte
+    // neighbour record of row `row` ({pack, sim bits}); a dropped one becomes zero.
+    constexpr int EU = 2;
+    int nkept = 0;
+    for (int i0 = gtid; i0 < n_ent; i0 += gthreads * EU) {
+        uint4 cv[EU];
+        int sidx[EU];
+        unsigned n[EU], mutu[EU];
+        OStat sj[EU];
+#pragma unroll
+        for (int u = 0; u < EU; ++u) {
+            const int i = i0 + u * gthreads;
+            sidx[u] = -1;
+            if (i < n_ent) {
+                sidx[u] = (int)occ_list[i];
+                cv[u] = T4[sidx[u]];
+                int oj;
+                if (direct) { n[u] = cv[u].x + cv[u].y; mutu[u] = cv[u].x; oj = top_ord - sidx[u]; }
+                else { oj = (int)cv[u].x - 1; n[u] = cv[u].y >> 16; mutu[u] = cv[u].y & 0xFFFFu; }
+                sj[u] = ostat[oj];
             }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (m) {
-            int basep = 0;
-            if (lane == 0) basep = atomicAdd(a.rec_cnt + row, __popc(m));
-            basep = __shfl_sync(0xffffffffu, basep, 0);
-            if (keep) {
+#pragma unroll
+        for (int u = 0; u < EU; ++u) {
+            if (sidx[u] < 0) continue;
+            uint4 out = make_uint4(0u, 0u, 0u, 0u);
+            const int q = qbase - min(cls_i, int(sj[u].prefix_cls & 0xFFu));
+            const long long fx = (long long)(((unsigned long long)cv[u].w << 32) | (unsigned long long)cv[u].z);
+            if (fx == 0 || mutu[u] == 0u) { T4[sidx[u]] = out; continue; }     // sim == 0 or mutu == 0: filtered
+            const double inner = (double)fx * pow2d(-q);
+            const double dd = __dmul_rn(si.den, sj[u].den);
+            const double cosv = (dd != 0.0) ? __ddiv_rn(inner, dd) : 0.0;
+            const int mn = min((int)n[u], a.num_atleast);
+            const double sim = __ddiv_rn(__dmul_rn(cosv, (double)mn), (double)a.num_atleast);
+            if (sim != 0.0 && mutu[u] != 0u) {
+                ++nkept;
+                const unsigned long long pk = rec_pack(sj[u].item, n[u], mutu[u]);
                 const unsigned long long sb = (unsigned long long)__double_as_longlong(sim);
-                const int pos = basep + __popc(m & ((1u << lane) - 1u));
-                if (pos < cap_i) rec[base_i + pos] = Rec{sb, rec_pack(jitem, n, mutu)};
-                else atomicExch(a.error_flag, 2);
-                const long long base_j = a.rec_ptr[jitem];
-                const int cap_j = (int)(a.rec_ptr[jitem + 1] - base_j);
-                const int p2 = atomicAdd(a.rec_cnt + jitem, 1);
-                if (p2 < cap_j) rec[base_j + p2] = Rec{sb, rec_pack((unsigned)row, n, mutu)};
-                else atomicExch(a.error_flag, 2);
-                if (label) { a.bb[row] = 1; a.bb[jitem] = 1; }
+                out = make_uint4((unsigned)pk, (unsigned)(pk >> 32), (unsigned)sb, (unsigned)(sb >> 32));
+                if ((sj[u].prefix_cls >> 8) != prefix_i) { a.bb[row] = 1; a.bb[sj[u].item] = 1; }
             }
+            T4[sidx[u]] = out;
         }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) nent += __shfl_xor_sync(0xffffffffu, nent, off);
-    if (lane == 0 && nent) {
-        if (CTA_ROW) atomicAdd(a.row_npairs + row, nent); else a.row_npairs[row] += nent;
+    for (int off = 16; off > 0; off >>= 1) nkept += __shfl_xor_sync(0xffffffffu, nkept, off);
+    if (nkept == 0) return;                                // warp-uniform; no barrier follows
+
+    // ---- epilogue pass 2: one reservation per warp in the row's own list, then append the records
+    // to the own list (compacted) and to each neighbour's list (one cursor bump per record) --------
+    Rec *__restrict__ rec = reinterpret_cast<Rec *>(a.rec);
+    const long long base_i = a.rec_ptr[row];
+    const int cap_i = (int)(a.rec_ptr[row + 1] - base_i);
+    int wbase = 0;
+    if (lane == 0) wbase = atomicAdd(a.rec_cnt + row, nkept);
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (wbase + nkept > cap_i) {
+        if (lane == 0) atomicExch(a.error_flag, 2);
+        return;
+    }
+    for (int i0 = gw * 32; i0 < n_ent; i0 += gthreads * EU) {
+        uint4 cv[EU];
+        bool keep[EU];
+        long long base_j[EU];
+        int cap_j[EU], p2[EU];
+#pragma unroll
+        for (int u = 0; u < EU; ++u) {
+            const int i = i0 + u * gthreads + lane;
+            cv[u] = (i < n_ent) ? T4[occ_list[i]] : make_uint4(0u, 0u, 0u, 0u);
+            keep[u] = (cv[u].z | cv[u].w) != 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < EU; ++u) {
+            if (keep[u]) {
+                const int jitem = int(cv[u].x & 0xFFFFFFu);
+                base_j[u] = a.rec_ptr[jitem];
+                cap_j[u] = (int)(a.rec_ptr[jitem + 1] - base_j[u]);
+                p2[u] = atomicAdd(a.rec_cnt + jitem, 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < EU; ++u) {
+            const unsigned m = __ballot_sync(0xffffffffu, keep[u]);
+            if (keep[u]) {
+                const unsigned long long pk = ((unsigned long long)cv[u].y << 32) | cv[u].x;
+                const unsigned long long sb = ((unsigned long long)cv[u].w << 32) | cv[u].z;
+                rec[base_i + wbase + __popc(m & lt_mask)] = Rec{sb, pk};
+                if (p2[u] < cap_j[u]) rec[base_j[u] + p2[u]] = Rec{sb, (pk & ~0xFFFFFFull) | (unsigned long long)row};
+                else atomicExch(a.error_flag, 2);
+            }
+            wbase += __popc(m);
+        }
     }
 }
+
+// shared memory per row: cells_cap cells + cells_cap 16-bit slot indices
+__host__ __device__ constexpr size_t row_smem_bytes(int cells_cap) { return (size_t)cells_cap * (sizeof(Cell) + 2); }
 
 // one warp per row, tables in shared memory, rows sorted by descending work
 __global__ void __launch_bounds__(128) tri_warp_kernel(xmap_sim_args a, const int32_t *__restrict__ rows, int n_rows,
@@ -250,22 +344,32 @@ __global__ void __launch_bounds__(128) tri_warp_kernel(xmap_sim_args a, const in
     const int warp = threadIdx.x >> 5;
     const int r = blockIdx.x * (blockDim.x >> 5) + warp;
     if (r >= n_rows) return;
-    tri_row<false>(a, reinterpret_cast<Cell *>(smem_raw) + (size_t)warp * cells_cap, cells_cap, rows[r]);
+    Cell *T = reinterpret_cast<Cell *>(smem_raw) + (size_t)warp * cells_cap;
+    unsigned short *occ = reinterpret_cast<unsigned short *>(smem_raw + (size_t)(blockDim.x >> 5) * cells_cap * sizeof(Cell)) +
+                          (size_t)warp * cells_cap;
+    tri_row<false, unsigned short>(a, T, occ, nullptr, cells_cap, rows[r]);
 }
 
 // one CTA per row, table in shared memory
 __global__ void __launch_bounds__(512) tri_cta_kernel(xmap_sim_args a, const int32_t *__restrict__ rows, int n_rows,
                                                        int cells_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    tri_row<true>(a, reinterpret_cast<Cell *>(smem_raw), cells_cap, rows[blockIdx.x]);
+    __shared__ int s_cnt;
+    tri_row<true, unsigned short>(a, reinterpret_cast<Cell *>(smem_raw),
+                                  reinterpret_cast<unsigned short *>(smem_raw + (size_t)cells_cap * sizeof(Cell)),
+                                  &s_cnt, cells_cap, rows[blockIdx.x]);
 }
 
-// persistent CTAs, tables in global memory (rows whose table exceeds shared memory)
+// persistent CTAs, tables in global memory (rows whose table exceeds shared memory):
+// per CTA cells_cap cells followed by cells_cap 32-bit slot indices
 __global__ void __launch_bounds__(512) tri_gmem_kernel(xmap_sim_args a, const int32_t *__restrict__ rows, int n_rows,
-                                                        int cells_cap, Cell *__restrict__ gtab) {
-    Cell *T = gtab + (size_t)blockIdx.x * cells_cap;
+                                                        int cells_cap, unsigned char *__restrict__ gtab) {
+    __shared__ int s_cnt;
+    unsigned char *mine = gtab + (size_t)blockIdx.x * (((size_t)cells_cap * (sizeof(Cell) + 4) + 15) & ~(size_t)15);
+    Cell *T = reinterpret_cast<Cell *>(mine);
+    unsigned *occ = reinterpret_cast<unsigned *>(mine + (size_t)cells_cap * sizeof(Cell));
     for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
-        tri_row<true>(a, T, cells_cap, rows[r]);
+        tri_row<true, unsigned>(a, T, occ, &s_cnt, cells_cap, rows[r]);
         __syncthreads();
     }
 }
@@ -274,8 +378,8 @@ __global__ void __launch_bounds__(512) tri_gmem_kernel(xmap_sim_args a, const in
 // Selection (extender.py:16-44).
 // --------------------------------------------------------------------------
 constexpr int SEL_BINS = 256;
-constexpr int SEL_BUF = 192;                  // survivors per list
-constexpr int SEL_BYTES = SEL_BUF * 16;       // >= 2 * SEL_BINS * 4
+constexpr int SEL_BUF = 192;                      // survivors per list
+constexpr int SEL_WARP_BYTES = 2 * SEL_BUF * 16;  // two survivor buffers; aliases the 2 x 256-bin histogram
 
 // 16 sub-bins per octave for |sim| in [2^-16, 2): bits 62..48 of the double, offset so that
 // 2^-16 maps to bin 0; smaller values share bin 0, values >= 1 clamp to the top bin.
@@ -289,7 +393,7 @@ __device__ __forceinline__ int sim_bin(unsigned long long key_bits) {
 //   BB row: list 0 = other-domain neighbours, list 1 = same-domain (extender.py:30-35)
 //   NB row: list 0 = BB neighbours, list 1 = every neighbour (extender.py:37-43, bug :41-42)
 __device__ __forceinline__ unsigned list_bits(const xmap_sim_args &a, bool bb_i, int dom_i, int j) {
-    if (bb_i) return ((a.contains[j] >> dom_i) & 1) ? 2u : 1u;
+    if (bb_i) return ((__ldg(a.contains + j) >> dom_i) & 1) ? 2u : 1u;
     return 2u | (a.bb[j] ? 1u : 0u);
 }
 
@@ -298,9 +402,12 @@ struct __align__(16) Surv {
     int q, j;
 };
 
+constexpr int SU = 4;                             // records per lane per step of the streaming passes
+constexpr int SEL_DIRECT = 64;                    // lists up to this long skip the histogram
+
 __global__ void __launch_bounds__(128) select_warp_kernel(xmap_sim_args a, const int32_t *__restrict__ rows,
                                                           int n_rows) {
-    __shared__ __align__(16) unsigned char s_sel[4][SEL_BYTES];
+    __shared__ __align__(16) unsigned char s_sel[4][SEL_WARP_BYTES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int r = blockIdx.x * 4 + warp;
     if (r >= n_rows) return;
@@ -315,8 +422,7 @@ __global__ void __launch_bounds__(128) select_warp_kernel(xmap_sim_args a, const
     const Rec *__restrict__ R = reinterpret_cast<const Rec *>(a.rec) + a.rec_ptr[row];
     const bool bb_i = a.bb[row] != 0;
     const int dom_i = a.dom_code[row];
-    unsigned *hist = reinterpret_cast<unsigned *>(s_sel[warp]);      // [2][SEL_BINS]
-    Surv *buf = reinterpret_cast<Surv *>(s_sel[warp]);
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     if (m <= 32) {
         // the whole list sits in one register per lane: rank by counting
@@ -356,101 +462,139 @@ __global__ void __launch_bounds__(128) select_warp_kernel(xmap_sim_args a, const
         return;
     }
 
-    // ---- pass A: per-list histogram of |sim| -----------------------------------------------------
-    for (int b = lane; b < 2 * SEL_BINS; b += 32) hist[b] = 0u;
-    __syncwarp();
-    int n0 = 0, n1 = 0;
-    for (int q = lane; q < m; q += 32) {
-        const Rec v = R[q];
-        const unsigned lb = list_bits(a, bb_i, dom_i, rec_item(v.pack));
-        const int bin = sim_bin(v.sim);
-        if (lb & 1u) { atomicAdd(&hist[bin], 1u); ++n0; }
-        if (lb & 2u) { atomicAdd(&hist[SEL_BINS + bin], 1u); ++n1; }
-    }
+    unsigned *hist = reinterpret_cast<unsigned *>(s_sel[warp]);      // [2][SEL_BINS]
+    Surv *buf[2] = {reinterpret_cast<Surv *>(s_sel[warp]), reinterpret_cast<Surv *>(s_sel[warp]) + SEL_BUF};
+    int nb[2] = {0, 0}, want[2] = {0, 0}, bstar[2] = {0, 0};
+    bool overflow[2] = {false, false};
+    if (m > SEL_DIRECT) {
+        // ---- pass A: per-list histogram of |sim| -------------------------------------------------
+        for (int b = lane; b < 2 * SEL_BINS; b += 32) hist[b] = 0u;
+        __syncwarp();
+        int n0 = 0, n1 = 0;
+        for (int q0 = 0; q0 < m; q0 += 32 * SU) {
+            Rec v[SU];
+            unsigned lb[SU];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        n0 += __shfl_xor_sync(0xffffffffu, n0, off);
-        n1 += __shfl_xor_sync(0xffffffffu, n1, off);
-    }
-    __syncwarp();
-    int bstar[2], want[2];
-    for (int list = 0; list < 2; ++list) {
-        want[list] = min(K, list == 0 ? n0 : n1);
-        bstar[list] = 0;
-        if (want[list] == 0) continue;
-        // largest bin b* such that #(bin >= b*) >= want: scan the histogram from the top
-        int run = 0;
-        bool found = false;
-        for (int hb = SEL_BINS - 32; hb >= 0 && !found; hb -= 32) {
-            unsigned suf = hist[list * SEL_BINS + hb + lane];          // suffix sums, highest lane = highest bin
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const unsigned t = __shfl_down_sync(0xffffffffu, suf, off);
-                if (lane + off < 32) suf += t;
+            for (int u = 0; u < SU; ++u) {
+                const int q = q0 + u * 32 + lane;
+                v[u] = (q < m) ? R[q] : Rec{0ull, 0ull};
             }
-            const unsigned hit = __ballot_sync(0xffffffffu, run + (int)suf >= want[list]);
-            if (hit) { bstar[list] = hb + (31 - __clz(hit)); found = true; }
-            else run += (int)__shfl_sync(0xffffffffu, suf, 0);
+#pragma unroll
+            for (int u = 0; u < SU; ++u)
+                lb[u] = (q0 + u * 32 + lane < m) ? list_bits(a, bb_i, dom_i, rec_item(v[u].pack)) : 0u;
+#pragma unroll
+            for (int u = 0; u < SU; ++u) {
+                const int bin = sim_bin(v[u].sim);
+                if (lb[u] & 1u) { atomicAdd(&hist[bin], 1u); ++n0; }
+                if (lb[u] & 2u) { atomicAdd(&hist[SEL_BINS + bin], 1u); ++n1; }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            n0 += __shfl_xor_sync(0xffffffffu, n0, off);
+            n1 += __shfl_xor_sync(0xffffffffu, n1, off);
+        }
+        __syncwarp();
+        for (int list = 0; list < 2; ++list) {
+            want[list] = min(K, list == 0 ? n0 : n1);
+            if (want[list] == 0) continue;
+            // largest bin b* such that #(bin >= b*) >= want: scan the histogram from the top
+            int run = 0;
+            bool found = false;
+            for (int hb = SEL_BINS - 32; hb >= 0 && !found; hb -= 32) {
+                unsigned suf = hist[list * SEL_BINS + hb + lane];      // suffix sums, highest lane = highest bin
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const unsigned t = __shfl_down_sync(0xffffffffu, suf, off);
+                    if (lane + off < 32) suf += t;
+                }
+                const unsigned hit = __ballot_sync(0xffffffffu, run + (int)suf >= want[list]);
+                if (hit) { bstar[list] = hb + (31 - __clz(hit)); found = true; }
+                else run += (int)__shfl_sync(0xffffffffu, suf, 0);
+            }
+        }
+        __syncwarp();                                      // the histogram is dead; its memory becomes the survivor buffers
+    }
+    // ---- pass B: the survivors of both lists (everything when the list fits the buffer) ------------
+    for (int q0 = 0; q0 < m; q0 += 32 * SU) {
+        Rec v[SU];
+        unsigned lb[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int q = q0 + u * 32 + lane;
+            v[u] = (q < m) ? R[q] : Rec{0ull, 0ull};
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u)
+            lb[u] = (q0 + u * 32 + lane < m) ? list_bits(a, bb_i, dom_i, rec_item(v[u].pack)) : 0u;
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const unsigned long long key = v[u].sim & 0x7FFFFFFFFFFFFFFFull;
+            const int bin = sim_bin(key);
+#pragma unroll
+            for (int list = 0; list < 2; ++list) {
+                const bool take = ((lb[u] >> list) & 1u) && bin >= bstar[list];
+                const unsigned mk = __ballot_sync(0xffffffffu, take);
+                if (overflow[list] || nb[list] + __popc(mk) > SEL_BUF) { overflow[list] = true; continue; }
+                if (take) buf[list][nb[list] + __popc(mk & lt_mask)] = Surv{key, q0 + u * 32 + lane, rec_item(v[u].pack)};
+                nb[list] += __popc(mk);
+            }
         }
     }
-    __syncwarp();                                          // the histogram is dead; its memory becomes the survivor buffer
-    // ---- pass B: survivors of the threshold bin, then K arg-best rounds ---------------------------
+    if (m <= SEL_DIRECT) { want[0] = min(K, nb[0]); want[1] = min(K, nb[1]); }
+    __syncwarp();
+    // ---- K arg-best rounds per list --------------------------------------------------------------
     for (int list = 0; list < 2; ++list) {
         int got = 0;
         const size_t o = ((size_t)row * 2 + list) * K;
-        if (want[list] > 0) {
-            int nb = 0;                                    // warp-uniform
-            bool overflow = false;
-            for (int q0 = 0; q0 < m; q0 += 32) {
-                const int q = q0 + lane;
-                bool take = false;
-                unsigned long long key = 0ull;
-                int j = 0;
-                if (q < m) {
+        unsigned long long last_k = ~0ull; int last_t = -1;
+        if (!overflow[list] && nb[list] <= 32) {
+            // one survivor per lane: rank by counting, every winner writes its own table entry
+            Surv mine{0ull, -1, 0x7FFFFFFF};
+            if (lane < nb[list]) mine = buf[list][lane];
+            int rank = 0;
+            for (int t = 0; t < nb[list]; ++t) {
+                const unsigned long long k2 = __shfl_sync(0xffffffffu, mine.key, t);
+                const int j2 = __shfl_sync(0xffffffffu, mine.j, t);
+                if (better(k2, j2, mine.key, mine.j)) ++rank;
+            }
+            if (lane < nb[list] && rank < want[list]) {
+                const Rec v = R[mine.q];
+                a.tab_idx[o + rank] = mine.j;
+                a.tab_sim[o + rank] = __longlong_as_double((long long)v.sim);
+                a.tab_mutu[o + rank] = rec_mutu(v.pack); a.tab_n[o + rank] = rec_n(v.pack);
+            }
+            if (lane == 0) a.tab_len[(size_t)row * 2 + list] = want[list];
+            continue;
+        }
+        for (int rr = 0; rr < want[list]; ++rr) {
+            unsigned long long bk = 0; int bt = 0x7FFFFFFF, bp = -1;
+            if (!overflow[list]) {
+                for (int q = lane; q < nb[list]; q += 32) {
+                    const Surv sv = buf[list][q];
+                    if (rr > 0 && !better(last_k, last_t, sv.key, sv.j)) continue;
+                    if (bp < 0 || better(sv.key, sv.j, bk, bt)) { bk = sv.key; bt = sv.j; bp = sv.q; }
+                }
+            } else {   // many equal similarities in the threshold bin: rounds over all records
+                for (int q = lane; q < m; q += 32) {
                     const Rec v = R[q];
-                    j = rec_item(v.pack);
-                    if ((list_bits(a, bb_i, dom_i, j) >> list) & 1u) {
-                        key = v.sim & 0x7FFFFFFFFFFFFFFFull;
-                        take = sim_bin(key) >= bstar[list];
-                    }
+                    const int tt = rec_item(v.pack);
+                    if (!((list_bits(a, bb_i, dom_i, tt) >> list) & 1u)) continue;
+                    const unsigned long long kk = v.sim & 0x7FFFFFFFFFFFFFFFull;
+                    if (rr > 0 && !better(last_k, last_t, kk, tt)) continue;
+                    if (bp < 0 || better(kk, tt, bk, bt)) { bk = kk; bt = tt; bp = q; }
                 }
-                const unsigned mk = __ballot_sync(0xffffffffu, take);
-                if (nb + __popc(mk) > SEL_BUF) { overflow = true; break; }
-                if (take) buf[nb + __popc(mk & ((1u << lane) - 1u))] = Surv{key, q, j};
-                nb += __popc(mk);
             }
-            __syncwarp();
-            unsigned long long last_k = ~0ull; int last_t = -1;
-            for (int rr = 0; rr < want[list]; ++rr) {
-                unsigned long long bk = 0; int bt = 0x7FFFFFFF, bp = -1;
-                if (!overflow) {
-                    for (int q = lane; q < nb; q += 32) {
-                        const Surv sv = buf[q];
-                        if (rr > 0 && !better(last_k, last_t, sv.key, sv.j)) continue;
-                        if (bp < 0 || better(sv.key, sv.j, bk, bt)) { bk = sv.key; bt = sv.j; bp = sv.q; }
-                    }
-                } else {   // many equal similarities in the threshold bin: rounds over all records
-                    for (int q = lane; q < m; q += 32) {
-                        const Rec v = R[q];
-                        const int tt = rec_item(v.pack);
-                        if (!((list_bits(a, bb_i, dom_i, tt) >> list) & 1u)) continue;
-                        const unsigned long long kk = v.sim & 0x7FFFFFFFFFFFFFFFull;
-                        if (rr > 0 && !better(last_k, last_t, kk, tt)) continue;
-                        if (bp < 0 || better(kk, tt, bk, bt)) { bk = kk; bt = tt; bp = q; }
-                    }
-                }
-                warp_argbest(bk, bt, bp);
-                if (bp < 0) break;
-                if (lane == 0) {
-                    const Rec v = R[bp];
-                    a.tab_idx[o + rr] = bt;
-                    a.tab_sim[o + rr] = __longlong_as_double((long long)v.sim);
-                    a.tab_mutu[o + rr] = rec_mutu(v.pack); a.tab_n[o + rr] = rec_n(v.pack);
-                }
-                last_k = bk; last_t = bt;
-                got = rr + 1;
+            warp_argbest(bk, bt, bp);
+            if (bp < 0) break;
+            if (lane == 0) {
+                const Rec v = R[bp];
+                a.tab_idx[o + rr] = bt;
+                a.tab_sim[o + rr] = __longlong_as_double((long long)v.sim);
+                a.tab_mutu[o + rr] = rec_mutu(v.pack); a.tab_n[o + rr] = rec_n(v.pack);
             }
-            __syncwarp();
+            last_k = bk; last_t = bt;
+            got = rr + 1;
         }
         if (lane == 0) a.tab_len[(size_t)row * 2 + list] = got;
     }
@@ -680,18 +824,18 @@ extern "C" int xmap_sim_accumulate(const xmap_sim_args *args_h, const int32_t *r
         if (gtab_ctas < 1) return fail_msg("xmap_sim_accumulate: gtab_ctas must be positive");
         const int grid = n_rows < gtab_ctas ? n_rows : gtab_ctas;
         tri_gmem_kernel<<<grid, threads_per_row < 64 ? 64 : threads_per_row, 0, st>>>(
-            *args_h, rows, n_rows, cells_cap, reinterpret_cast<Cell *>(gtab));
+            *args_h, rows, n_rows, cells_cap, reinterpret_cast<unsigned char *>(gtab));
         XMAP_LAUNCH_CHECK();
         return 0;
     }
     if (cells_cap > XMAP_SIM_MAX_SMEM_CELLS) return fail_msg("xmap_sim_accumulate: cells_cap exceeds shared memory");
     if (threads_per_row == 32) {
-        const size_t smem = (size_t)4 * cells_cap * sizeof(Cell);
+        const size_t smem = 4 * row_smem_bytes(cells_cap);
         if (smem > 227 * 1024) return fail_msg("xmap_sim_accumulate: warp-row tables exceed shared memory");
         XMAP_CUDA(cudaFuncSetAttribute(tri_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tri_warp_kernel<<<(n_rows + 3) / 4, 128, smem, st>>>(*args_h, rows, n_rows, cells_cap);
     } else {
-        const size_t smem = (size_t)cells_cap * sizeof(Cell);
+        const size_t smem = row_smem_bytes(cells_cap);
         XMAP_CUDA(cudaFuncSetAttribute(tri_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tri_cta_kernel<<<n_rows, threads_per_row, smem, st>>>(*args_h, rows, n_rows, cells_cap);
     }

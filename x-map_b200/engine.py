@@ -8,6 +8,7 @@ sit on top of this module.  No CPU fallback exists: without a GPU and the built
 extension these functions raise.
 """
 import math
+import os
 from dataclasses import dataclass, field
 
 import torch
@@ -120,8 +121,15 @@ class SimTables:
         return 2 * int(self.row_npairs.sum().item())
 
 
-CELL_CLASSES = (256, 512, 1024, 2048, 4096, 8192, 14336)   # table capacities (16-byte cells) of the launches
-CELL_THREADS = (32, 32, 32, 128, 256, 512, 512)            # threads per row each capacity gets at least
+CELL_CLASSES = (256, 512, 1024, 2048, 4096, 8192, 12288)   # table capacities (16-byte cells) of the launches
+
+
+def _threads_for_cells(c):
+    """Threads per row a table capacity gets at least: ~8 cells per thread, so that shared memory
+    (the occupancy limiter) is matched by enough resident warps."""
+    cpt = int(os.environ.get("XMAP_CELLS_PER_THREAD", "8"))
+    return max(32, min(512, (c // cpt + 31) // 32 * 32))
+
 REC_BYTES = 16
 REC_CNT_LIMIT = 1 << 20                                     # n and mutu are 20-bit fields of a record
 
@@ -160,14 +168,14 @@ class SimEngine:
             raise N.NativeError("an item has >= 2^20 ratings: neighbour records hold 20-bit co-rating counts")
         self.ord = popularity_order(count)
         self.tcsr_ent = torch.empty(layout.nnz, dtype=torch.int64, device=dev)
-        self.csc_aux = torch.empty(layout.nnz, dtype=torch.int64, device=dev)
+        self.csc_aux = torch.empty((layout.nnz, 2), dtype=torch.int64, device=dev)
         self.ostat = torch.empty(max(I, 1) * 16, dtype=torch.uint8, device=dev)
         self.tri_work = torch.zeros(I, dtype=torch.int64, device=dev)
         ws_bytes = L.xmap_tri_workspace_bytes(layout.nnz)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         N.check(L.xmap_build_tri_layout(
             N.ptr(layout.csr_ptr), N.ptr(layout.csr_ent), N.ptr(layout.csc_ptr), N.ptr(layout.csc_ent),
-            N.ptr(layout.item_stats), N.ptr(meta.prefix_code), N.ptr(self.ord),
+            N.ptr(layout.user_mu), N.ptr(layout.item_stats), N.ptr(meta.prefix_code), N.ptr(self.ord),
             layout.n_users, I, layout.nnz, N.METHODS[method],
             N.ptr(self.tcsr_ent), N.ptr(self.csc_aux), N.ptr(self.ostat), N.ptr(self.tri_work),
             N.ptr(ws), ws_bytes, _stream_ptr()), "xmap_build_tri_layout")
@@ -201,7 +209,7 @@ class SimEngine:
         lay, m = self.lay, self.meta
         a = N.SimArgs()
         a.csc_ptr, a.csc_ent, a.csc_aux = N.ptr(lay.csc_ptr), N.ptr(lay.csc_ent), N.ptr(self.csc_aux)
-        a.tcsr_ent, a.user_mu = N.ptr(self.tcsr_ent), N.ptr(lay.user_mu)
+        a.tcsr_ent = N.ptr(self.tcsr_ent)
         a.ostat, a.ord, a.tri_work = N.ptr(self.ostat), N.ptr(self.ord), N.ptr(self.tri_work)
         a.dom_code, a.contains = N.ptr(m.dom_code), N.ptr(m.contains)
         a.n_items, a.method = lay.n_items, N.METHODS[self.method]
@@ -237,8 +245,7 @@ class SimEngine:
             classes.append(self.max_smem_cells)
         bounds = torch.tensor(classes, dtype=torch.int64, device=dev)
         cls = torch.bucketize(cells, bounds)                       # len(classes) = global-memory fallback
-        t_cells = torch.tensor([CELL_THREADS[min(q, len(CELL_THREADS) - 1)] if classes[q] > 1024 or q >= 3 else 32
-                                for q in range(len(classes))] + [512], dtype=torch.int64, device=dev)[cls]
+        t_cells = torch.tensor([_threads_for_cells(c) for c in classes] + [512], dtype=torch.int64, device=dev)[cls]
         t_work = torch.full_like(work, 32)
         t_work[work > 3072] = 128
         t_work[work > 8192] = 256
@@ -307,7 +314,7 @@ class SimEngine:
             gtab, ctas = None, 0
             if in_gmem:
                 ctas = min(int(r.numel()), 296)
-                need = ctas * cells_cap * 16
+                need = ctas * ((cells_cap * 20 + 15) // 16 * 16)
                 if self._gtab is None or self._gtab.numel() < need:
                     self._gtab = None
                     self._gtab = torch.empty(need, dtype=torch.uint8, device=self.device)
