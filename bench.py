@@ -302,35 +302,40 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_val = P_total / float(e2e_s)
 
-    # pipeline wall-time: similarity + X-SIM extension + generation (rank 0 owns extension here)
+    # pipeline wall-time: similarity + X-SIM extension (sharded by start) + generation (sharded by user)
     pipe = None
-    if not args.no_pipeline and rank == 0:
-        torch.cuda.synchronize()
+    for timed in ((False, True) if not args.no_pipeline else ()):      # one untimed pass first, like the warm-up steps
+        barrier()
         t0 = time.perf_counter()
         plan = X.build_plan(tabs, lay.item_stats[:, 3].contiguous(), meta.has_S, meta.has_T)
         torch.cuda.synchronize(); t1 = time.perf_counter()
         xe = X.XsimEngine(plan, 10)
-        res = xe.run()
-        torch.cuda.synchronize(); t2 = time.perf_counter()
+        res = MG.allreduce_xsim(xe.run(rank, world))
+        barrier(); t2 = time.perf_counter()
         ch = G.choose_mapping(res, "argmax", sim_method=args.method)
         mp = G.invert_mapping(res.start_item, ch, wl["n_items"])
-        ou, oi, orr, ot = G.build_alterego(lay, wl["ts"], mp)
-        torch.cuda.synchronize(); t3 = time.perf_counter()
+        ou, oi, orr, ot = MG.build_alterego_sharded(lay, wl["ts"], mp, MG.UserShard(lay.csr_ptr, rank, world))
+        n_rec = torch.tensor([ou.numel()], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(n_rec)
+        barrier(); t3 = time.perf_counter()
         combos = int(res.combos.sum().item())
         pipe = {"similarity_ms": ms_step, "extend_plan_ms": (t1 - t0) * 1e3, "extend_kernel_ms": (t2 - t1) * 1e3,
                 "generate_ms": (t3 - t2) * 1e3,
                 "alterego_pipeline_ms": ms_step + (t3 - t0) * 1e3,
                 "xsim_paths": combos, "xsim_paths_per_s": combos / max(t2 - t1, 1e-9),
                 "xsim_starts": int(res.start_item.numel()), "xsim_pairs": int(res.count.sum().item()),
-                "alterego_synthetic_records": int(ou.numel()), "bridge_pairs": plan.n_src,
-                "joint_pairs": plan.n_joint}
+                "alterego_synthetic_records": int(n_rec.item()), "bridge_pairs": plan.n_src,
+                "joint_pairs": plan.n_joint,
+                "sharding": "X-SIM by start item x%d, generation by user x%d (host wall-clock of rank 0 between barriers)" % (world, world)}
+        del plan, xe, res
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
         # the stage evaluates every unordered pair once: W/2 products of 8 B, one pass over the CSC
-        # (16 B per rating: entry + suffix extent), 2 x 16 B records written and read back per kept pair,
+        # (24 B per rating: entry + suffix extent + rater mean), 2 x 16 B records written and read back per kept pair,
         # and the tables out
-        alg_bytes = 8.0 * (wl["W"] / 2) + 16.0 * wl["nnz"] + 32.0 * P_kept + 80.0 * k * wl["n_items"]
+        alg_bytes = 8.0 * (wl["W"] / 2) + 24.0 * wl["nnz"] + 32.0 * P_kept + 80.0 * k * wl["n_items"]
         stage_gbs = alg_bytes / (ms_step * 1e-3) / 1e9
         # kernels: the accumulate launches are one kernel function per group width
         launches_plan, _ = eng.plan(None if world == 1 else shard.rows(dev))
@@ -379,7 +384,7 @@ def main():
                          "per_launch_ms_per_step": {kk: v[1] / args.steps for kk, v in prof.items()},
                          "note": "achieved = algorithmic bytes of the kernel (8 B per co-rating product for the "
                                  "accumulate kernels, 16 B per neighbour record for the selection kernels) / its "
-                                 "CUDA-event time; stage figure = (8*W/2 + 16*nnz + 32*P_kept + 80*k*I) / step time"},
+                                 "CUDA-event time; stage figure = (8*W/2 + 24*nnz + 32*P_kept + 80*k*I) / step time"},
             "pipeline": pipe,
         }
         if not args.no_cpu:

@@ -27,10 +27,23 @@ def main():
     eng._check_error()
     ok = all(torch.equal(getattr(ref, f), getattr(tabs, f)) for f in
              ("row_flags", "row_npairs", "row_nkept", "tab_len", "tab_idx", "tab_sim", "tab_mutu", "tab_n"))
+    # X-SIM extension sharded by start, generation sharded by user
+    from xmap_b200 import extend as X, generate as G
+    cnt = lay.item_stats[:, 3].contiguous()
+    plan = X.build_plan(ref, cnt, meta.has_S, meta.has_T)
+    res1 = X.XsimEngine(plan, 10).run()
+    resN = MG.allreduce_xsim(X.XsimEngine(X.build_plan(tabs, cnt, meta.has_S, meta.has_T), 10).run(rank, world))
+    ok = ok and all(torch.equal(getattr(res1, f), getattr(resN, f)) for f in
+                    ("count", "combos", "top_end", "top_xsim", "top_len"))
+    mp1 = G.invert_mapping(res1.start_item, G.choose_mapping(res1, "argmax"), case["n_items"])
+    mpN = G.invert_mapping(resN.start_item, G.choose_mapping(resN, "argmax"), case["n_items"])
+    a1 = G.build_alterego(lay, case["ts"], mp1)
+    aN = MG.build_alterego_sharded(lay, case["ts"], mpN, MG.UserShard(lay.csr_ptr, rank, world), gather=True)
+    ok = ok and torch.equal(mp1, mpN) and all(torch.equal(x, y) for x, y in zip(a1, aN))
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("multi-GPU (world=%d) result bit-identical to single GPU: %s" % (world, bool(flag.item())))
+        print("multi-GPU (world=%d) similarity tables, X-SIM top-m, mapping and AlterEgo records bit-identical to single GPU: %s" % (world, bool(flag.item())))
     dist.destroy_process_group()
     sys.exit(0 if flag.item() else 1)
 

@@ -287,9 +287,9 @@ def eval_plan_numpy(plan):
                 s = par_s[pp]
                 Nm = Nl + pv[0][pp]; Dm = Dl + pv[1][pp]; Cm = Cl * pv[2][pp]
                 a, b = rs_ptr[s], rs_ptr[s + 1]
-                Nn = (Nm + rv[0][a:b]) + rv[3][a:b]
-                Dd = (Dm + rv[1][a:b]) + rv[4][a:b]
-                cp = (Cm * rv[2][a:b]) * rv[5][a:b]
+                Nn = Nm + (rv[0][a:b] + rv[3][a:b])
+                Dd = Dm + (rv[1][a:b] + rv[4][a:b])
+                cp = Cm * (rv[2][a:b] * rv[5][a:b])
                 with np.errstate(invalid="ignore", divide="ignore"):
                     sp = np.where(Dd != 0, Nn / Dd, 0.0)
                 combos += b - a

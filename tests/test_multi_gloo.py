@@ -96,6 +96,55 @@ def test_record_exchange_world2():
     assert all(ok for _, ok in res)
 
 
+def _xsim_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from xmap_b200.multi import allreduce_xsim
+    from xmap_b200.extend import XsimResult
+    n, m = 37, 4
+    g = torch.Generator().manual_seed(9)
+    full = XsimResult(torch.arange(n, dtype=torch.int32), torch.randint(1, 50, (n,), generator=g, dtype=torch.int32),
+                      torch.randint(1, 500, (n,), generator=g), torch.randint(-1, 90, (n, m), generator=g, dtype=torch.int32),
+                      torch.randn(n, m, generator=g, dtype=torch.float64), torch.randint(0, m + 1, (n,), generator=g, dtype=torch.int32), 0)
+    mine = torch.zeros(n, dtype=torch.bool); mine[rank::world] = True
+    part = XsimResult(full.start_item, torch.where(mine, full.count, 0), torch.where(mine, full.combos, 0),
+                      torch.where(mine[:, None], full.top_end, -1), torch.where(mine[:, None], full.top_xsim, 0.0),
+                      torch.where(mine, full.top_len, 0), 0)
+    out = allreduce_xsim(part)
+    ok = all(torch.equal(getattr(out, f), getattr(full, f)) for f in ("count", "combos", "top_end", "top_xsim", "top_len"))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_xsim_allreduce_world2():
+    from tests import parity  # noqa: F401
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_xsim_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
+
+
+def test_user_shard_balances_ratings():
+    from xmap_b200.multi import UserShard
+    g = torch.Generator().manual_seed(4)
+    deg = (torch.rand(5000, generator=g) ** 3 * 200).int()
+    ptr = torch.zeros(5001, dtype=torch.int32); ptr[1:] = torch.cumsum(deg, 0)
+    for world in (1, 2, 4, 8):
+        sh = [UserShard(ptr, r, world) for r in range(world)]
+        assert sh[0].lo == 0 and sh[-1].hi == 5000 and all(a.hi == b.lo for a, b in zip(sh, sh[1:]))
+        loads = [int(ptr[s.hi] - ptr[s.lo]) for s in sh]
+        assert max(loads) <= sum(loads) / world + 200
+    e = UserShard(torch.zeros(1, dtype=torch.int32), 0, 2)
+    assert (e.lo, e.hi) == (0, 0)
+
+
 def test_row_shard_single_rank_and_edge_cases():
     from xmap_b200.multi import RowShard
     sh = RowShard(torch.tensor([5, 0, 7]), 0, 1)

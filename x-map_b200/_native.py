@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libxmap_b200.so")
+LIB_PATH = os.environ.get("XMAP_B200_LIB") or os.path.join(_HERE, "libxmap_b200.so")
 
 KMAX = 64
 METHODS = {"adjust_cosine": 0, "cosine": 1}
@@ -39,7 +39,7 @@ class XsimArgs(C.Structure):
         ("leg_e1", _p), ("leg_m1", _p), ("leg_f1", _p), ("leg_e2", _p), ("leg_m2", _p), ("leg_f2", _p),
         ("par_ptr", _p), ("par_s", _p), ("par_joint", _p), ("par_e", _p), ("par_m", _p), ("par_f", _p),
         ("rs_ptr", _p), ("rs_end", _p),
-        ("rs_e1", _p), ("rs_m1", _p), ("rs_f1", _p), ("rs_e2", _p), ("rs_m2", _p), ("rs_f2", _p),
+        ("rs_n", _p), ("rs_d", _p), ("rs_c", _p),
         ("hash_off", _p), ("hash_size", _p), ("hash_cells", _p), ("epoch", C.c_uint32),
         ("n_rounds", C.c_int32), ("round_ptr_h", _p), ("pair_dst", _p), ("pair_src", _p),
         ("top_m", C.c_int32), ("mode", C.c_int32),

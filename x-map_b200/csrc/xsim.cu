@@ -7,7 +7,7 @@
 // fixed order, so a cell's sum depends only on the path structure (identical
 // items get bit-identical X-SIM values, which keeps top-k ties deterministic).
 //
-// Bound by accumulator traffic: each combo reads 7 doubles + 1 int of the
+// Bound by accumulator traffic: each combo reads 3 doubles + 1 int of the
 // right-segment table (coalesced across the warp, L2-resident because a bridge
 // source is shared by many starts) and does one hash-cell read-modify-write.
 #include "common.cuh"
@@ -28,31 +28,24 @@ struct XCell {
 // find-or-insert: returns the cell index or -1 (table full).  Only one warp (accumulate) or one
 // CTA (merge) ever writes a given table; the CAS resolves lanes racing for one empty cell, and the
 // thread whose CAS inserts the key initialises the values.
-__device__ __forceinline__ int table_slot(XCell *tab, int hsize, int shift, unsigned long long key, unsigned epoch) {
-    const unsigned mask = (unsigned)hsize - 1u;
-    unsigned slot = (((unsigned)key - 1u) * 2654435761u) >> shift;
+__device__ __forceinline__ int table_slot(XCell *tab, int hsize, unsigned long long key, unsigned epoch) {
+    int slot = (int)__umulhi(((unsigned)key - 1u) * 2654435761u, (unsigned)hsize);
     for (int probe = 0; probe < hsize; ++probe) {
         unsigned long long cur = *(volatile unsigned long long *)&tab[slot].key;
         if (cur != key) {
             if ((unsigned)(cur >> 32) != epoch) {          // empty (stale epoch): try to claim it
                 const unsigned long long old = atomicCAS(&tab[slot].key, cur, key);
-                if (old == cur) { tab[slot].num = 0.0; tab[slot].den = 0.0; return (int)slot; }
+                if (old == cur) { tab[slot].num = 0.0; tab[slot].den = 0.0; return slot; }
                 cur = old;
-                if (cur == key) return (int)slot;
+                if (cur == key) return slot;
                 if ((unsigned)(cur >> 32) != epoch) { --probe; continue; }   // changed under us but still empty: retry
             }
-            slot = (slot + 1) & mask;
+            slot = (slot + 1 == hsize) ? 0 : slot + 1;
             continue;
         }
-        return (int)slot;
+        return slot;
     }
     return -1;
-}
-
-__device__ __forceinline__ int table_shift(int hsize) {
-    int shift = 32;
-    for (int s = hsize; s > 1; s >>= 1) --shift;
-    return shift;
 }
 
 // One warp per work unit (a start item, or a slice of the legs of a heavy start).
@@ -61,11 +54,10 @@ __global__ void __launch_bounds__(XS_THREADS) xsim_accum_kernel(xmap_xsim_args a
     const int lane = threadIdx.x & 31;
     if (x >= a.n_units) return;
     const int hsize = a.hash_size[x];
-    if (hsize < 32 || (hsize & (hsize - 1)) != 0) {   // contract: power of two >= 32
+    if (hsize < 32) {                                  // contract: at least 32 cells
         if (lane == 0) atomicExch(a.error_flag, 3);
         return;
     }
-    const int shift = table_shift(hsize);
     XCell *tab = reinterpret_cast<XCell *>(a.hash_cells) + a.hash_off[x];
     const unsigned epoch = a.epoch;
     const unsigned long long ekey = (unsigned long long)epoch << 32;
@@ -85,16 +77,29 @@ __global__ void __launch_bounds__(XS_THREADS) xsim_accum_kernel(xmap_xsim_args a
             const double Dm = __dadd_rn(Dl, a.par_m[pp]);
             const double Cm = __dmul_rn(Cl, a.par_f[pp]);
             const int64_t rb = a.rs_ptr[s], re = a.rs_ptr[s + 1];
+            // right-segment data of the next 32 paths is requested before the table update of the current ones
+            int y_n = -1;
+            double n_n = 0.0, d_n = 0.0, c_n = 0.0;
+            if (rb + lane < re) {
+                const int64_t r = rb + lane;
+                y_n = a.rs_end[r];
+                n_n = a.rs_n[r]; d_n = a.rs_d[r]; c_n = a.rs_c[r];
+            }
             for (int64_t r0 = rb; r0 < re; r0 += 32) {
-                const int64_t r = r0 + lane;
-                const bool valid = r < re;
-                int y = -1;
+                const bool valid = r0 + lane < re;
+                const int y = y_n;
+                const double rn = n_n, rd = d_n, rc = c_n;
+                y_n = -1;
+                if (r0 + 32 + lane < re) {
+                    const int64_t r = r0 + 32 + lane;
+                    y_n = a.rs_end[r];
+                    n_n = a.rs_n[r]; d_n = a.rs_d[r]; c_n = a.rs_c[r];
+                }
                 double num = 0.0, den = 0.0;
                 if (valid) {
-                    y = a.rs_end[r];
-                    const double Nn = __dadd_rn(__dadd_rn(Nm, a.rs_e1[r]), a.rs_e2[r]);
-                    const double Dd = __dadd_rn(__dadd_rn(Dm, a.rs_m1[r]), a.rs_m2[r]);
-                    const double cp = __dmul_rn(__dmul_rn(Cm, a.rs_f1[r]), a.rs_f2[r]);
+                    const double Nn = __dadd_rn(Nm, rn);
+                    const double Dd = __dadd_rn(Dm, rd);
+                    const double cp = __dmul_rn(Cm, rc);
                     const double sp = (Dd != 0.0) ? __ddiv_rn(Nn, Dd) : 0.0;
                     num = __dmul_rn(sp, cp);
                     den = cp;
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(XS_THREADS) xsim_accum_kernel(xmap_xsim_args a
                     if (rem) { an = __dadd_rn(an, n2); ad = __dadd_rn(ad, d2); rem &= rem - 1u; }
                 }
                 if (leader) {
-                    const int slot = table_slot(tab, hsize, shift, ekey | (unsigned)(y + 1), epoch);
+                    const int slot = table_slot(tab, hsize, ekey | (unsigned)(y + 1), epoch);
                     if (slot < 0) atomicExch(a.error_flag, 2);
                     else { tab[slot].num = __dadd_rn(tab[slot].num, an); tab[slot].den = __dadd_rn(tab[slot].den, ad); }
                 }
@@ -132,14 +137,13 @@ __global__ void __launch_bounds__(XS_THREADS) xsim_merge_kernel(xmap_xsim_args a
                                                                 const int32_t *__restrict__ pair_src) {
     const int d = pair_dst[blockIdx.x], sx = pair_src[blockIdx.x];
     const int dsize = a.hash_size[d], ssize = a.hash_size[sx];
-    const int dshift = table_shift(dsize);
     XCell *dt = reinterpret_cast<XCell *>(a.hash_cells) + a.hash_off[d];
     const XCell *st = reinterpret_cast<const XCell *>(a.hash_cells) + a.hash_off[sx];
     const unsigned epoch = a.epoch;
     for (int q = threadIdx.x; q < ssize; q += XS_THREADS) {
         const unsigned long long key = st[q].key;
         if ((unsigned)(key >> 32) != epoch) continue;
-        const int slot = table_slot(dt, dsize, dshift, key, epoch);
+        const int slot = table_slot(dt, dsize, key, epoch);
         if (slot < 0) { atomicExch(a.error_flag, 2); continue; }
         dt[slot].num = __dadd_rn(dt[slot].num, st[q].num);
         dt[slot].den = __dadd_rn(dt[slot].den, st[q].den);
@@ -172,7 +176,8 @@ __global__ void __launch_bounds__(XS_THREADS) xsim_finalize_kernel(xmap_xsim_arg
         int64_t base = a.emit_ptr[x];
         int written = 0;
         for (int s0 = 0; s0 < hsize; s0 += 32) {
-            const XCell c = tab[s0 + lane];
+            XCell c{0ull, 0.0, 0.0};
+            if (s0 + lane < hsize) c = tab[s0 + lane];
             const bool occ = (unsigned)(c.key >> 32) == epoch;
             const unsigned m = __ballot_sync(0xffffffffu, occ);
             if (occ) {
@@ -224,7 +229,8 @@ __global__ void __launch_bounds__(XS_THREADS) xsim_finalize_kernel(xmap_xsim_arg
     int nb = 0;
     bool overflow = false;
     for (int s0 = 0; s0 < hsize && M > 0; s0 += 32) {
-        const XCell c = tab[s0 + lane];
+        XCell c{0ull, 0.0, 0.0};
+        if (s0 + lane < hsize) c = tab[s0 + lane];
         bool take = false;
         unsigned long long kk = 0ull;
         if ((unsigned)(c.key >> 32) == epoch) {

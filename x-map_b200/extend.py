@@ -298,10 +298,14 @@ class XsimEngine:
         end_cap = int(torch.unique(p.rs_end).numel()) if p.rs_end.numel() else 1
         # distinct ends <= min(paths, reachable ends): a table of >= 1.25x that bound never fills up
         # (worst-case load 0.8; typical load ~0.25 because several paths share an end)
-        self.hsize = torch.clamp(_pow2_at_least((5 * torch.clamp(sub_ub, max=end_cap) + 3) // 4), min=32)
+        self.hsize = torch.clamp((5 * torch.clamp(sub_ub, max=end_cap) + 3) // 4, min=32)
         self.start_bytes = torch.zeros(n, dtype=i64, device=dev)
         if n_units:
             self.start_bytes.index_add_(0, self.unit_start, self.hsize * 24)
+        # the two edges of a right segment folded into one (N, D, C) triple: 28 instead of 60 bytes per
+        # path (the sums are reassociated by at most one rounding; D is an exact integer either way)
+        e1, m1, f1, e2, m2, f2 = p.rs_vals
+        self.rs_ndc = ((e1 + e2).contiguous(), (m1 + m2).contiguous(), (f1 * f2).contiguous())
         self.order = torch.argsort(p.ub, descending=True, stable=True)
         self.n_units = n_units
         self._cells = None
@@ -316,8 +320,10 @@ class XsimEngine:
             self._cells = torch.zeros(need, dtype=torch.int64, device=self.device)
         return self._cells
 
-    def _batches(self):
-        order = self.order
+    def _batches(self, rank=0, world=1):
+        """Starts of this rank (every world-th start of the descending-work order, so the ranks'
+        loads match), cut into launches bounded by the hash budget."""
+        order = self.order[rank::world] if world > 1 else self.order
         if order.numel() == 0:
             return
         cum = torch.cumsum(self.start_bytes[order], 0).cpu()
@@ -376,7 +382,7 @@ class XsimEngine:
         a.par_ptr = P(p.par_ptr); a.par_s = P(p.par_s); a.par_joint = P(p.par_joint)
         a.par_e, a.par_m, a.par_f = [P(v) for v in p.par_vals]
         a.rs_ptr = P(p.rs_ptr); a.rs_end = P(p.rs_end)
-        (a.rs_e1, a.rs_m1, a.rs_f1, a.rs_e2, a.rs_m2, a.rs_f2) = [P(v) for v in p.rs_vals]
+        a.rs_n, a.rs_d, a.rs_c = [P(v) for v in self.rs_ndc]
         a.hash_off = P(hoff); a.hash_size = P(hs.to(torch.int32))
         a.hash_cells = N.ptr(cells)
         self.epoch += 1
@@ -406,15 +412,16 @@ class XsimEngine:
             raise N.NativeError("X-SIM kernel error %d (2: hash overflow, 3: bad table size)"
                                 % int(self.error_flag.item()))
 
-    def run(self):
-        """count + top-m for every start of the plan."""
+    def run(self, rank=0, world=1):
+        """count + top-m for every start of the plan (world > 1: only this rank's starts are filled in;
+        multi.allreduce_xsim assembles the full result on every rank)."""
         p, dev, n = self.plan, self.device, self.plan.start_item.numel()
         out = dict(count=torch.zeros(n, dtype=torch.int32, device=dev),
                    combos=torch.zeros(n, dtype=torch.int64, device=dev),
                    top_end=torch.full((n, self.top_m), -1, dtype=torch.int32, device=dev),
                    top_xsim=torch.zeros((n, self.top_m), dtype=torch.float64, device=dev),
                    top_len=torch.zeros(n, dtype=torch.int32, device=dev))
-        for sel in self._batches():
+        for sel in self._batches(rank, world):
             self._launch(sel, 0, out)
         return XsimResult(p.start_item, out["count"], out["combos"], out["top_end"], out["top_xsim"],
                           out["top_len"], self.launches)

@@ -15,6 +15,14 @@ the gathers the reference performs as collect + broadcast:
   3. all-gather of the neighbour tables after selection (the collectAsMap +
      broadcast of assist.py:121-132) -- n_items * 2k * 20 bytes.
 
+X-SIM extension shards by start item (starts are independent; every rank builds
+the same plan from the gathered tables and evaluates every world-th start of the
+descending-work order); the per-start top-m rows are summed across ranks (each
+row is non-zero on exactly one rank).  Generation shards by user: the item map is
+tiny and replicated, every rank rewrites the ratings of a contiguous block of
+users holding an equal share of the ratings, and the AlterEgo records stay
+sharded (the reference's result is an RDD) unless the caller gathers them.
+
 Because the accumulators are order-free integers and selection uses a total
 order, the result is bit-identical for any world size.  The exchange helpers are
 device-agnostic so they can be exercised with the gloo backend on CPU tensors.
@@ -145,3 +153,64 @@ def similarity_step(engine, shard, group=None):
                   engine.tab_mutu, engine.tab_n):
             allgather_rows(t, shard, group)
     return engine.tables(dict(accumulate=stats, rows=(shard.lo, shard.hi)))
+
+
+def allreduce_xsim(res, group=None):
+    """XsimResult filled for this rank's starts only -> the full result on every rank."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return res
+    res.top_end.add_(1)                                   # -1 fill -> 0 so that a sum assembles the rows
+    for t in (res.count, res.combos, res.top_end, res.top_xsim, res.top_len):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    res.top_end.sub_(1)
+    return res
+
+
+class UserShard(object):
+    """Contiguous block of users holding ~1/world of the ratings (csr_ptr: int32 [n_users + 1])."""
+
+    def __init__(self, csr_ptr, rank=0, world=1):
+        n = int(csr_ptr.numel()) - 1
+        nnz = int(csr_ptr[-1]) if n >= 0 and csr_ptr.numel() else 0
+        if world == 1 or n <= 0:
+            bounds = [0] + [max(n, 0)] * world
+        else:
+            targets = torch.tensor([nnz * r // world for r in range(1, world)], dtype=csr_ptr.dtype,
+                                   device=csr_ptr.device)
+            cuts = torch.searchsorted(csr_ptr[:-1].contiguous(), targets).tolist()
+            bounds = [0] + [int(c) for c in cuts] + [n]
+            for i in range(1, len(bounds)):
+                bounds[i] = max(bounds[i], bounds[i - 1])
+        self.rank, self.world, self.bounds = rank, world, bounds
+        self.lo, self.hi = bounds[rank], bounds[rank + 1]
+
+
+def build_alterego_sharded(layout, ts, mapping, shard, gather=False, group=None):
+    """AlterEgo records of the users this rank owns (generator.py:113-157); gather=True
+    concatenates every rank's records, in user order, on every rank."""
+    from . import generate as G
+    import copy
+    lo, hi = shard.lo, shard.hi
+    e_lo, e_hi = int(layout.csr_ptr[lo]), int(layout.csr_ptr[hi])
+    sub = copy.copy(layout)
+    sub.n_users, sub.nnz = hi - lo, e_hi - e_lo
+    sub.csr_ptr = (layout.csr_ptr[lo:hi + 1] - e_lo).contiguous()
+    sub.csr_ent = layout.csr_ent[e_lo:e_hi]
+    sub.csr_src = layout.csr_src[e_lo:e_hi]
+    ou, oi, orr, ot = G.build_alterego(sub, ts, mapping)
+    ou = ou + lo
+    if not gather or shard.world == 1:
+        return ou, oi, orr, ot
+    n = torch.tensor([ou.numel()], dtype=torch.int64, device=ou.device)
+    sizes = [torch.zeros_like(n) for _ in range(shard.world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(x) for x in sizes]
+    cap = max(max(sizes), 1)
+    out = []
+    for t in (ou, oi, orr, ot):
+        send = torch.zeros(cap, dtype=t.dtype, device=t.device)
+        send[: t.numel()] = t
+        recv = [torch.empty_like(send) for _ in range(shard.world)]
+        dist.all_gather(recv, send, group=group)
+        out.append(torch.cat([r[:m] for r, m in zip(recv, sizes)]))
+    return tuple(out)
