@@ -143,32 +143,45 @@ __global__ void tri_keys_kernel(const int32_t *__restrict__ csr_ptr, const uint6
     vals[k] = (e & 0xFFFFFFFF00000000ull) | (uint64_t)((w0 & ~ITEM_MASK) | o);
 }
 
-// One warp per item: position of (i, u) in u's ord-sorted row, suffix length, row work.
+// One thread per CSC entry (i, u): position of the entry in u's ord-sorted row, suffix length, and
+// the row work of i (entries of one item are contiguous, so a warp usually folds its 32 lengths
+// into one atomic).
 __global__ void tri_aux_kernel(const int32_t *__restrict__ csr_ptr, const int32_t *__restrict__ csc_ptr,
                                const uint64_t *__restrict__ csc_ent, const uint64_t *__restrict__ tcsr_ent,
                                const double *__restrict__ user_mu, const int32_t *__restrict__ ord, int32_t n_items,
-                               int32_t method, uint4 *__restrict__ csc_aux, int64_t *__restrict__ tri_work) {
-    int32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (i >= n_items) return;
+                               int64_t nnz, int32_t method, uint4 *__restrict__ csc_aux,
+                               unsigned long long *__restrict__ tri_work) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const uint32_t oi = (uint32_t)ord[i];
-    long long w = 0;
-    for (int32_t e = csc_ptr[i] + lane; e < csc_ptr[i + 1]; e += 32) {
-        const uint32_t u = (uint32_t)(csc_ent[e] & 0x7FFFFFFFu);
-        int32_t lo = csr_ptr[u], hi = csr_ptr[u + 1];
-        const int32_t end = hi;
-        while (hi - lo > 1) {                           // largest pos with ord(pos) <= oi
+    int32_t item = -1;
+    long long len = 0;
+    if (e < nnz) {
+        int32_t lo = 0, hi = n_items;                   // largest i with csc_ptr[i] <= e
+        while (hi - lo > 1) {
             const int32_t mid = (lo + hi) >> 1;
-            if (((uint32_t)__ldg(tcsr_ent + mid) & ITEM_MASK) <= oi) lo = mid; else hi = mid;
+            if (__ldg(csc_ptr + mid) <= e) lo = mid; else hi = mid;
         }
-        const int32_t len = end - lo - 1;
+        item = lo;
+        const uint32_t oi = (uint32_t)__ldg(ord + item);
+        const uint32_t u = (uint32_t)(csc_ent[e] & 0x7FFFFFFFu);
+        int32_t plo = csr_ptr[u], phi = csr_ptr[u + 1];
+        const int32_t end = phi;
+        while (phi - plo > 1) {                         // largest pos with ord(pos) <= oi
+            const int32_t mid = (plo + phi) >> 1;
+            if (((uint32_t)__ldg(tcsr_ent + mid) & ITEM_MASK) <= oi) plo = mid; else phi = mid;
+        }
+        len = end - plo - 1;
         const double mu = (method == XMAP_METHOD_ADJUST_COSINE) ? user_mu[u] : 0.0;
-        csc_aux[e] = make_uint4((uint32_t)lo, (uint32_t)len, (uint32_t)__double2loint(mu), (uint32_t)__double2hiint(mu));
-        w += len;
+        csc_aux[e] = make_uint4((uint32_t)plo, (uint32_t)len, (uint32_t)__double2loint(mu), (uint32_t)__double2hiint(mu));
     }
+    const int32_t item0 = __shfl_sync(0xffffffffu, item, 0);
+    if (__all_sync(0xffffffffu, item == item0)) {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) w += __shfl_xor_sync(0xffffffffu, w, off);
-    if (lane == 0) tri_work[i] = w;
+        for (int off = 16; off > 0; off >>= 1) len += __shfl_xor_sync(0xffffffffu, len, off);
+        if (lane == 0 && item0 >= 0 && len) atomicAdd(tri_work + item0, (unsigned long long)len);
+    } else if (item >= 0 && len) {
+        atomicAdd(tri_work + item, (unsigned long long)len);
+    }
 }
 
 __global__ void tri_ostat_kernel(const double *__restrict__ item_stats, const int32_t *__restrict__ prefix_code,
@@ -326,8 +339,9 @@ extern "C" int xmap_build_tri_layout(const int32_t *csr_ptr, const uint64_t *csr
     XMAP_LAUNCH_CHECK();
     XMAP_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, keys_a, keys_b, vals_a, tcsr_ent, nnz, 0,
                                               32 + bits_for(n_users), st));
-    tri_aux_kernel<<<(unsigned)(((int64_t)n_items * 32 + T - 1) / T), T, 0, st>>>(
-        csr_ptr, csc_ptr, csc_ent, tcsr_ent, user_mu, ord, n_items, method, reinterpret_cast<uint4 *>(csc_aux), tri_work);
+    tri_aux_kernel<<<gN, T, 0, st>>>(csr_ptr, csc_ptr, csc_ent, tcsr_ent, user_mu, ord, n_items, nnz, method,
+                                     reinterpret_cast<uint4 *>(csc_aux),
+                                     reinterpret_cast<unsigned long long *>(tri_work));
     XMAP_LAUNCH_CHECK();
     return 0;
 }

@@ -121,7 +121,7 @@ class SimTables:
         return 2 * int(self.row_npairs.sum().item())
 
 
-CELL_CLASSES = (256, 512, 1024, 2048, 4096, 8192, 12288)   # table capacities (16-byte cells) of the launches
+CELL_CLASSES = tuple(int(c) for c in os.environ.get("XMAP_CELL_CLASSES", "256,512,1024,1536,2048,3072,4096,6144,8192,12288").split(","))   # table capacities (16-byte cells) of the launches
 
 
 def _threads_for_cells(c):
@@ -131,6 +131,7 @@ def _threads_for_cells(c):
     return max(32, min(512, (c // cpt + 31) // 32 * 32))
 
 REC_BYTES = 16
+_PINNED = {}                                                # pinned host buffers of tables_to_host
 REC_CNT_LIMIT = 1 << 20                                     # n and mutu are 20-bit fields of a record
 
 
@@ -201,6 +202,7 @@ class SimEngine:
         self.tab_n = torch.zeros((I, 2, k), dtype=torch.int32, device=dev)
         self.tab_len = torch.zeros((I, 2), dtype=torch.int32, device=dev)
         self._gtab = None
+        self._side = None
         self._plans = {}
         self.profile = None        # dict kind -> [(start_event, end_event)] when enabled
 
@@ -304,13 +306,23 @@ class SimEngine:
         self.row_npairs.zero_()
 
     def accumulate(self, rows=None):
-        """Triangular similarity rows -> neighbour records of both ends, BB flags (xmap_sim_accumulate)."""
+        """Triangular similarity rows -> neighbour records of both ends, BB flags (xmap_sim_accumulate).
+        The launches (one per table capacity / group width) are dealt round-robin to a few streams so
+        that the tail of one overlaps the next and the long-running popular rows do not hold the GPU;
+        with per-kernel timing enabled everything is serialised on the current stream."""
         L = N.lib()
-        st = _stream_ptr()
         args = self._args()
         launches, _ = self.plan(rows)
+        main = torch.cuda.current_stream()
+        n_streams = int(os.environ.get("XMAP_SIM_STREAMS", "3"))
+        use_side = self.profile is None and len(launches) > 1 and n_streams > 1
+        if use_side and self._side is None:
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(n_streams - 1)]
+        if use_side:
+            for sd in self._side:
+                sd.wait_stream(main)
         stats = []
-        for r, cells_cap, threads, in_gmem in launches:
+        for q, (r, cells_cap, threads, in_gmem) in enumerate(launches):
             gtab, ctas = None, 0
             if in_gmem:
                 ctas = min(int(r.numel()), 296)
@@ -320,10 +332,17 @@ class SimEngine:
                     self._gtab = torch.empty(need, dtype=torch.uint8, device=self.device)
                 gtab = self._gtab
             kind = "accumulate_%s%d_t%d" % ("g" if in_gmem else "c", cells_cap, threads)
+            stream = main
+            if use_side and not in_gmem and q % n_streams:
+                stream = self._side[q % n_streams - 1]
+            st = stream.cuda_stream
             self._timed(kind, lambda: N.check(L.xmap_sim_accumulate(
                 args, N.ptr(r), r.numel(), cells_cap, threads, N.ptr(gtab), ctas, st), "xmap_sim_accumulate"))
             self.launches += 1
             stats.append((kind, int(r.numel())))
+        if use_side:
+            for sd in self._side:
+                main.wait_stream(sd)
         return stats
 
     def select(self, rows=None):
@@ -353,6 +372,22 @@ class SimEngine:
         return SimTables(self.k, self.lay.n_items, self.bb, self.row_npairs, self.rec_cnt,
                          self.tab_idx, self.tab_sim, self.tab_mutu, self.tab_n, self.tab_len,
                          self.launches, stats or {})
+
+    def tables_to_host(self, tabs=None):
+        """Neighbour tables + BB flags in pinned host memory (allocated once per shape, reused):
+        the device -> host read of the stage's result (the reference's collectAsMap, assist.py:121-129)."""
+        tabs = tabs or self.tables()
+        src = dict(row_flags=tabs.row_flags, tab_len=tabs.tab_len, tab_idx=tabs.tab_idx, tab_sim=tabs.tab_sim,
+                   tab_mutu=tabs.tab_mutu, tab_n=tabs.tab_n)
+        key = tuple((k, tuple(v.shape), v.dtype) for k, v in src.items())
+        if key not in _PINNED:                      # page-locking is slow: keep the buffers for the next engine
+            _PINNED.clear()
+            _PINNED[key] = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in src.items()}
+        host = _PINNED[key]
+        for k, v in src.items():
+            host[k].copy_(v, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host
 
     def emit_pairs(self, rows=None):
         """Every kept directed pair (the return value of baseliner_calculate_sim_pipeline,
