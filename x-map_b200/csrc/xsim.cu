@@ -25,6 +25,8 @@ struct XCell {
     double num, den;
 };
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // find-or-insert: returns the cell index or -1 (table full).  Only one warp (accumulate) or one
 // CTA (merge) ever writes a given table; the CAS resolves lanes racing for one empty cell, and the
 // thread whose CAS inserts the key initialises the values.
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(XS_THREADS) xsim_accum_kernel(xmap_xsim_args a
                 const int64_t r = rb + lane;
                 y_n = a.rs_end[r];
                 n_n = a.rs_n[r]; d_n = a.rs_d[r]; c_n = a.rs_c[r];
+                prefetch_l2(&tab[__umulhi((unsigned)y_n * 2654435761u, (unsigned)hsize)]);
             }
             for (int64_t r0 = rb; r0 < re; r0 += 32) {
                 const bool valid = r0 + lane < re;
@@ -94,6 +97,8 @@ __global__ void __launch_bounds__(XS_THREADS) xsim_accum_kernel(xmap_xsim_args a
                     const int64_t r = r0 + 32 + lane;
                     y_n = a.rs_end[r];
                     n_n = a.rs_n[r]; d_n = a.rs_d[r]; c_n = a.rs_c[r];
+                    // pull the home cell of the next step's end towards L2 while this step updates the table
+                    prefetch_l2(&tab[__umulhi((unsigned)y_n * 2654435761u, (unsigned)hsize)]);
                 }
                 double num = 0.0, den = 0.0;
                 if (valid) {

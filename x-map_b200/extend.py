@@ -305,7 +305,13 @@ class XsimEngine:
         # the two edges of a right segment folded into one (N, D, C) triple: 28 instead of 60 bytes per
         # path (the sums are reassociated by at most one rounding; D is an exact integer either way)
         e1, m1, f1, e2, m2, f2 = p.rs_vals
-        self.rs_ndc = ((e1 + e2).contiguous(), (m1 + m2).contiguous(), (f1 * f2).contiguous())
+        # ... and every list ordered by end (stable), so that right segments of one source that end at the
+        # same item sit in the same 32-path step and are combined before they reach the table
+        rl = p.rs_ptr[1:] - p.rs_ptr[:-1]
+        seg = _segment_ids(rl)
+        perm = torch.argsort(seg * int(p.n_items) + p.rs_end.long(), stable=True) if seg.numel() else seg
+        self.rs_end = p.rs_end[perm].contiguous()
+        self.rs_ndc = ((e1 + e2)[perm].contiguous(), (m1 + m2)[perm].contiguous(), (f1 * f2)[perm].contiguous())
         self.order = torch.argsort(p.ub, descending=True, stable=True)
         self.n_units = n_units
         self._cells = None
@@ -381,7 +387,7 @@ class XsimEngine:
         (a.leg_e1, a.leg_m1, a.leg_f1, a.leg_e2, a.leg_m2, a.leg_f2) = [P(v) for v in p.leg_vals]
         a.par_ptr = P(p.par_ptr); a.par_s = P(p.par_s); a.par_joint = P(p.par_joint)
         a.par_e, a.par_m, a.par_f = [P(v) for v in p.par_vals]
-        a.rs_ptr = P(p.rs_ptr); a.rs_end = P(p.rs_end)
+        a.rs_ptr = P(p.rs_ptr); a.rs_end = P(self.rs_end)
         a.rs_n, a.rs_d, a.rs_c = [P(v) for v in self.rs_ndc]
         a.hash_off = P(hoff); a.hash_size = P(hs.to(torch.int32))
         a.hash_cells = N.ptr(cells)
