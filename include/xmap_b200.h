@@ -66,8 +66,8 @@ int xmap_build_layout(const int32_t *user, const int32_t *item, const float *rat
 
 /* Per output row i of R^T R: w[i] = sum over raters u of i of degree(u), the
  * number of co-rating products the full row would cost (W + nnz in
- * total).  Bounds the length of a row's neighbour-record list and balances the
- * multi-GPU row blocks. */
+ * total).  Bounds the length of a row's neighbour-record list.  Synchronises the
+ * stream once (it reads nnz = csc_ptr[n_items]). */
 int xmap_row_work(const int32_t *csr_ptr, const int32_t *csc_ptr, const uint64_t *csc_ent,
                   int32_t n_items, int64_t *row_work, void *stream);
 

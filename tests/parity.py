@@ -39,29 +39,47 @@ def to_device_meta(meta, device="cuda"):
         has_T=torch.as_tensor(meta["has_T"], dtype=torch.bool, device=device))
 
 
-def synth_case(n_users, n_items, n_draws, overlap, seed, half=False):
-    """Synthetic arrays + per-item codes (ids built like the reference's)."""
+def _case_from_ratings(sr, keep=None, half=False):
+    """Compact the (optionally masked) synthetic ratings to the users / items that occur, numbered in
+    sorted id order, with the per-item codes (ids built like the reference's)."""
     from xmap_b200 import synth
     from xmap_b200.encode import item_codes
-    sr = synth.make_ratings(n_users, n_items, n_draws, overlap=overlap, seed=seed)
-    # compact to the users / items that occur, numbered in sorted id order
-    iid_all = np.array([synth.item_id(int(g), sr.n_items_per_domain, sr.labels)
-                        for g in np.unique(sr.item)])
+    user, item, rating_i, ts = sr.user, sr.item, sr.rating, sr.ts
+    if keep is not None:
+        user, item, rating_i, ts = user[keep], item[keep], rating_i[keep], ts[keep]
+    present = np.unique(item)
+    iid_all = np.array([synth.item_id(int(g), sr.n_items_per_domain, sr.labels) for g in present])
     order = np.argsort(iid_all)
-    present = np.unique(sr.item)[order]
-    iids = iid_all[order]
-    imap = np.full(int(sr.item.max()) + 1, -1, dtype=np.int64)
+    present, iids = present[order], iid_all[order]
+    imap = np.full(int(item.max()) + 1, -1, dtype=np.int64)
     imap[present] = np.arange(len(present))
-    uu = np.unique(sr.user)           # user ids are zero-padded -> numeric order == string order
-    umap = np.full(int(sr.user.max()) + 1, -1, dtype=np.int64)
+    uu = np.unique(user)              # user ids are zero-padded -> numeric order == string order
+    umap = np.full(int(user.max()) + 1, -1, dtype=np.int64)
     umap[uu] = np.arange(len(uu))
-    rating = sr.rating.astype(np.float64)
+    rating = rating_i.astype(np.float64)
     if half:
-        rating = rating - 0.5 * ((sr.user + sr.item) & 1)
+        rating = rating - 0.5 * ((user + item) & 1)
     pc, dc, ct, hs, ht = item_codes(iids)
-    return dict(user=umap[sr.user], item=imap[sr.item], rating=rating, ts=sr.ts,
+    return dict(user=umap[user], item=imap[item], rating=rating, ts=ts,
                 n_users=len(uu), n_items=len(iids), iids=iids,
                 meta=dict(prefix_code=pc, dom_code=dc, contains=ct, has_S=hs, has_T=ht))
+
+
+def synth_case(n_users, n_items, n_draws, overlap, seed, half=False):
+    """Synthetic two-domain arrays + per-item codes."""
+    from xmap_b200 import synth
+    return _case_from_ratings(synth.make_ratings(n_users, n_items, n_draws, overlap=overlap, seed=seed), half=half)
+
+
+def multi_domain_cases(n_users, n_items, n_draws, overlap, seed, n_domains=3):
+    """The multi-domain shape (labels "S:1:", "S:2:", ..., "T:"): the reference runs one independent
+    two-domain pipeline per source domain and unions the results (multidomain_demo.py:101-128), so
+    this yields one two-domain case per source domain, cut from ONE multi-domain rating set."""
+    from xmap_b200 import synth
+    sr = synth.make_ratings(n_users, n_items, n_draws, n_domains=n_domains, overlap=overlap, seed=seed)
+    tgt = n_domains - 1
+    return [(sr.labels[d], _case_from_ratings(sr, (sr.domain == d) | (sr.domain == tgt)))
+            for d in range(n_domains - 1)]
 
 
 def run_gpu_sim(user, item, rating, n_users, n_items, meta, method, num_atleast, k, emit=True,

@@ -84,6 +84,27 @@ def test_xsim_vs_restatement_and_batching():
     assert bad <= 0.002 * len(rows) + 1, "%d top-m rows differ (only near-ties in xsim may)" % bad
 
 
+def test_multi_domain_shape():
+    """BASELINE.json configs[3] in miniature: three domains ("S:1:", "S:2:", "T:"), one source -> target
+    pipeline per source domain as multidomain_demo.py:101-128 runs them; similarity, neighbour lists,
+    X-SIM and the argmax mapping of each against the restatement."""
+    from oracle import restate as RS
+    from xmap_b200 import generate as G
+    cases = PT.multi_domain_cases(4500, 500, 60000, 0.08, seed=31)
+    assert [lab for lab, _ in cases] == ["S:1:", "S:2:"]
+    for lab, case in cases:
+        assert any(lab in str(i) for i in case["iids"]) and any(str(i).endswith("T:") for i in case["iids"])
+        out = PT.check_sim_against_restatement(case, "adjust_cosine", 50, 6)
+        Xr = RS.xsim_extend(out["P"], out["knn"], case["n_items"], case["meta"]["has_S"], case["meta"]["has_T"])
+        plan, xe, res, (s, e, v) = PT.run_gpu_extend(out["tabs"], out["lay"], case["meta"])
+        assert len(s) > 0 and plan.n_src == Xr["n_src"]
+        PT.compare_xsim(s, e, v, Xr["start"], Xr["end"], Xr["xsim"])
+        rows, cands = RS.candidates(Xr["start"], Xr["end"], Xr["xsim"], 10)
+        ch = G.choose_mapping(res, "argmax").cpu().numpy()
+        bad = sum(0 if ch[r] == cands[r][0][0] else 1 for r in range(len(rows)))
+        assert bad <= 0.002 * len(rows) + 1, "%d argmax mappings differ (only near-ties in xsim may)" % bad
+
+
 def test_exponential_mechanism_injected_uniforms_and_philox():
     """Injected uniforms reproduce oracle/restate.choose exactly; the Philox stream matches its
     numpy port; sampled frequencies pass a chi-square test against exp(eps*xsim/(2*k*GS))."""

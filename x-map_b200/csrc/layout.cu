@@ -41,17 +41,20 @@ __global__ void user_mean_kernel(const int32_t *__restrict__ csr_ptr, const int3
     mu[u] = (b > a) ? s / (double)(b - a) : 0.0;
 }
 
-// One warp per item: sum r, sum r^2, sum (r - mu_u)^2, count (baselinerSim.py:56-81).
-__global__ void item_stats_kernel(const int32_t *__restrict__ csc_ptr, const uint64_t *__restrict__ keys_i,
-                                  const int32_t *__restrict__ perm, const float *__restrict__ rating,
-                                  const double *__restrict__ mu, int32_t n_items,
-                                  double *__restrict__ stats) {
-    int32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (i >= n_items) return;
-    int lane = threadIdx.x & 31;
-    int32_t a = csc_ptr[i], b = csc_ptr[i + 1];
+// One CTA per item: sum r, sum r^2, sum (r - mu_u)^2, count (baselinerSim.py:56-81).  Thread t takes
+// raters t, t + 256, ...; the partial sums are folded lane-wise (xor tree) and then warp by warp in
+// index order, so the result is a fixed function of the column (no atomics).
+constexpr int IS_THREADS = 256;
+__global__ void __launch_bounds__(IS_THREADS) item_stats_kernel(
+    const int32_t *__restrict__ csc_ptr, const uint64_t *__restrict__ keys_i, const int32_t *__restrict__ perm,
+    const float *__restrict__ rating, const double *__restrict__ mu, int32_t n_items, double *__restrict__ stats) {
+    __shared__ double sh[3][IS_THREADS / 32];
+    const int32_t i = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int32_t a = csc_ptr[i], b = csc_ptr[i + 1];
+    if (warp > 0 && b - a <= 32 * warp) return;          // short columns: the surplus warps leave (no barrier needed)
     double s = 0.0, s2 = 0.0, a2 = 0.0;
-    for (int32_t k = a + lane; k < b; k += 32) {
+    for (int32_t k = a + threadIdx.x; k < b; k += IS_THREADS) {
         double r = (double)rating[perm[k]];
         double c = r - mu[(uint32_t)(keys_i[k] & 0xFFFFFFFFu)];
         s += r;
@@ -64,7 +67,17 @@ __global__ void item_stats_kernel(const int32_t *__restrict__ csc_ptr, const uin
         s2 += __shfl_xor_sync(0xffffffffu, s2, off);
         a2 += __shfl_xor_sync(0xffffffffu, a2, off);
     }
-    if (lane == 0) {
+    const int live = min(IS_THREADS / 32, (b - a + 31) / 32);        // warps that stayed (>= 1 unless empty)
+    if (live > 1) {
+        if (lane == 0) { sh[0][warp] = s; sh[1][warp] = s2; sh[2][warp] = a2; }
+        // every staying warp reaches this barrier: bar.sync counts warps, and exited warps no longer count
+        __syncthreads();
+        if (warp == 0) {
+            s = sh[0][0]; s2 = sh[1][0]; a2 = sh[2][0];
+            for (int w = 1; w < live; ++w) { s += sh[0][w]; s2 = __dadd_rn(s2, sh[1][w]); a2 = __dadd_rn(a2, sh[2][w]); }
+        }
+    }
+    if (threadIdx.x == 0) {
         double n = (double)(b - a);
         stats[4 * (int64_t)i + 0] = (b > a) ? s / n : 0.0;
         stats[4 * (int64_t)i + 1] = sqrt(s2);
@@ -102,20 +115,32 @@ __global__ void pack_csc_kernel(const uint64_t *__restrict__ keys_i, const int32
     csc_ent[k] = ((uint64_t)__float_as_uint(r) << 32) | (user | (ge << 31));
 }
 
+// One thread per CSC entry; a warp whose 32 entries belong to one item folds them into one atomic.
 __global__ void row_work_kernel(const int32_t *__restrict__ csr_ptr, const int32_t *__restrict__ csc_ptr,
-                                const uint64_t *__restrict__ csc_ent, int32_t n_items,
-                                int64_t *__restrict__ work) {
-    int32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (i >= n_items) return;
-    int lane = threadIdx.x & 31;
+                                const uint64_t *__restrict__ csc_ent, int32_t n_items, int64_t nnz,
+                                unsigned long long *__restrict__ work) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int32_t item = -1;
     long long w = 0;
-    for (int32_t k = csc_ptr[i] + lane; k < csc_ptr[i + 1]; k += 32) {
-        uint32_t u = (uint32_t)(csc_ent[k] & 0x7FFFFFFFu);
-        w += csr_ptr[u + 1] - csr_ptr[u];
+    if (e < nnz) {
+        int32_t lo = 0, hi = n_items;                   // largest i with csc_ptr[i] <= e
+        while (hi - lo > 1) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (__ldg(csc_ptr + mid) <= e) lo = mid; else hi = mid;
+        }
+        item = lo;
+        const uint32_t u = (uint32_t)(csc_ent[e] & 0x7FFFFFFFu);
+        w = csr_ptr[u + 1] - csr_ptr[u];
     }
+    const int32_t item0 = __shfl_sync(0xffffffffu, item, 0);
+    if (__all_sync(0xffffffffu, item == item0)) {
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) w += __shfl_xor_sync(0xffffffffu, w, off);
-    if (lane == 0) work[i] = w;
+        for (int off = 16; off > 0; off >>= 1) w += __shfl_xor_sync(0xffffffffu, w, off);
+        if (lane == 0 && item0 >= 0) atomicAdd(work + item0, (unsigned long long)w);
+    } else if (item >= 0) {
+        atomicAdd(work + item, (unsigned long long)w);
+    }
 }
 
 // ---- triangular layout (see include/xmap_b200.h) ---------------------------------------------
@@ -282,8 +307,8 @@ extern "C" int xmap_build_layout(const int32_t *user, const int32_t *item, const
                                               32 + bits_for(n_items), st));
     boundaries_kernel<<<gN1, T, 0, st>>>(keys_i, nnz, n_items, csc_ptr);
     XMAP_LAUNCH_CHECK();
-    item_stats_kernel<<<(unsigned)(((int64_t)n_items * 32 + T - 1) / T), T, 0, st>>>(
-        csc_ptr, keys_i, perm_i, rating, user_mu, n_items, item_stats);
+    item_stats_kernel<<<(unsigned)n_items, IS_THREADS, 0, st>>>(csc_ptr, keys_i, perm_i, rating, user_mu, n_items,
+                                                                item_stats);
     XMAP_LAUNCH_CHECK();
     pack_csr_kernel<<<gN, T, 0, st>>>(keys_u, perm_u, rating, item_stats, nnz, csr_ent, csr_src);
     XMAP_LAUNCH_CHECK();
@@ -297,8 +322,13 @@ extern "C" int xmap_row_work(const int32_t *csr_ptr, const int32_t *csc_ptr, con
     cudaStream_t st = (cudaStream_t)stream_;
     const int T = 256;
     if (n_items == 0) return 0;
-    row_work_kernel<<<(unsigned)(((int64_t)n_items * 32 + T - 1) / T), T, 0, st>>>(csr_ptr, csc_ptr, csc_ent,
-                                                                                  n_items, row_work);
+    XMAP_CUDA(cudaMemsetAsync(row_work, 0, sizeof(int64_t) * (size_t)n_items, st));
+    int32_t nnz32 = 0;
+    XMAP_CUDA(cudaMemcpyAsync(&nnz32, csc_ptr + n_items, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    XMAP_CUDA(cudaStreamSynchronize(st));
+    if (nnz32 <= 0) return 0;
+    row_work_kernel<<<(unsigned)(((int64_t)nnz32 + T - 1) / T), T, 0, st>>>(
+        csr_ptr, csc_ptr, csc_ent, n_items, (int64_t)nnz32, reinterpret_cast<unsigned long long *>(row_work));
     XMAP_LAUNCH_CHECK();
     return 0;
 }
