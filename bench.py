@@ -351,11 +351,13 @@ def main():
         alg_bytes = 8.0 * (wl["W"] / 2) + 24.0 * wl["nnz"] + 32.0 * P_kept + 80.0 * k * wl["n_items"]
         stage_gbs = alg_bytes / (ms_step * 1e-3) / 1e9
         # kernels: the accumulate launches are one kernel function per group width
-        launches_plan, _ = eng.plan(None if world == 1 else shard.rows(dev))
+        launches_plan, _, split_plan = eng.plan(None if world == 1 else shard.rows(dev))
         fam_ms, fam_n, fam_bytes = {}, {}, {}
         for kk, (n, ms_k) in prof.items():
-            if kk.startswith("accumulate"):
+            if kk.startswith("accumulate_c") or kk.startswith("accumulate_g"):
                 fam = "tri_warp_kernel" if kk.endswith("_t32") else ("tri_gmem_kernel" if "_g" in kk else "tri_cta_kernel")
+            elif kk == "accumulate_split":
+                fam = "tri_split_kernel"
             elif kk == "select_warp":
                 fam = "select_warp_kernel"
             elif kk == "select_cta":
@@ -367,6 +369,8 @@ def main():
         for r, cells_cap, threads, in_gmem in launches_plan:
             fam = "tri_gmem_kernel" if in_gmem else ("tri_warp_kernel" if threads == 32 else "tri_cta_kernel")
             fam_bytes[fam] = fam_bytes.get(fam, 0.0) + 8.0 * float(eng.tri_work[r.long()].sum().item())
+        if split_plan is not None:
+            fam_bytes["tri_split_kernel"] = 8.0 * float(eng.tri_work[split_plan["rows"].long()].sum().item())
         long_rows = tabs.row_nkept > 8192
         fam_bytes["select_cta_kernel"] = 16.0 * float(tabs.row_nkept[long_rows].sum().item())
         fam_bytes["select_warp_kernel"] = 16.0 * float(tabs.row_nkept[~long_rows].sum().item())

@@ -156,6 +156,17 @@ int xmap_sim_accumulate(const xmap_sim_args *args_h, const int32_t *rows, int32_
                         int32_t cells_cap, int32_t threads_per_row,
                         void *gtab, int32_t gtab_ctas, void *stream);
 
+/* Rows with very many raters (the most popular items: long rater lists, few products per rater)
+ * are bound by the walk over their raters, so their rater list is cut into segments, one CTA each.
+ * Segment g covers CSC positions [seg_lo[g], seg_hi[g]) of row seg_row[g], which is the seg_slot[g]-th
+ * split row; slot_nseg[slot] = number of segments of that row.  Only direct-indexed rows (at most
+ * cells_cap more popular items) may be split.  gtab: [n_slots][cells_cap] 16-byte cells and
+ * done: [n_slots] ints, both zero on entry and zero again on exit.  Results are bit-identical to
+ * the unsplit row (the partial tables are combined with exact integer adds). */
+int xmap_sim_accumulate_split(const xmap_sim_args *args_h, const int32_t *seg_row, const int32_t *seg_lo,
+                              const int32_t *seg_hi, const int32_t *seg_slot, const int32_t *slot_nseg,
+                              int32_t n_segs, int32_t cells_cap, void *gtab, int32_t *done, void *stream);
+
 /* Per-row top-k selection over the neighbour-record lists (extender.py:16-44), after
  * every rank's records are in place and bb holds the flags of ALL items:
  *   BB row : table slot 0 = BB_BB (top-k other-domain), slot 1 = BB_NB (top-k same-domain)

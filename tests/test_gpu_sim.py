@@ -71,6 +71,25 @@ def test_global_memory_tables_give_identical_results():
         assert np.array_equal(getattr(a["tabs"], t).cpu().numpy(), getattr(b["tabs"], t).cpu().numpy()), t
 
 
+def test_split_rows_give_identical_results(monkeypatch):
+    """Rows with long rater lists cut into segments over several CTAs (merged through a global table
+    with exact integer adds): forcing the split on a small case must not change a bit."""
+    from xmap_b200 import engine as E
+    case = PT.synth_case(6000, 1200, 120000, 0.1, seed=5)
+    a = PT.check_sim_against_restatement(case, "adjust_cosine", 50, 7)
+    assert not any(k == "accumulate_split" for k in _kinds(a))
+    monkeypatch.setattr(E, "SPLIT_RATERS", 64)
+    monkeypatch.setattr(E, "SPLIT_SEG", 96)
+    b = PT.check_sim_against_restatement(case, "adjust_cosine", 50, 7)
+    assert dict(b["tabs"].stats["accumulate"])["accumulate_split"] > 10
+    for k in ("i", "j", "sim", "mutu", "n"):
+        assert np.array_equal(a["pairs"][k].cpu().numpy(), b["pairs"][k].cpu().numpy()), k
+    for t in ("tab_idx", "tab_sim", "tab_len", "row_flags"):
+        assert np.array_equal(getattr(a["tabs"], t).cpu().numpy(), getattr(b["tabs"], t).cpu().numpy()), t
+    tabs2 = b["eng"].run()                                # the global tables and counters were left clean
+    assert np.array_equal(tabs2.tab_idx.cpu().numpy(), a["tabs"].tab_idx.cpu().numpy())
+
+
 def test_rerun_is_idempotent():
     """Running the stage twice on the same engine gives the same tables (cursors / flags reset)."""
     case = PT.synth_case(3000, 500, 40000, 0.2, seed=9)

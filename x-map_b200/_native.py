@@ -62,6 +62,7 @@ _SIGS = {
                                         _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "xmap_sim_row_cells": (C.c_int64, [C.c_int64, C.c_int32]),
     "xmap_sim_accumulate": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, C.c_int32, C.c_int32, _p, C.c_int32, _p]),
+    "xmap_sim_accumulate_split": (C.c_int, [C.POINTER(SimArgs), _p, _p, _p, _p, _p, C.c_int32, C.c_int32, _p, _p, _p]),
     "xmap_sim_select": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, C.c_int32, _p]),
     "xmap_xsim_extend": (C.c_int, [C.POINTER(XsimArgs), _p]),
     "xmap_choose_mapping": (C.c_int, [_p, _p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -98,9 +98,20 @@ __device__ __forceinline__ RaterDesc load_rater(const xmap_sim_args &a, int e, i
 // Accumulate + epilogue of one row by a group of threads (one warp, or a whole CTA).
 //   T    : cells_cap accumulator cells;  occ : cells_cap slot indices (IDX = uint16 in shared memory)
 //   s_cnt: one int of group-shared scratch (CTA mode)
+// A row with very many raters can be cut into segments of its rater list, one CTA each: every
+// segment accumulates into its own shared-memory table, adds it into the row's table in global
+// memory (exact integer adds, so the split never changes a bit), and the CTA that arrives last
+// reloads the sum, clears the global table for the next use and runs the epilogue.
+struct SplitCtx {
+    uint4 *gtab;        // the row's direct-indexed table in global memory, zero outside a stage
+    int *done;          // arrival counter of the row's segments, zero outside a stage
+    int nseg;
+    int seg_lo, seg_hi; // rater range (CSC positions) of this segment
+};
+
 template <bool CTA_ROW, class IDX>
 __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__restrict__ occ_list, int *s_cnt,
-                        int cells_cap, int row) {
+                        int cells_cap, int row, const SplitCtx *sp = nullptr) {
     const int lane = threadIdx.x & 31;
     const int gwarps = CTA_ROW ? (blockDim.x >> 5) : 1;
     const int gw = CTA_ROW ? (threadIdx.x >> 5) : 0;
@@ -112,7 +123,7 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__res
     const OStat si = ostat[oi];
     const int cls_i = int(si.prefix_cls & 0xFFu);
     const unsigned prefix_i = si.prefix_cls >> 8;
-    const int lo = a.csc_ptr[row], hi = a.csc_ptr[row + 1];
+    const int lo = sp ? sp->seg_lo : a.csc_ptr[row], hi = sp ? sp->seg_hi : a.csc_ptr[row + 1];
     const long long work = a.tri_work[row];
     const int rtop = a.n_items - 1 - oi;                   // items more popular than `row`
     const long long hcells = hash_cells_for(work);
@@ -213,6 +224,34 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__res
         }
     }
     group_sync<CTA_ROW>();
+
+    if (CTA_ROW && sp) {
+        if (!direct) {                                     // only direct-indexed rows can be merged cell by cell
+            if (gtid == 0) atomicExch(a.error_flag, 1);
+            return;
+        }
+        for (int s = gtid; s < ncell; s += gthreads) {
+            const uint4 v = T4[s];
+            if (v.x) atomicAdd(&sp->gtab[s].x, v.x);
+            if (v.y) atomicAdd(&sp->gtab[s].y, v.y);
+            const unsigned long long fx = ((unsigned long long)v.w << 32) | v.z;
+            if (fx) atomicAdd(reinterpret_cast<unsigned long long *>(&sp->gtab[s].z), fx);
+        }
+        __threadfence();
+        __syncthreads();
+        if (gtid == 0) *s_cnt = (atomicAdd(sp->done, 1) == sp->nseg - 1) ? 1 : 0;
+        __syncthreads();
+        const bool last = *s_cnt != 0;
+        __syncthreads();
+        if (!last) return;
+        __threadfence();
+        for (int s = gtid; s < ncell; s += gthreads) {
+            T4[s] = __ldcg(sp->gtab + s);
+            sp->gtab[s] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (gtid == 0) { *sp->done = 0; *s_cnt = 0; }
+        __syncthreads();
+    }
 
     // ---- index list of the occupied cells (order irrelevant) ---------------------------------------
     int n_ent = 0;
@@ -358,6 +397,21 @@ __global__ void __launch_bounds__(512) tri_cta_kernel(xmap_sim_args a, const int
     tri_row<true, unsigned short>(a, reinterpret_cast<Cell *>(smem_raw),
                                   reinterpret_cast<unsigned short *>(smem_raw + (size_t)cells_cap * sizeof(Cell)),
                                   &s_cnt, cells_cap, rows[blockIdx.x]);
+}
+
+// one CTA per segment of a split row (see SplitCtx)
+__global__ void __launch_bounds__(512) tri_split_kernel(xmap_sim_args a, const int32_t *__restrict__ seg_row,
+                                                         const int32_t *__restrict__ seg_lo, const int32_t *__restrict__ seg_hi,
+                                                         const int32_t *__restrict__ seg_slot,
+                                                         const int32_t *__restrict__ slot_nseg, int cells_cap,
+                                                         uint4 *__restrict__ gtab, int *__restrict__ done) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_cnt;
+    const int g = blockIdx.x, slot = seg_slot[g];
+    SplitCtx sp{gtab + (size_t)slot * cells_cap, done + slot, slot_nseg[slot], seg_lo[g], seg_hi[g]};
+    tri_row<true, unsigned short>(a, reinterpret_cast<Cell *>(smem_raw),
+                                  reinterpret_cast<unsigned short *>(smem_raw + (size_t)cells_cap * sizeof(Cell)),
+                                  &s_cnt, cells_cap, seg_row[g], &sp);
 }
 
 // persistent CTAs, tables in global memory (rows whose table exceeds shared memory):
@@ -839,6 +893,22 @@ extern "C" int xmap_sim_accumulate(const xmap_sim_args *args_h, const int32_t *r
         XMAP_CUDA(cudaFuncSetAttribute(tri_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tri_cta_kernel<<<n_rows, threads_per_row, smem, st>>>(*args_h, rows, n_rows, cells_cap);
     }
+    XMAP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xmap_sim_accumulate_split(const xmap_sim_args *args_h, const int32_t *seg_row, const int32_t *seg_lo,
+                                         const int32_t *seg_hi, const int32_t *seg_slot, const int32_t *slot_nseg,
+                                         int32_t n_segs, int32_t cells_cap, void *gtab, int32_t *done, void *stream_) {
+    if (int rc = check_args(*args_h)) return rc;
+    if (n_segs <= 0) return 0;
+    if (cells_cap < 1 || cells_cap > XMAP_SIM_MAX_SMEM_CELLS)
+        return fail_msg("xmap_sim_accumulate_split: cells_cap out of range");
+    cudaStream_t st = (cudaStream_t)stream_;
+    const size_t smem = row_smem_bytes(cells_cap);
+    XMAP_CUDA(cudaFuncSetAttribute(tri_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tri_split_kernel<<<n_segs, 512, smem, st>>>(*args_h, seg_row, seg_lo, seg_hi, seg_slot, slot_nseg, cells_cap,
+                                                reinterpret_cast<uint4 *>(gtab), done);
     XMAP_LAUNCH_CHECK();
     return 0;
 }

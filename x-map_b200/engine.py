@@ -131,6 +131,8 @@ def _threads_for_cells(c):
     return max(32, min(512, (c // cpt + 31) // 32 * 32))
 
 REC_BYTES = 16
+SPLIT_RATERS = int(os.environ.get("XMAP_SPLIT_RATERS", "16384"))   # rows with at least this many raters are split ...
+SPLIT_SEG = 4096                                            # ... into segments of this many raters
 _PINNED = {}                                                # pinned host buffers of tables_to_host
 REC_CNT_LIMIT = 1 << 20                                     # n and mutu are 20-bit fields of a record
 
@@ -226,9 +228,10 @@ class SimEngine:
     # -- planning ----------------------------------------------------------
     def plan(self, rows=None):
         """Group the rows by table capacity and threads per row (cached per row set).
-        Returns (launches, long_candidates): launches = [(rows sorted by descending work,
+        Returns (launches, long_candidates, split): launches = [(rows sorted by descending work,
         cells_cap, threads_per_row, in_global_memory)], long_candidates = rows whose record
-        list can exceed XMAP_SELECT_LONG."""
+        list can exceed XMAP_SELECT_LONG, split = segment arrays of the rows whose rater list is
+        cut over several CTAs (or None)."""
         key = None if rows is None else (int(rows[0]) if rows.numel() else -1, int(rows.numel()))
         if key in self._plans:
             return self._plans[key]
@@ -254,6 +257,27 @@ class SimEngine:
         t_work[work > 32768] = 512
         threads = torch.maximum(t_cells, t_work)
         live = work > 0
+        # rows with very long rater lists (popular items) are cut into segments, one CTA each
+        craters = (self.lay.csc_ptr[rl + 1] - self.lay.csc_ptr[rl]).long()
+        is_split = live & (rtop <= h) & (craters >= SPLIT_RATERS) & (cells <= self.max_smem_cells)
+        split = None
+        if bool(is_split.any()):
+            srows, sr_c = rows[is_split], craters[is_split]
+            o = torch.argsort(sr_c, descending=True, stable=True)
+            srows, sr_c = srows[o], sr_c[o]
+            nseg = (sr_c + SPLIT_SEG - 1) // SPLIT_SEG
+            slot = torch.repeat_interleave(torch.arange(srows.numel(), device=dev), nseg)
+            q = torch.arange(int(nseg.sum().item()), device=dev) - (torch.cumsum(nseg, 0) - nseg)[slot]
+            base = self.lay.csc_ptr[srows.long()].long()[slot]
+            seg_lo = base + q * SPLIT_SEG
+            seg_hi = torch.minimum(seg_lo + SPLIT_SEG, base + sr_c[slot])
+            cap = max(32, int(cells[is_split].max().item()))
+            i32 = lambda t: t.to(torch.int32).contiguous()
+            split = dict(seg_row=i32(srows[slot]), seg_lo=i32(seg_lo), seg_hi=i32(seg_hi), seg_slot=i32(slot),
+                         slot_nseg=i32(nseg), n_segs=int(slot.numel()), cells_cap=cap, rows=srows,
+                         gtab=torch.zeros((srows.numel() * cap, 2), dtype=torch.int64, device=dev),
+                         done=torch.zeros(srows.numel(), dtype=torch.int32, device=dev))
+            live = live & ~is_split
         code = (cls * 2048 + threads)[live]
         rows_l, work_l, cells_l = rows[live], work[live], cells[live]
         launches = []
@@ -268,7 +292,7 @@ class SimEngine:
                 launches.append((r, int(cells_l[m].max().item()), 512, True))
         launches.sort(key=lambda t: (-t[2], -t[1]))                # big CTAs first
         long_cand = rows[self.rec_cap[rl] > N.SELECT_LONG].contiguous()
-        out = (launches, long_cand)
+        out = (launches, long_cand, split)
         self._plans[key] = out
         return out
 
@@ -312,7 +336,7 @@ class SimEngine:
         with per-kernel timing enabled everything is serialised on the current stream."""
         L = N.lib()
         args = self._args()
-        launches, _ = self.plan(rows)
+        launches, _, split = self.plan(rows)
         main = torch.cuda.current_stream()
         n_streams = int(os.environ.get("XMAP_SIM_STREAMS", "3"))
         use_side = self.profile is None and len(launches) > 1 and n_streams > 1
@@ -322,6 +346,14 @@ class SimEngine:
             for sd in self._side:
                 sd.wait_stream(main)
         stats = []
+        if split is not None:
+            sp = split
+            self._timed("accumulate_split", lambda: N.check(L.xmap_sim_accumulate_split(
+                args, N.ptr(sp["seg_row"]), N.ptr(sp["seg_lo"]), N.ptr(sp["seg_hi"]), N.ptr(sp["seg_slot"]),
+                N.ptr(sp["slot_nseg"]), sp["n_segs"], sp["cells_cap"], N.ptr(sp["gtab"]), N.ptr(sp["done"]),
+                main.cuda_stream), "xmap_sim_accumulate_split"))
+            self.launches += 1
+            stats.append(("accumulate_split", int(sp["rows"].numel())))
         for q, (r, cells_cap, threads, in_gmem) in enumerate(launches):
             gtab, ctas = None, 0
             if in_gmem:
@@ -350,7 +382,7 @@ class SimEngine:
         L = N.lib()
         st = _stream_ptr()
         args = self._args()
-        _, long_cand = self.plan(rows)
+        _, long_cand, _ = self.plan(rows)
         n = self.lay.n_items if rows is None else int(rows.numel())
         rp = None if rows is None else N.ptr(rows.to(self.device, dtype=torch.int32).contiguous())
         self._timed("select_warp", lambda: N.check(L.xmap_sim_select(args, rp, n, 0, st), "xmap_sim_select"))
