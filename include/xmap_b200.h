@@ -117,6 +117,9 @@ int xmap_build_tri_layout(const int32_t *csr_ptr, const uint64_t *csr_ent,
  * (label by 2-character prefix, baselinerSim.py:191; the BB set of assist.py:84-86).
  * row_npairs[i] += co-rated columns row i evaluated (pre-filter).
  * rec_cnt, bb, row_npairs must be zero on entry of the first call of a stage.
+ * List extents: rec_ptr may come from the upper bound min(n_items - 1, row_work - count) per row, or,
+ * when that does not fit in memory, from a sizing pass (count_only = 1) that leaves the exact list
+ * lengths in rec_cnt (the caller scans them into rec_ptr, clears the counters and runs the real pass).
  *
  * A row's accumulator lives in shared memory: a direct-indexed table when the
  * row has few more-popular columns (the popular rows), otherwise an open-
@@ -137,7 +140,7 @@ typedef struct xmap_sim_args {
     const uint8_t *contains;       /* bit d: label d is a substring of iid -- extender.py:32,34 */
     int32_t n_items; int32_t method; int32_t num_atleast; int32_t k;
     int32_t r2_bits;               /* ceil(log2(max |product|)) for the fixed-point scale */
-    int32_t pad0;
+    int32_t count_only;            /* 1: sizing pass -- bump the list cursors, write no record (rec_ptr unused) */
     /* neighbour-record lists */
     const int64_t *rec_ptr;        /* [n_items + 1] list extents (capacity) */
     int32_t *rec_cnt;              /* [n_items] cursors = list lengths */

@@ -25,8 +25,13 @@ def main():
     eng = E.SimEngine(lay, meta, "adjust_cosine", 50, 10)
     tabs = MG.similarity_step(eng, MG.RowShard(eng.tri_work, rank, world))
     eng._check_error()
-    ok = all(torch.equal(getattr(ref, f), getattr(tabs, f)) for f in
-             ("row_flags", "row_npairs", "row_nkept", "tab_len", "tab_idx", "tab_sim", "tab_mutu", "tab_n"))
+    fields = ("row_flags", "row_npairs", "row_nkept", "tab_len", "tab_idx", "tab_sim", "tab_mutu", "tab_n")
+    ok = all(torch.equal(getattr(ref, f), getattr(tabs, f)) for f in fields)
+    # the same with exact list sizing (counting pass + all-reduce of the list lengths)
+    eng_x = E.SimEngine(lay, meta, "adjust_cosine", 50, 10, rec_budget=0)
+    tabs_x = MG.similarity_step(eng_x, MG.RowShard(eng_x.tri_work, rank, world))
+    eng_x._check_error()
+    ok = ok and all(torch.equal(getattr(ref, f), getattr(tabs_x, f)) for f in fields)
     # X-SIM extension sharded by start, generation sharded by user
     from xmap_b200 import extend as X, generate as G
     cnt = lay.item_stats[:, 3].contiguous()

@@ -90,6 +90,27 @@ def test_split_rows_give_identical_results(monkeypatch):
     assert np.array_equal(tabs2.tab_idx.cpu().numpy(), a["tabs"].tab_idx.cpu().numpy())
 
 
+def test_exact_list_sizing_gives_identical_results():
+    """When the upper bound on the record lists does not fit in memory the engine sizes them with a
+    counting pass first; forced here with a zero budget."""
+    import torch
+    from xmap_b200 import engine as E
+    case = PT.synth_case(6000, 1200, 120000, 0.1, seed=5)
+    a = PT.check_sim_against_restatement(case, "adjust_cosine", 50, 7)
+    lay = a["lay"]
+    eng = E.SimEngine(lay, PT.to_device_meta(case["meta"]), "adjust_cosine", 50, 7, rec_budget=0)
+    assert eng.exact_sizing and eng.rec is None
+    tabs = eng.run()
+    assert int(eng.rec_ptr[-1]) == int(tabs.row_nkept.sum())          # extents are exact
+    pairs = eng.emit_pairs()
+    for k in ("i", "j", "sim", "mutu", "n"):
+        assert np.array_equal(a["pairs"][k].cpu().numpy(), pairs[k].cpu().numpy()), k
+    for t in ("tab_idx", "tab_sim", "tab_len", "row_flags", "row_npairs"):
+        assert np.array_equal(getattr(a["tabs"], t).cpu().numpy(), getattr(tabs, t).cpu().numpy()), t
+    tabs = eng.run()                                                      # second run reuses the exact extents
+    assert np.array_equal(a["tabs"].tab_idx.cpu().numpy(), tabs.tab_idx.cpu().numpy())
+
+
 def test_rerun_is_idempotent():
     """Running the stage twice on the same engine gives the same tables (cursors / flags reset)."""
     case = PT.synth_case(3000, 500, 40000, 0.2, seed=9)

@@ -3,11 +3,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bench
 from xmap_b200 import engine as E
 from tests.parity import to_device_meta
+from xmap_b200 import _native as _N
+print("lib", _N.LIB_PATH, flush=True)
 wl = bench.make_workload("cfg2")
 dev = torch.device("cuda"); meta = to_device_meta(wl["meta"], dev)
 lay = E.build_layout(wl["user"], wl["item"], wl["rating"], wl["n_users"], wl["n_items"], device=dev)
-for classes in ("256,512,1024,2048,4096,8192,12288", "256,512,1024,1536,2048,3072,4096,6144,8192,12288"):
-    for ns in ("1", "3", "5"):
+for classes in ("256,512,1024,1536,2048,3072,4096,6144,8192,12288",):
+    for ns in ("1", "3"):
         os.environ["XMAP_SIM_STREAMS"] = ns
         E.CELL_CLASSES = tuple(int(c) for c in classes.split(","))
         eng = E.SimEngine(lay, meta, "adjust_cosine", 50, wl["k"], max_smem_cells=E.CELL_CLASSES[-1])

@@ -40,3 +40,15 @@ w.index_add_(0, plan.par_s.long(), legs_into_t[t_of_par])
 uk, inv = torch.unique(key, return_inverse=True)
 dist_per_s = torch.bincount(torch.div(uk, plan.n_items, rounding_mode="floor"), minlength=w.numel()).double()
 print("walk-weighted: paths %.4g, after per-list dedupe %.4g" % (float((w * rl).sum()), float((w * dist_per_s).sum())))
+# legs of one start that share a bridge target: their paths hit the same ends
+leg_start = torch.repeat_interleave(torch.arange(plan.start_item.numel(), device=dev), (plan.leg_ptr[1:] - plan.leg_ptr[:-1]))
+lk = leg_start * (plan.par_ptr.numel()) + plan.leg_t.long()
+uq, cnts = torch.unique(lk, return_counts=True)
+print("legs %d distinct (start,t) %d" % (lk.numel(), uq.numel()))
+# path-weighted: paths per (start,t) group = group_size * fan(t); updates after grouping = fan(t)
+fan = torch.zeros(plan.par_ptr.numel() - 1, dtype=torch.float64, device=dev)
+fan.index_add_(0, t_of_par, rl[plan.par_s.long()])
+t_of_group = (uq % plan.par_ptr.numel())
+print("paths(all partners) %.4g -> grouped updates %.4g" % (float((cnts.double() * fan[t_of_group]).sum()), float(fan[t_of_group].sum())))
+jo = plan.leg_joint_only.bool()
+print("joint-only legs %d of %d" % (int(jo.sum()), jo.numel()))

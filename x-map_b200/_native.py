@@ -24,7 +24,7 @@ class SimArgs(C.Structure):
         ("ostat", _p), ("ord", _p), ("tri_work", _p),
         ("dom_code", _p), ("contains", _p),
         ("n_items", C.c_int32), ("method", C.c_int32), ("num_atleast", C.c_int32),
-        ("k", C.c_int32), ("r2_bits", C.c_int32), ("pad0", C.c_int32),
+        ("k", C.c_int32), ("r2_bits", C.c_int32), ("count_only", C.c_int32),
         ("rec_ptr", _p), ("rec_cnt", _p), ("rec", _p), ("bb", _p), ("row_npairs", _p),
         ("tab_idx", _p), ("tab_sim", _p), ("tab_mutu", _p), ("tab_n", _p), ("tab_len", _p),
         ("error_flag", _p),

@@ -212,13 +212,18 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__res
                     else atomicExch(a.error_flag, 1);
                 }
                 if (ok) {
-                    const unsigned flo = (unsigned)(unsigned long long)fx;
-                    unsigned fhi = (unsigned)((unsigned long long)fx >> 32);
-                    if (flo) {
-                        const unsigned old = atomicAdd(&T[slot].lo, flo);
-                        fhi += ((unsigned)(old + flo) < old) ? 1u : 0u;
+                    if (sizeof(IDX) == 4) {
+                        // table in global memory: one native 64-bit reduction, nothing to wait for
+                        atomicAdd(reinterpret_cast<unsigned long long *>(&T[slot].lo), (unsigned long long)fx);
+                    } else {
+                        const unsigned flo = (unsigned)(unsigned long long)fx;
+                        unsigned fhi = (unsigned)((unsigned long long)fx >> 32);
+                        if (flo) {
+                            const unsigned old = atomicAdd(&T[slot].lo, flo);
+                            fhi += ((unsigned)(old + flo) < old) ? 1u : 0u;
+                        }
+                        if (fhi) atomicAdd(&T[slot].hi, fhi);
                     }
-                    if (fhi) atomicAdd(&T[slot].hi, fhi);
                 }
             }
         }
@@ -334,6 +339,13 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__res
     int wbase = 0;
     if (lane == 0) wbase = atomicAdd(a.rec_cnt + row, nkept);
     wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (a.count_only) {                                    // sizing pass: only the list lengths are wanted
+        for (int i = gw * 32 + lane; i < n_ent; i += gthreads) {
+            const uint4 cv = T4[occ_list[i]];
+            if ((cv.z | cv.w) != 0u) atomicAdd(a.rec_cnt + int(cv.x & 0xFFFFFFu), 1);
+        }
+        return;
+    }
     if (wbase + nkept > cap_i) {
         if (lane == 0) atomicExch(a.error_flag, 2);
         return;

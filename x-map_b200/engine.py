@@ -151,7 +151,7 @@ class SimEngine:
     """Similarity + top-k selection over a Layout (C ABI section 2)."""
 
     def __init__(self, layout, meta, method="adjust_cosine", num_atleast=50, k=10,
-                 max_smem_cells=CELL_CLASSES[-1]):
+                 max_smem_cells=CELL_CLASSES[-1], rec_budget=None):
         if method not in N.METHODS:
             raise ValueError("unknown similarity method %r" % (method,))
         if not (1 <= k <= N.KMAX):
@@ -183,17 +183,18 @@ class SimEngine:
             N.ptr(self.tcsr_ent), N.ptr(self.csc_aux), N.ptr(self.ostat), N.ptr(self.tri_work),
             N.ptr(ws), ws_bytes, _stream_ptr()), "xmap_build_tri_layout")
         del ws
-        # ---- neighbour-record lists: capacity = co-rating products of the full row, at most I - 1 ----
+        # ---- neighbour-record lists: capacity = co-rating products of the full row, at most I - 1;
+        # when that bound does not fit (rec_budget), the first run does an exact sizing pass instead
         cap = torch.clamp(layout.row_work - count.long(), min=0, max=max(I - 1, 0))
         self.rec_ptr = torch.zeros(I + 1, dtype=torch.int64, device=dev)
         self.rec_ptr[1:] = torch.cumsum(cap, 0)
         self.rec_cap = cap
         total = int(self.rec_ptr[-1].item()) if I else 0
-        free, _ = torch.cuda.mem_get_info(dev)
-        if total * REC_BYTES > free - (1 << 30):
-            raise N.NativeError("neighbour-record lists need %.1f GB, %.1f GB free" %
-                                (total * REC_BYTES / 1e9, free / 1e9))
-        self.rec = torch.empty((max(total, 1), 2), dtype=torch.int64, device=dev)
+        if rec_budget is None:
+            free, _ = torch.cuda.mem_get_info(dev)
+            rec_budget = free // 2
+        self.exact_sizing = total * REC_BYTES > rec_budget
+        self.rec = None if self.exact_sizing else torch.empty((max(total, 1), 2), dtype=torch.int64, device=dev)
         self.rec_cnt = torch.zeros(I, dtype=torch.int32, device=dev)
         self.bb = torch.zeros(I, dtype=torch.uint8, device=dev)
         self.row_npairs = torch.zeros(I, dtype=torch.int32, device=dev)
@@ -219,6 +220,7 @@ class SimEngine:
         a.n_items, a.method = lay.n_items, N.METHODS[self.method]
         a.num_atleast, a.k, a.r2_bits = self.num_atleast, self.k, self.r2_bits
         a.rec_ptr, a.rec_cnt, a.rec = N.ptr(self.rec_ptr), N.ptr(self.rec_cnt), N.ptr(self.rec)
+        a.count_only = 1 if self.rec is None else 0
         a.bb, a.row_npairs = N.ptr(self.bb), N.ptr(self.row_npairs)
         a.tab_idx, a.tab_sim = N.ptr(self.tab_idx), N.ptr(self.tab_sim)
         a.tab_mutu, a.tab_n, a.tab_len = N.ptr(self.tab_mutu), N.ptr(self.tab_n), N.ptr(self.tab_len)
@@ -329,7 +331,33 @@ class SimEngine:
         self.bb.zero_()
         self.row_npairs.zero_()
 
+    def _size_lists(self, rows=None):
+        """Exact sizing pass (only when the upper bound does not fit): the accumulate kernels run once
+        with count_only = 1, the list lengths become the extents.  In a multi-GPU run the lengths are
+        this rank's own records; the exchange appends the others', so the caller must add them (see
+        multi.similarity_step)."""
+        self.rec = None
+        self.reset()
+        self._accumulate(rows)
+        self._check_error()
+        return self.rec_cnt.long().clone()
+
+    def _alloc_lists(self, lengths):
+        I, dev = self.lay.n_items, self.device
+        self.rec_ptr = torch.zeros(I + 1, dtype=torch.int64, device=dev)
+        self.rec_ptr[1:] = torch.cumsum(lengths, 0)
+        self.rec_cap = lengths
+        total = int(self.rec_ptr[-1].item()) if I else 0
+        self.rec = torch.empty((max(total, 1), 2), dtype=torch.int64, device=dev)
+        self._plans = {}
+        self.reset()
+
     def accumulate(self, rows=None):
+        if self.rec is None:
+            self._alloc_lists(self._size_lists(rows))
+        return self._accumulate(rows)
+
+    def _accumulate(self, rows=None):
         """Triangular similarity rows -> neighbour records of both ends, BB flags (xmap_sim_accumulate).
         The launches (one per table capacity / group width) are dealt round-robin to a few streams so
         that the tail of one overlaps the next and the long-running popular rows do not hold the GPU;
@@ -356,8 +384,10 @@ class SimEngine:
             stats.append(("accumulate_split", int(sp["rows"].numel())))
         for q, (r, cells_cap, threads, in_gmem) in enumerate(launches):
             gtab, ctas = None, 0
+            if os.environ.get("XMAP_FORCE_GMEM"):          # experiment: every table in global memory (L2)
+                in_gmem = True
             if in_gmem:
-                ctas = min(int(r.numel()), 296)
+                ctas = min(int(r.numel()), 296 if not os.environ.get("XMAP_FORCE_GMEM") else 148 * max(2, 1536 // threads))
                 need = ctas * ((cells_cap * 20 + 15) // 16 * 16)
                 if self._gtab is None or self._gtab.numel() < need:
                     self._gtab = None

@@ -142,6 +142,14 @@ def exchange_records(rec, rec_ptr, rec_cnt, shard, group=None):
 def similarity_step(engine, shard, group=None):
     """Triangular rows of the owned block -> record exchange -> BB flags -> selection -> gather."""
     rows = None if shard.world == 1 else shard.rows(engine.device)
+    if engine.rec is None and shard.world > 1:
+        # exact list sizing: a rank's lists hold its own records for every row, plus, for the rows it
+        # owns, the records the other ranks will send
+        own = engine._size_lists(rows)
+        tot = own.clone()
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+        own[shard.lo:shard.hi] = tot[shard.lo:shard.hi]
+        engine._alloc_lists(own)
     engine.reset()
     stats = engine.accumulate(rows)
     if shard.world > 1:
