@@ -536,8 +536,12 @@ __global__ void __launch_bounds__(128) select_warp_kernel(xmap_sim_args a, const
         // ---- pass A: per-list histogram of |sim| -------------------------------------------------
         for (int b = lane; b < 2 * SEL_BINS; b += 32) hist[b] = 0u;
         __syncwarp();
+        // long lists: the histogram is built from every 4th block of 128 records.  The threshold bin of
+        // the sample has at least min(K, sample members) entries at or above it, so the full list has
+        // too, and pass B (which sees every record) keeps a superset of the true top-K.
+        const int stride = (m > 1024) ? 4 : 1;
         int n0 = 0, n1 = 0;
-        for (int q0 = 0; q0 < m; q0 += 32 * SU) {
+        for (int q0 = 0; q0 < m; q0 += 32 * SU * stride) {
             Rec v[SU];
             unsigned lb[SU];
 #pragma unroll
@@ -562,8 +566,8 @@ __global__ void __launch_bounds__(128) select_warp_kernel(xmap_sim_args a, const
         }
         __syncwarp();
         for (int list = 0; list < 2; ++list) {
-            want[list] = min(K, list == 0 ? n0 : n1);
-            if (want[list] == 0) continue;
+            want[list] = min(K, list == 0 ? n0 : n1);       // of the sample; the final value comes from pass B
+            if (want[list] < K) continue;                    // fewer than K sampled members: keep everything (b* = 0)
             // largest bin b* such that #(bin >= b*) >= want: scan the histogram from the top
             int run = 0;
             bool found = false;
@@ -582,6 +586,7 @@ __global__ void __launch_bounds__(128) select_warp_kernel(xmap_sim_args a, const
         __syncwarp();                                      // the histogram is dead; its memory becomes the survivor buffers
     }
     // ---- pass B: the survivors of both lists (everything when the list fits the buffer) ------------
+    int nl0 = 0, nl1 = 0;                                  // members of each list, counted over every record
     for (int q0 = 0; q0 < m; q0 += 32 * SU) {
         Rec v[SU];
         unsigned lb[SU];
@@ -597,6 +602,7 @@ __global__ void __launch_bounds__(128) select_warp_kernel(xmap_sim_args a, const
         for (int u = 0; u < SU; ++u) {
             const unsigned long long key = v[u].sim & 0x7FFFFFFFFFFFFFFFull;
             const int bin = sim_bin(key);
+            nl0 += int(lb[u] & 1u); nl1 += int((lb[u] >> 1) & 1u);
 #pragma unroll
             for (int list = 0; list < 2; ++list) {
                 const bool take = ((lb[u] >> list) & 1u) && bin >= bstar[list];
@@ -607,28 +613,41 @@ __global__ void __launch_bounds__(128) select_warp_kernel(xmap_sim_args a, const
             }
         }
     }
-    if (m <= SEL_DIRECT) { want[0] = min(K, nb[0]); want[1] = min(K, nb[1]); }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        nl0 += __shfl_xor_sync(0xffffffffu, nl0, off);
+        nl1 += __shfl_xor_sync(0xffffffffu, nl1, off);
+    }
+    want[0] = min(K, nl0); want[1] = min(K, nl1);
     __syncwarp();
     // ---- K arg-best rounds per list --------------------------------------------------------------
     for (int list = 0; list < 2; ++list) {
         int got = 0;
         const size_t o = ((size_t)row * 2 + list) * K;
         unsigned long long last_k = ~0ull; int last_t = -1;
-        if (!overflow[list] && nb[list] <= 32) {
-            // one survivor per lane: rank by counting, every winner writes its own table entry
-            Surv mine{0ull, -1, 0x7FFFFFFF};
-            if (lane < nb[list]) mine = buf[list][lane];
-            int rank = 0;
-            for (int t = 0; t < nb[list]; ++t) {
-                const unsigned long long k2 = __shfl_sync(0xffffffffu, mine.key, t);
-                const int j2 = __shfl_sync(0xffffffffu, mine.j, t);
-                if (better(k2, j2, mine.key, mine.j)) ++rank;
+        if (!overflow[list] && nb[list] <= 64) {
+            // at most two survivors per lane: rank by counting, every winner writes its own table entry
+            const int n = nb[list];
+            Surv m0{0ull, -1, 0x7FFFFFFF}, m1{0ull, -1, 0x7FFFFFFF};
+            if (lane < n) m0 = buf[list][lane];
+            if (lane + 32 < n) m1 = buf[list][lane + 32];
+            int r0 = 0, r1 = 0;
+            for (int t = 0; t < n; ++t) {
+                const Surv o2 = buf[list][t];               // same address in every lane: a broadcast read
+                r0 += better(o2.key, o2.j, m0.key, m0.j) ? 1 : 0;
+                r1 += better(o2.key, o2.j, m1.key, m1.j) ? 1 : 0;
             }
-            if (lane < nb[list] && rank < want[list]) {
-                const Rec v = R[mine.q];
-                a.tab_idx[o + rank] = mine.j;
-                a.tab_sim[o + rank] = __longlong_as_double((long long)v.sim);
-                a.tab_mutu[o + rank] = rec_mutu(v.pack); a.tab_n[o + rank] = rec_n(v.pack);
+            if (lane < n && r0 < want[list]) {
+                const Rec v = R[m0.q];
+                a.tab_idx[o + r0] = m0.j;
+                a.tab_sim[o + r0] = __longlong_as_double((long long)v.sim);
+                a.tab_mutu[o + r0] = rec_mutu(v.pack); a.tab_n[o + r0] = rec_n(v.pack);
+            }
+            if (lane + 32 < n && r1 < want[list]) {
+                const Rec v = R[m1.q];
+                a.tab_idx[o + r1] = m1.j;
+                a.tab_sim[o + r1] = __longlong_as_double((long long)v.sim);
+                a.tab_mutu[o + r1] = rec_mutu(v.pack); a.tab_n[o + r1] = rec_n(v.pack);
             }
             if (lane == 0) a.tab_len[(size_t)row * 2 + list] = want[list];
             continue;
