@@ -39,7 +39,8 @@ WORKLOADS = {
 METRIC = "item_pair_sims_per_sec"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
 # (profiles/), keyed by kernel group; None until captured.
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {"tri_cta_kernel": 5.857e9 / 14}   # (2.883 GB read + 2.974 GB written) over the 14 launches of one stage,
+                                                 # profiles/r1_ncu_full_cfg2.csv; per launch like `achieved`
 
 
 def make_workload(name):
