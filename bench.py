@@ -261,7 +261,7 @@ def main():
     # resident layout for the device-timed metric
     lay = E.build_layout(h_user, h_item, h_rating, wl["n_users"], wl["n_items"], device=dev)
     eng = E.SimEngine(lay, meta, args.method, 50, k)
-    shard = MG.RowShard(eng.tri_work, rank, world)
+    shard = MG.similarity_shard(eng, rank, world)
 
     def sim_step(engine):
         return MG.similarity_step(engine, shard)
@@ -301,7 +301,7 @@ def main():
     def e2e_step():
         lay2 = E.build_layout(h_user, h_item, h_rating, wl["n_users"], wl["n_items"], device=dev)
         eng2 = E.SimEngine(lay2, meta, args.method, 50, k)
-        t = MG.similarity_step(eng2, MG.RowShard(eng2.tri_work, rank, world))
+        t = MG.similarity_step(eng2, MG.similarity_shard(eng2, rank, world))
         out = eng2.tables_to_host(t)                 # pinned host buffers, synchronises
         return sum(o.numel() * o.element_size() for o in out.values())
     e2e_step()

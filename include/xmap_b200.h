@@ -182,6 +182,14 @@ int xmap_sim_accumulate_split(const xmap_sim_args *args_h, const int32_t *seg_ro
 int xmap_sim_select(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
                     int32_t long_rows, void *stream);
 
+/* Segmented copy of 16-byte records: record k of segment g goes from src[src_pos[g] + k] to
+ * dst[dst_pos[g] + k]; seg_off = exclusive scan of the segment lengths, total = their sum.
+ * Packs the neighbour-record lists addressed to another rank's rows into a contiguous send buffer
+ * and appends received records to the owned lists, around the NCCL all-to-all that replaces the
+ * reduceByKey shuffle of baselinerSim.py:210-211, 232-233. */
+int xmap_segmented_copy16(const void *src, const int64_t *src_pos, void *dst, const int64_t *dst_pos,
+                          const int64_t *seg_off, int32_t n_seg, int64_t total, void *stream);
+
 /* ---------------------------------------------------------------------------
  * (3) X-SIM extension: masked path composition with fused aggregation.
  * Replaces: ExtendSim.sim_extend + get_final_extension (extender.py:46-217).

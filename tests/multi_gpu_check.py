@@ -23,13 +23,13 @@ def main():
     lay = E.build_layout(case["user"], case["item"], case["rating"], case["n_users"], case["n_items"], device=dev)
     ref = E.SimEngine(lay, meta, "adjust_cosine", 50, 10).run()
     eng = E.SimEngine(lay, meta, "adjust_cosine", 50, 10)
-    tabs = MG.similarity_step(eng, MG.RowShard(eng.tri_work, rank, world))
+    tabs = MG.similarity_step(eng, MG.similarity_shard(eng, rank, world))
     eng._check_error()
     fields = ("row_flags", "row_npairs", "row_nkept", "tab_len", "tab_idx", "tab_sim", "tab_mutu", "tab_n")
     ok = all(torch.equal(getattr(ref, f), getattr(tabs, f)) for f in fields)
     # the same with exact list sizing (counting pass + all-reduce of the list lengths)
     eng_x = E.SimEngine(lay, meta, "adjust_cosine", 50, 10, rec_budget=0)
-    tabs_x = MG.similarity_step(eng_x, MG.RowShard(eng_x.tri_work, rank, world))
+    tabs_x = MG.similarity_step(eng_x, MG.similarity_shard(eng_x, rank, world))
     eng_x._check_error()
     ok = ok and all(torch.equal(getattr(ref, f), getattr(tabs_x, f)) for f in fields)
     # X-SIM extension sharded by start, generation sharded by user

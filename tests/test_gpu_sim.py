@@ -111,6 +111,30 @@ def test_exact_list_sizing_gives_identical_results():
     assert np.array_equal(a["tabs"].tab_idx.cpu().numpy(), tabs.tab_idx.cpu().numpy())
 
 
+def test_segmented_copy_matches_torch():
+    """The pack / append kernel of the multi-GPU record exchange against plain indexing."""
+    import torch
+    from xmap_b200 import multi as MG
+    g = torch.Generator().manual_seed(12)
+    n_seg = 5000
+    seg_len = (torch.rand(n_seg, generator=g) ** 6 * 3000).long()
+    seg_len[::7] = 0
+    seg_len[123] = 200000                                  # one very long list
+    seg_len = seg_len.cuda()
+    total = int(seg_len.sum())
+    src = torch.randint(-2**62, 2**62, (total + 1000, 2), generator=g, dtype=torch.int64).cuda()
+    gaps = torch.randint(0, 5, (n_seg,), generator=g).cuda()
+    dst_pos = torch.cumsum(seg_len + gaps, 0) - seg_len - gaps + 3
+    src_pos = torch.cumsum(seg_len, 0) - seg_len + 1000
+    dst = torch.zeros((int((seg_len + gaps).sum()) + 8, 2), dtype=torch.int64, device="cuda")
+    MG._segmented_copy(src, src_pos, dst, dst_pos, seg_len)
+    seg = torch.repeat_interleave(torch.arange(n_seg, device="cuda"), seg_len)
+    k = torch.arange(total, device="cuda") - (torch.cumsum(seg_len, 0) - seg_len)[seg]
+    want = torch.zeros_like(dst)
+    want[dst_pos[seg] + k] = src[src_pos[seg] + k]
+    assert torch.equal(dst, want)
+
+
 def test_rerun_is_idempotent():
     """Running the stage twice on the same engine gives the same tables (cursors / flags reset)."""
     case = PT.synth_case(3000, 500, 40000, 0.2, seed=9)

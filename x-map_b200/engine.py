@@ -125,10 +125,8 @@ CELL_CLASSES = tuple(int(c) for c in os.environ.get("XMAP_CELL_CLASSES", "256,51
 
 
 def _threads_for_cells(c):
-    """Threads per row a table capacity gets at least: ~8 cells per thread, so that shared memory
-    (the occupancy limiter) is matched by enough resident warps."""
-    cpt = int(os.environ.get("XMAP_CELLS_PER_THREAD", "8"))
-    return max(32, min(512, (c // cpt + 31) // 32 * 32))
+    """Threads per row a table capacity gets at least: 8 cells per thread (measured best of 4 / 8 / 16 / 32)."""
+    return max(32, min(512, (c // 8 + 31) // 32 * 32))
 
 REC_BYTES = 16
 SPLIT_RATERS = int(os.environ.get("XMAP_SPLIT_RATERS", "16384"))   # rows with at least this many raters are split ...
@@ -384,10 +382,8 @@ class SimEngine:
             stats.append(("accumulate_split", int(sp["rows"].numel())))
         for q, (r, cells_cap, threads, in_gmem) in enumerate(launches):
             gtab, ctas = None, 0
-            if os.environ.get("XMAP_FORCE_GMEM"):          # experiment: every table in global memory (L2)
-                in_gmem = True
             if in_gmem:
-                ctas = min(int(r.numel()), 296 if not os.environ.get("XMAP_FORCE_GMEM") else 148 * max(2, 1536 // threads))
+                ctas = min(int(r.numel()), 296)
                 need = ctas * ((cells_cap * 20 + 15) // 16 * 16)
                 if self._gtab is None or self._gtab.numel() < need:
                     self._gtab = None

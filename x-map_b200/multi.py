@@ -105,12 +105,60 @@ def _list_slots(base, seg):
     return base[r] + (torch.arange(tot, device=seg.device) - first[r]), tot
 
 
+def _segmented_copy(src, src_pos, dst, dst_pos, seg_len):
+    """dst[dst_pos[g] + k] = src[src_pos[g] + k] for k < seg_len[g] (16-byte records, CUDA)."""
+    from . import _native as N
+    seg_off = (torch.cumsum(seg_len, 0) - seg_len).contiguous()
+    total = int(seg_len.sum())
+    N.check(N.lib().xmap_segmented_copy16(N.ptr(src), N.ptr(src_pos.contiguous()), N.ptr(dst),
+                                          N.ptr(dst_pos.contiguous()), N.ptr(seg_off), int(seg_len.numel()), total,
+                                          torch.cuda.current_stream().cuda_stream), "xmap_segmented_copy16")
+
+
+def exchange_records_cuda(rec, rec_ptr, rec_cnt, shard, group=None):
+    """exchange_records on the GPU: one packing kernel, one all-to-all of the lengths, one all-to-all
+    of the records (NCCL), one appending kernel; two small device -> host reads for the split sizes."""
+    world, rank, dev = shard.world, shard.rank, rec.device
+    I = shard.n_items
+    lo, hi = shard.lo, shard.hi
+    own = hi - lo
+    bounds = torch.tensor(shard.bounds, dtype=torch.int64, device=dev)
+    cnt = rec_cnt.long()
+    out_cnt = cnt.clone()
+    out_cnt[lo:hi] = 0                                       # rows are rank-major, so is the packed buffer
+    csum = torch.zeros(I + 1, dtype=torch.int64, device=dev)
+    csum[1:] = torch.cumsum(out_cnt, 0)
+    in_split = (csum[bounds[1:]] - csum[bounds[:-1]])         # records for each destination
+    # lengths first (device all-to-all of int64 vectors of unequal size)
+    send_cnt = [out_cnt[shard.bounds[s]:shard.bounds[s + 1]].contiguous() for s in range(world)]
+    recv_cnt = [torch.empty(own, dtype=torch.int64, device=dev) for _ in range(world)]
+    _all_to_all(recv_cnt, send_cnt, group)
+    RC = torch.stack(recv_cnt)                               # [world, own]; row `rank` is zero
+    sizes = torch.cat([in_split, RC.sum(1)]).tolist()         # the one host read
+    in_sizes, out_sizes = sizes[:world], sizes[world:]
+    send = torch.empty((max(sum(in_sizes), 1), 2), dtype=rec.dtype, device=dev)
+    _segmented_copy(rec, rec_ptr[:-1], send, csum[:-1], out_cnt)
+    recv = torch.empty((max(sum(out_sizes), 1), 2), dtype=rec.dtype, device=dev)
+    dist.all_to_all_single(recv[:sum(out_sizes)], send[:sum(in_sizes)], out_sizes, in_sizes, group=group)
+    # append: source-major segments (s, row) land after the row's own records and the earlier sources'
+    before = torch.cumsum(RC, 0) - RC + cnt[lo:hi].unsqueeze(0)
+    seg_len = RC.reshape(-1)
+    src_pos = torch.cumsum(seg_len, 0) - seg_len
+    dst_pos = (rec_ptr[lo:hi].unsqueeze(0) + before).reshape(-1)
+    _segmented_copy(recv, src_pos, rec, dst_pos, seg_len)
+    new_cnt = cnt[lo:hi] + RC.sum(0)
+    rec_cnt.zero_()
+    rec_cnt[lo:hi] = new_cnt.to(rec_cnt.dtype)
+
+
 def exchange_records(rec, rec_ptr, rec_cnt, shard, group=None):
     """rec [total, 2] int64 records, rec_ptr [I + 1] list extents, rec_cnt [I] list lengths.
     On entry the lists hold the records THIS rank produced, for every row; on exit the lists of the
     rows this rank owns hold the records of every rank and the other lists are empty."""
     if shard.world == 1:
         return
+    if rec.is_cuda:
+        return exchange_records_cuda(rec, rec_ptr, rec_cnt, shard, group)
     world, rank = shard.world, shard.rank
     cnt = rec_cnt.long()
     blocks = [(shard.bounds[s], shard.bounds[s + 1]) for s in range(world)]
@@ -137,6 +185,12 @@ def exchange_records(rec, rec_ptr, rec_cnt, shard, group=None):
         cur += recv_cnt[s]
     rec_cnt.zero_()
     rec_cnt[shard.lo:shard.hi] = cur.to(rec_cnt.dtype)
+
+
+def similarity_shard(engine, rank=0, world=1):
+    """Row blocks balanced by the cost of both phases: the products a row evaluates (accumulate,
+    ~30 ps each) and the records it will have to select from (~1/6 of its list capacity at ~18 ps)."""
+    return RowShard(engine.tri_work + engine.rec_cap // 6, rank, world)
 
 
 def similarity_step(engine, shard, group=None):
