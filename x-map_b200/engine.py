@@ -278,18 +278,23 @@ class SimEngine:
                          gtab=torch.zeros((srows.numel() * cap, 2), dtype=torch.int64, device=dev),
                          done=torch.zeros(srows.numel(), dtype=torch.int32, device=dev))
             live = live & ~is_split
+        # one sort by (launch group, descending work) yields every launch's row list as a slice
         code = (cls * 2048 + threads)[live]
         rows_l, work_l, cells_l = rows[live], work[live], cells[live]
-        launches = []
-        for c in torch.unique(code).tolist():
-            m = code == c
-            r, w = rows_l[m], work_l[m]
-            r = r[torch.argsort(w, descending=True, stable=True)].contiguous()
+        order = torch.argsort(code * (1 << 40) + ((1 << 40) - 1 - work_l.clamp(max=(1 << 40) - 1)))
+        rows_s = rows_l[order].contiguous()
+        codes, counts = torch.unique_consecutive(code[order], return_counts=True)
+        gmax = torch.zeros(int(cls.max().item()) * 2048 + 2048 if cls.numel() else 1, dtype=torch.int64, device=dev)
+        gmax.scatter_reduce_(0, code, cells_l, "amax")
+        launches, at = [], 0
+        for c, n, mx in zip(codes.tolist(), counts.tolist(), gmax[codes].tolist()):
+            r = rows_s[at:at + n]
+            at += n
             q, th = c // 2048, c % 2048
             if q < len(classes):
                 launches.append((r, classes[q], th, False))
             else:
-                launches.append((r, int(cells_l[m].max().item()), 512, True))
+                launches.append((r, int(mx), 512, True))
         launches.sort(key=lambda t: (-t[2], -t[1]))                # big CTAs first
         long_cand = rows[self.rec_cap[rl] > N.SELECT_LONG].contiguous()
         out = (launches, long_cand, split)
