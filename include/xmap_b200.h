@@ -221,7 +221,7 @@ typedef struct xmap_xsim_args {
     const int64_t *rs_ptr;                    /* [n_s+1] */
     const int32_t *rs_end;
     const double *rs_n, *rs_d, *rs_c;         /* per right segment: sum sim*mutu, sum mutu, prod frac of its edges */
-    /* per-unit hash region: [hash_off[u], hash_off[u]+hash_size[u]) 24-byte cells {u64 key, f64 num,
+    /* per-unit hash region: [hash_off[u], hash_off[u]+hash_size[u]) 32-byte cells {u64 key, f64 num,
      * f64 den}, size >= 32.  key = epoch << 32 | (end + 1): cells of another epoch are
      * empty, so the workspace is zeroed once when allocated and every launch passes a fresh epoch >= 1. */
     const int64_t *hash_off; const int32_t *hash_size;

@@ -16,13 +16,14 @@ namespace xmap {
 
 constexpr int XS_THREADS = 256;
 
-// 24-byte accumulator cell.  key = epoch << 32 | (end item + 1): a cell whose epoch differs from the
-// launch's epoch is empty, so the workspace never has to be cleared between launches (it is zeroed
-// once when allocated and every launch uses a fresh epoch).  Key and values share a 32-byte sector
-// in 3 of 4 cells, so a probe + update costs about one DRAM sector each way.
-struct XCell {
+// 32-byte accumulator cell, aligned to a DRAM sector, so a probe + update touches exactly one sector each
+// way (a packed 24-byte cell straddles a sector boundary half of the time).  key = epoch << 32 |
+// (end item + 1): a cell whose epoch differs from the launch's epoch is empty, so the workspace never has
+// to be cleared between launches (it is zeroed once when allocated and every launch uses a fresh epoch).
+struct __align__(32) XCell {
     unsigned long long key;
     double num, den;
+    unsigned long long pad;
 };
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(XS_THREADS) xsim_finalize_kernel(xmap_xsim_arg
         int64_t base = a.emit_ptr[x];
         int written = 0;
         for (int s0 = 0; s0 < hsize; s0 += 32) {
-            XCell c{0ull, 0.0, 0.0};
+            XCell c{0ull, 0.0, 0.0, 0ull};
             if (s0 + lane < hsize) c = tab[s0 + lane];
             const bool occ = (unsigned)(c.key >> 32) == epoch;
             const unsigned m = __ballot_sync(0xffffffffu, occ);
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(XS_THREADS) xsim_finalize_kernel(xmap_xsim_arg
     int nb = 0;
     bool overflow = false;
     for (int s0 = 0; s0 < hsize && M > 0; s0 += 32) {
-        XCell c{0ull, 0.0, 0.0};
+        XCell c{0ull, 0.0, 0.0, 0ull};
         if (s0 + lane < hsize) c = tab[s0 + lane];
         bool take = false;
         unsigned long long kk = 0ull;

@@ -301,7 +301,7 @@ class XsimEngine:
         self.hsize = torch.clamp((5 * torch.clamp(sub_ub, max=end_cap) + 3) // 4, min=32)
         self.start_bytes = torch.zeros(n, dtype=i64, device=dev)
         if n_units:
-            self.start_bytes.index_add_(0, self.unit_start, self.hsize * 24)
+            self.start_bytes.index_add_(0, self.unit_start, self.hsize * 32)
         # the two edges of a right segment folded into one (N, D, C) triple: 28 instead of 60 bytes per
         # path (the sums are reassociated by at most one rounding; D is an exact integer either way)
         e1, m1, f1, e2, m2, f2 = p.rs_vals
@@ -319,8 +319,8 @@ class XsimEngine:
 
     # ------------------------------------------------------------------
     def _workspace(self, n_cells):
-        """Persistent cell workspace (24 B cells), zeroed once; launches are told apart by epoch."""
-        need = n_cells * 3
+        """Persistent cell workspace (32 B cells), zeroed once; launches are told apart by epoch."""
+        need = n_cells * 4
         if self._cells is None or self._cells.numel() < need:
             self._cells = None
             self._cells = torch.zeros(need, dtype=torch.int64, device=self.device)
