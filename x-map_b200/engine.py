@@ -431,8 +431,9 @@ class SimEngine:
         self._check_error()
         return self.tables(dict(accumulate=stats))
 
-    def tables(self, stats=None):
-        return SimTables(self.k, self.lay.n_items, self.bb, self.row_npairs, self.rec_cnt,
+    def tables(self, stats=None, row_nkept=None):
+        return SimTables(self.k, self.lay.n_items, self.bb, self.row_npairs,
+                         self.rec_cnt if row_nkept is None else row_nkept,
                          self.tab_idx, self.tab_sim, self.tab_mutu, self.tab_n, self.tab_len,
                          self.launches, stats or {})
 

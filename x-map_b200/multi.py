@@ -210,11 +210,13 @@ def similarity_step(engine, shard, group=None):
         engine._timed("exchange", lambda: exchange_records(engine.rec, engine.rec_ptr, engine.rec_cnt, shard, group))
         dist.all_reduce(engine.bb, op=dist.ReduceOp.MAX, group=group)
     engine.select(rows)
+    nkept = None
     if shard.world > 1:
-        for t in (engine.row_npairs, engine.rec_cnt, engine.tab_len, engine.tab_idx, engine.tab_sim,
+        nkept = engine.rec_cnt.clone()          # the lists stay sharded: only the lengths are gathered
+        for t in (engine.row_npairs, nkept, engine.tab_len, engine.tab_idx, engine.tab_sim,
                   engine.tab_mutu, engine.tab_n):
             allgather_rows(t, shard, group)
-    return engine.tables(dict(accumulate=stats, rows=(shard.lo, shard.hi)))
+    return engine.tables(dict(accumulate=stats, rows=(shard.lo, shard.hi)), row_nkept=nkept)
 
 
 def allreduce_xsim(res, group=None):
