@@ -367,7 +367,7 @@ def main():
                 fam = kk
             fam_ms[fam] = fam_ms.get(fam, 0.0) + ms_k
             fam_n[fam] = fam_n.get(fam, 0) + n
-        for r, cells_cap, threads, in_gmem in launches_plan:
+        for r, cells_cap, threads, in_gmem, _hdr in launches_plan:
             fam = "tri_gmem_kernel" if in_gmem else ("tri_warp_kernel" if threads == 32 else "tri_cta_kernel")
             fam_bytes[fam] = fam_bytes.get(fam, 0.0) + 8.0 * float(eng.tri_work[r.long()].sum().item())
         if split_plan is not None:

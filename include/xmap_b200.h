@@ -152,23 +152,31 @@ typedef struct xmap_sim_args {
     int32_t *error_flag;           /* device int: 1 table overflow, 2 list capacity, 3 count range */
 } xmap_sim_args;
 
+/* Row headers: everything a row's thread group needs before it can start (item, ord, rater range, work,
+ * norm, prefix / class, list extent) gathered into one 48-byte record per launch slot, so a group begins
+ * with one load instead of a chain of dependent gathers.  Built once per plan (and again when rec_ptr
+ * changes).  seg_lo / seg_hi (both NULL or both given) replace the rater range for split rows. */
+#define XMAP_SIM_ROW_HDR_BYTES 48
+int xmap_sim_row_headers(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
+                         const int32_t *seg_lo, const int32_t *seg_hi, void *hdr_out, void *stream);
+
 #define XMAP_SIM_MAX_SMEM_CELLS 12288     /* 12288 x (16-byte cell + 2-byte slot index) = 216 KB */
 /* cells a row needs: min(#more popular items, ceil(4/3 * tri_work)), at least 32 */
 int64_t xmap_sim_row_cells(int64_t tri_work, int32_t n_more_popular);
-int xmap_sim_accumulate(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
+int xmap_sim_accumulate(const xmap_sim_args *args_h, const void *row_hdr, int32_t n_rows,
                         int32_t cells_cap, int32_t threads_per_row,
                         void *gtab, int32_t gtab_ctas, void *stream);
 
 /* Rows with very many raters (the most popular items: long rater lists, few products per rater)
  * are bound by the walk over their raters, so their rater list is cut into segments, one CTA each.
- * Segment g covers CSC positions [seg_lo[g], seg_hi[g]) of row seg_row[g], which is the seg_slot[g]-th
+ * Segment g (header seg_hdr[g], built with its rater range [seg_lo[g], seg_hi[g])) belongs to the seg_slot[g]-th
  * split row; slot_nseg[slot] = number of segments of that row.  Only direct-indexed rows (at most
  * cells_cap more popular items) may be split.  gtab: [n_slots][cells_cap] 16-byte cells and
  * done: [n_slots] ints, both zero on entry and zero again on exit.  Results are bit-identical to
  * the unsplit row (the partial tables are combined with exact integer adds). */
-int xmap_sim_accumulate_split(const xmap_sim_args *args_h, const int32_t *seg_row, const int32_t *seg_lo,
-                              const int32_t *seg_hi, const int32_t *seg_slot, const int32_t *slot_nseg,
-                              int32_t n_segs, int32_t cells_cap, void *gtab, int32_t *done, void *stream);
+int xmap_sim_accumulate_split(const xmap_sim_args *args_h, const void *seg_hdr, const int32_t *seg_slot,
+                              const int32_t *slot_nseg, int32_t n_segs, int32_t cells_cap, void *gtab,
+                              int32_t *done, void *stream);
 
 /* Per-row top-k selection over the neighbour-record lists (extender.py:16-44), after
  * every rank's records are in place and bb holds the flags of ALL items:

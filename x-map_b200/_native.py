@@ -14,6 +14,7 @@ KMAX = 64
 METHODS = {"adjust_cosine": 0, "cosine": 1}
 SELECT_LONG = 8192            # XMAP_SELECT_LONG
 ABI_VERSION = 2
+ROW_HDR_BYTES = 48          # XMAP_SIM_ROW_HDR_BYTES
 
 _p = C.c_void_p
 
@@ -62,7 +63,8 @@ _SIGS = {
                                         _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "xmap_sim_row_cells": (C.c_int64, [C.c_int64, C.c_int32]),
     "xmap_sim_accumulate": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, C.c_int32, C.c_int32, _p, C.c_int32, _p]),
-    "xmap_sim_accumulate_split": (C.c_int, [C.POINTER(SimArgs), _p, _p, _p, _p, _p, C.c_int32, C.c_int32, _p, _p, _p]),
+    "xmap_sim_row_headers": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, _p, _p, _p, _p]),
+    "xmap_sim_accumulate_split": (C.c_int, [C.POINTER(SimArgs), _p, _p, _p, C.c_int32, C.c_int32, _p, _p, _p]),
     "xmap_sim_select": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, C.c_int32, _p]),
     "xmap_segmented_copy16": (C.c_int, [_p, _p, _p, _p, _p, C.c_int32, C.c_int64, _p]),
     "xmap_xsim_extend": (C.c_int, [C.POINTER(XsimArgs), _p]),

@@ -62,6 +62,49 @@ __device__ __forceinline__ int rec_item(unsigned long long p) { return int(p & 0
 __device__ __forceinline__ int rec_n(unsigned long long p) { return int((p >> 24) & REC_CNT_MASK); }
 __device__ __forceinline__ int rec_mutu(unsigned long long p) { return int((p >> 44) & REC_CNT_MASK); }
 
+// Everything a row's group needs before it can start, gathered once at planning time into one
+// 48-byte record per launch slot (one load instead of a chain of dependent gathers).
+struct __align__(16) RowHdr {
+    int row, oi, lo, hi;          // item, its ord, its rater range (CSC positions; a segment of it for split rows)
+    long long work;               // tri_work[row]
+    double den;                   // ostat[oi].den
+    long long rec_base;           // rec_ptr[row]
+    unsigned prefix_cls;          // ostat[oi].prefix_cls
+    int rec_cap;                  // rec_ptr[row + 1] - rec_ptr[row]
+};
+static_assert(sizeof(RowHdr) == 48, "RowHdr layout");
+
+__device__ __forceinline__ RowHdr load_hdr(const RowHdr *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    const uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    RowHdr h;
+    h.row = (int)a.x; h.oi = (int)a.y; h.lo = (int)a.z; h.hi = (int)a.w;
+    h.work = (long long)(((unsigned long long)b.y << 32) | b.x);
+    h.den = __hiloint2double((int)b.w, (int)b.z);
+    h.rec_base = (long long)(((unsigned long long)c.y << 32) | c.x);
+    h.prefix_cls = c.z; h.rec_cap = (int)c.w;
+    return h;
+}
+
+__global__ void row_headers_kernel(xmap_sim_args a, const int32_t *__restrict__ rows, int n_rows,
+                                   const int32_t *__restrict__ seg_lo, const int32_t *__restrict__ seg_hi,
+                                   RowHdr *__restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const int row = rows[r];
+    const OStat *ostat = reinterpret_cast<const OStat *>(a.ostat);
+    RowHdr h;
+    h.row = row; h.oi = a.ord[row];
+    h.lo = seg_lo ? seg_lo[r] : a.csc_ptr[row];
+    h.hi = seg_hi ? seg_hi[r] : a.csc_ptr[row + 1];
+    h.work = a.tri_work[row];
+    const OStat si = ostat[h.oi];
+    h.den = si.den; h.prefix_cls = si.prefix_cls;
+    h.rec_base = a.rec_ptr[row];
+    h.rec_cap = (int)(a.rec_ptr[row + 1] - a.rec_ptr[row]);
+    out[r] = h;
+}
+
 __host__ __device__ __forceinline__ long long hash_cells_for(long long work) {
     long long c = (work * 4 + 2) / 3;
     return c < 32 ? 32 : c;
@@ -106,12 +149,11 @@ struct SplitCtx {
     uint4 *gtab;        // the row's direct-indexed table in global memory, zero outside a stage
     int *done;          // arrival counter of the row's segments, zero outside a stage
     int nseg;
-    int seg_lo, seg_hi; // rater range (CSC positions) of this segment
 };
 
 template <bool CTA_ROW, class IDX>
 __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__restrict__ occ_list, int *s_cnt,
-                        int cells_cap, int row, const SplitCtx *sp = nullptr) {
+                        int cells_cap, const RowHdr *hdr_p, const SplitCtx *sp = nullptr) {
     const int lane = threadIdx.x & 31;
     const int gwarps = CTA_ROW ? (blockDim.x >> 5) : 1;
     const int gw = CTA_ROW ? (threadIdx.x >> 5) : 0;
@@ -119,12 +161,12 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__res
     const unsigned lt_mask = (1u << lane) - 1u;
     const OStat *__restrict__ ostat = reinterpret_cast<const OStat *>(a.ostat);
 
-    const int oi = a.ord[row];
-    const OStat si = ostat[oi];
-    const int cls_i = int(si.prefix_cls & 0xFFu);
-    const unsigned prefix_i = si.prefix_cls >> 8;
-    const int lo = sp ? sp->seg_lo : a.csc_ptr[row], hi = sp ? sp->seg_hi : a.csc_ptr[row + 1];
-    const long long work = a.tri_work[row];
+    const RowHdr hd = load_hdr(hdr_p);
+    const int row = hd.row, oi = hd.oi;
+    const int cls_i = int(hd.prefix_cls & 0xFFu);
+    const unsigned prefix_i = hd.prefix_cls >> 8;
+    const int lo = hd.lo, hi = hd.hi;
+    const long long work = hd.work;
     const int rtop = a.n_items - 1 - oi;                   // items more popular than `row`
     const long long hcells = hash_cells_for(work);
     const bool direct = (long long)rtop <= hcells;
@@ -313,7 +355,7 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__res
             const long long fx = (long long)(((unsigned long long)cv[u].w << 32) | (unsigned long long)cv[u].z);
             if (fx == 0 || mutu[u] == 0u) { T4[sidx[u]] = out; continue; }     // sim == 0 or mutu == 0: filtered
             const double inner = (double)fx * pow2d(-q);
-            const double dd = __dmul_rn(si.den, sj[u].den);
+            const double dd = __dmul_rn(hd.den, sj[u].den);
             const double cosv = (dd != 0.0) ? __ddiv_rn(inner, dd) : 0.0;
             const int mn = min((int)n[u], a.num_atleast);
             const double sim = __ddiv_rn(__dmul_rn(cosv, (double)mn), (double)a.num_atleast);
@@ -334,8 +376,8 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__res
     // ---- epilogue pass 2: one reservation per warp in the row's own list, then append the records
     // to the own list (compacted) and to each neighbour's list (one cursor bump per record) --------
     Rec *__restrict__ rec = reinterpret_cast<Rec *>(a.rec);
-    const long long base_i = a.rec_ptr[row];
-    const int cap_i = (int)(a.rec_ptr[row + 1] - base_i);
+    const long long base_i = hd.rec_base;
+    const int cap_i = hd.rec_cap;
     int wbase = 0;
     if (lane == 0) wbase = atomicAdd(a.rec_cnt + row, nkept);
     wbase = __shfl_sync(0xffffffffu, wbase, 0);
@@ -389,7 +431,7 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__res
 __host__ __device__ constexpr size_t row_smem_bytes(int cells_cap) { return (size_t)cells_cap * (sizeof(Cell) + 2); }
 
 // one warp per row, tables in shared memory, rows sorted by descending work
-__global__ void __launch_bounds__(128) tri_warp_kernel(xmap_sim_args a, const int32_t *__restrict__ rows, int n_rows,
+__global__ void __launch_bounds__(128) tri_warp_kernel(xmap_sim_args a, const RowHdr *__restrict__ hdr, int n_rows,
                                                        int cells_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
@@ -398,44 +440,43 @@ __global__ void __launch_bounds__(128) tri_warp_kernel(xmap_sim_args a, const in
     Cell *T = reinterpret_cast<Cell *>(smem_raw) + (size_t)warp * cells_cap;
     unsigned short *occ = reinterpret_cast<unsigned short *>(smem_raw + (size_t)(blockDim.x >> 5) * cells_cap * sizeof(Cell)) +
                           (size_t)warp * cells_cap;
-    tri_row<false, unsigned short>(a, T, occ, nullptr, cells_cap, rows[r]);
+    tri_row<false, unsigned short>(a, T, occ, nullptr, cells_cap, hdr + r);
 }
 
 // one CTA per row, table in shared memory
-__global__ void __launch_bounds__(512) tri_cta_kernel(xmap_sim_args a, const int32_t *__restrict__ rows, int n_rows,
+__global__ void __launch_bounds__(512) tri_cta_kernel(xmap_sim_args a, const RowHdr *__restrict__ hdr, int n_rows,
                                                        int cells_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_cnt;
     tri_row<true, unsigned short>(a, reinterpret_cast<Cell *>(smem_raw),
                                   reinterpret_cast<unsigned short *>(smem_raw + (size_t)cells_cap * sizeof(Cell)),
-                                  &s_cnt, cells_cap, rows[blockIdx.x]);
+                                  &s_cnt, cells_cap, hdr + blockIdx.x);
 }
 
 // one CTA per segment of a split row (see SplitCtx)
-__global__ void __launch_bounds__(512) tri_split_kernel(xmap_sim_args a, const int32_t *__restrict__ seg_row,
-                                                         const int32_t *__restrict__ seg_lo, const int32_t *__restrict__ seg_hi,
+__global__ void __launch_bounds__(512) tri_split_kernel(xmap_sim_args a, const RowHdr *__restrict__ hdr,
                                                          const int32_t *__restrict__ seg_slot,
                                                          const int32_t *__restrict__ slot_nseg, int cells_cap,
                                                          uint4 *__restrict__ gtab, int *__restrict__ done) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_cnt;
     const int g = blockIdx.x, slot = seg_slot[g];
-    SplitCtx sp{gtab + (size_t)slot * cells_cap, done + slot, slot_nseg[slot], seg_lo[g], seg_hi[g]};
+    SplitCtx sp{gtab + (size_t)slot * cells_cap, done + slot, slot_nseg[slot]};
     tri_row<true, unsigned short>(a, reinterpret_cast<Cell *>(smem_raw),
                                   reinterpret_cast<unsigned short *>(smem_raw + (size_t)cells_cap * sizeof(Cell)),
-                                  &s_cnt, cells_cap, seg_row[g], &sp);
+                                  &s_cnt, cells_cap, hdr + g, &sp);
 }
 
 // persistent CTAs, tables in global memory (rows whose table exceeds shared memory):
 // per CTA cells_cap cells followed by cells_cap 32-bit slot indices
-__global__ void __launch_bounds__(512) tri_gmem_kernel(xmap_sim_args a, const int32_t *__restrict__ rows, int n_rows,
+__global__ void __launch_bounds__(512) tri_gmem_kernel(xmap_sim_args a, const RowHdr *__restrict__ hdr, int n_rows,
                                                         int cells_cap, unsigned char *__restrict__ gtab) {
     __shared__ int s_cnt;
     unsigned char *mine = gtab + (size_t)blockIdx.x * (((size_t)cells_cap * (sizeof(Cell) + 4) + 15) & ~(size_t)15);
     Cell *T = reinterpret_cast<Cell *>(mine);
     unsigned *occ = reinterpret_cast<unsigned *>(mine + (size_t)cells_cap * sizeof(Cell));
     for (int r = blockIdx.x; r < n_rows; r += gridDim.x) {
-        tri_row<true, unsigned>(a, T, occ, &s_cnt, cells_cap, rows[r]);
+        tri_row<true, unsigned>(a, T, occ, &s_cnt, cells_cap, hdr + r);
         __syncthreads();
     }
 }
@@ -896,9 +937,20 @@ extern "C" int64_t xmap_sim_row_cells(int64_t tri_work, int32_t n_more_popular) 
     return (long long)n_more_popular <= h ? (long long)n_more_popular : h;
 }
 
-extern "C" int xmap_sim_accumulate(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
+extern "C" int xmap_sim_row_headers(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_rows,
+                                    const int32_t *seg_lo, const int32_t *seg_hi, void *hdr_out, void *stream_) {
+    if (n_rows <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream_;
+    row_headers_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(*args_h, rows, n_rows, seg_lo, seg_hi,
+                                                             reinterpret_cast<RowHdr *>(hdr_out));
+    XMAP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xmap_sim_accumulate(const xmap_sim_args *args_h, const void *hdr_, int32_t n_rows,
                                    int32_t cells_cap, int32_t threads_per_row,
                                    void *gtab, int32_t gtab_ctas, void *stream_) {
+    const RowHdr *rows = reinterpret_cast<const RowHdr *>(hdr_);
     if (int rc = check_args(*args_h)) return rc;
     if (n_rows <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream_;
@@ -928,9 +980,9 @@ extern "C" int xmap_sim_accumulate(const xmap_sim_args *args_h, const int32_t *r
     return 0;
 }
 
-extern "C" int xmap_sim_accumulate_split(const xmap_sim_args *args_h, const int32_t *seg_row, const int32_t *seg_lo,
-                                         const int32_t *seg_hi, const int32_t *seg_slot, const int32_t *slot_nseg,
-                                         int32_t n_segs, int32_t cells_cap, void *gtab, int32_t *done, void *stream_) {
+extern "C" int xmap_sim_accumulate_split(const xmap_sim_args *args_h, const void *hdr_, const int32_t *seg_slot,
+                                         const int32_t *slot_nseg, int32_t n_segs, int32_t cells_cap, void *gtab,
+                                         int32_t *done, void *stream_) {
     if (int rc = check_args(*args_h)) return rc;
     if (n_segs <= 0) return 0;
     if (cells_cap < 1 || cells_cap > XMAP_SIM_MAX_SMEM_CELLS)
@@ -938,8 +990,8 @@ extern "C" int xmap_sim_accumulate_split(const xmap_sim_args *args_h, const int3
     cudaStream_t st = (cudaStream_t)stream_;
     const size_t smem = row_smem_bytes(cells_cap);
     XMAP_CUDA(cudaFuncSetAttribute(tri_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tri_split_kernel<<<n_segs, 512, smem, st>>>(*args_h, seg_row, seg_lo, seg_hi, seg_slot, slot_nseg, cells_cap,
-                                                reinterpret_cast<uint4 *>(gtab), done);
+    tri_split_kernel<<<n_segs, 512, smem, st>>>(*args_h, reinterpret_cast<const RowHdr *>(hdr_), seg_slot, slot_nseg,
+                                                cells_cap, reinterpret_cast<uint4 *>(gtab), done);
     XMAP_LAUNCH_CHECK();
     return 0;
 }

@@ -229,7 +229,7 @@ class SimEngine:
     def plan(self, rows=None):
         """Group the rows by table capacity and threads per row (cached per row set).
         Returns (launches, long_candidates, split): launches = [(rows sorted by descending work,
-        cells_cap, threads_per_row, in_global_memory)], long_candidates = rows whose record
+        cells_cap, threads_per_row, in_global_memory, row headers)], long_candidates = rows whose record
         list can exceed XMAP_SELECT_LONG, split = segment arrays of the rows whose rater list is
         cut over several CTAs (or None)."""
         key = None if rows is None else (int(rows[0]) if rows.numel() else -1, int(rows.numel()))
@@ -273,7 +273,7 @@ class SimEngine:
             seg_hi = torch.minimum(seg_lo + SPLIT_SEG, base + sr_c[slot])
             cap = max(32, int(cells[is_split].max().item()))
             i32 = lambda t: t.to(torch.int32).contiguous()
-            split = dict(seg_row=i32(srows[slot]), seg_lo=i32(seg_lo), seg_hi=i32(seg_hi), seg_slot=i32(slot),
+            split = dict(hdr=self._headers(i32(srows[slot]), i32(seg_lo), i32(seg_hi)), seg_slot=i32(slot),
                          slot_nseg=i32(nseg), n_segs=int(slot.numel()), cells_cap=cap, rows=srows,
                          gtab=torch.zeros((srows.numel() * cap, 2), dtype=torch.int64, device=dev),
                          done=torch.zeros(srows.numel(), dtype=torch.int32, device=dev))
@@ -292,14 +292,22 @@ class SimEngine:
             at += n
             q, th = c // 2048, c % 2048
             if q < len(classes):
-                launches.append((r, classes[q], th, False))
+                launches.append((r, classes[q], th, False, self._headers(r)))
             else:
-                launches.append((r, int(mx), 512, True))
+                launches.append((r, int(mx), 512, True, self._headers(r)))
         launches.sort(key=lambda t: (-t[2], -t[1]))                # big CTAs first
         long_cand = rows[self.rec_cap[rl] > N.SELECT_LONG].contiguous()
         out = (launches, long_cand, split)
         self._plans[key] = out
         return out
+
+    def _headers(self, rows, seg_lo=None, seg_hi=None):
+        """48-byte row headers of a launch (xmap_sim_row_headers)."""
+        n = int(rows.numel())
+        hdr = torch.empty(max(n, 1) * N.ROW_HDR_BYTES, dtype=torch.uint8, device=self.device)
+        N.check(N.lib().xmap_sim_row_headers(self._args(), N.ptr(rows), n, N.ptr(seg_lo), N.ptr(seg_hi), N.ptr(hdr),
+                                             _stream_ptr()), "xmap_sim_row_headers")
+        return hdr
 
     def enable_profile(self):
         """Record a CUDA event pair around every kernel group (read with profile_ms())."""
@@ -380,12 +388,11 @@ class SimEngine:
         if split is not None:
             sp = split
             self._timed("accumulate_split", lambda: N.check(L.xmap_sim_accumulate_split(
-                args, N.ptr(sp["seg_row"]), N.ptr(sp["seg_lo"]), N.ptr(sp["seg_hi"]), N.ptr(sp["seg_slot"]),
-                N.ptr(sp["slot_nseg"]), sp["n_segs"], sp["cells_cap"], N.ptr(sp["gtab"]), N.ptr(sp["done"]),
-                main.cuda_stream), "xmap_sim_accumulate_split"))
+                args, N.ptr(sp["hdr"]), N.ptr(sp["seg_slot"]), N.ptr(sp["slot_nseg"]), sp["n_segs"], sp["cells_cap"],
+                N.ptr(sp["gtab"]), N.ptr(sp["done"]), main.cuda_stream), "xmap_sim_accumulate_split"))
             self.launches += 1
             stats.append(("accumulate_split", int(sp["rows"].numel())))
-        for q, (r, cells_cap, threads, in_gmem) in enumerate(launches):
+        for q, (r, cells_cap, threads, in_gmem, hdr) in enumerate(launches):
             gtab, ctas = None, 0
             if in_gmem:
                 ctas = min(int(r.numel()), 296)
@@ -400,7 +407,7 @@ class SimEngine:
                 stream = self._side[q % n_streams - 1]
             st = stream.cuda_stream
             self._timed(kind, lambda: N.check(L.xmap_sim_accumulate(
-                args, N.ptr(r), r.numel(), cells_cap, threads, N.ptr(gtab), ctas, st), "xmap_sim_accumulate"))
+                args, N.ptr(hdr), r.numel(), cells_cap, threads, N.ptr(gtab), ctas, st), "xmap_sim_accumulate"))
             self.launches += 1
             stats.append((kind, int(r.numel())))
         if use_side:
