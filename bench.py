@@ -305,20 +305,23 @@ def main():
         out = eng2.tables_to_host(t)                 # pinned host buffers, synchronises
         return sum(o.numel() * o.element_size() for o in out.values())
     e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    n_e2e = max(2, min(args.steps, 3))
+    n_e2e = max(3, min(args.steps, 7))
+    e2e_times = []
     for _ in range(n_e2e):
+        barrier()
+        t0 = time.perf_counter()
         d2h_bytes = e2e_step()
-    barrier()
-    e2e_s = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+        barrier()
+        e2e_times.append(time.perf_counter() - t0)
+    # median of the per-step wall-clock times (the host is shared: a single descheduling would skew a mean)
+    e2e_s = torch.tensor([float(np.median(e2e_times))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_val = P_total / float(e2e_s)
 
     # pipeline wall-time: similarity + X-SIM extension (sharded by start) + generation (sharded by user)
     pipe = None
-    for timed in ((False, True) if not args.no_pipeline else ()):      # one untimed pass first, like the warm-up steps
+    for timed in ((False, True, True) if not args.no_pipeline else ()):  # one untimed pass, then the faster of two
         barrier()
         t0 = time.perf_counter()
         plan = X.build_plan(tabs, lay.item_stats[:, 3].contiguous(), meta.has_S, meta.has_T)
@@ -334,6 +337,9 @@ def main():
             dist.all_reduce(n_rec)
         barrier(); t3 = time.perf_counter()
         combos = int(res.combos.sum().item())
+        if not timed or (pipe is not None and pipe["alterego_pipeline_ms"] <= ms_step + (t3 - t0) * 1e3):
+            del plan, xe, res
+            continue
         pipe = {"similarity_ms": ms_step, "extend_plan_ms": (t1 - t0) * 1e3, "extend_kernel_ms": (t2 - t1) * 1e3,
                 "generate_ms": (t3 - t2) * 1e3,
                 "alterego_pipeline_ms": ms_step + (t3 - t0) * 1e3,
@@ -341,7 +347,8 @@ def main():
                 "xsim_starts": int(res.start_item.numel()), "xsim_pairs": int(res.count.sum().item()),
                 "alterego_synthetic_records": int(n_rec.item()), "bridge_pairs": plan.n_src,
                 "joint_pairs": plan.n_joint,
-                "sharding": "X-SIM by start item x%d, generation by user x%d (host wall-clock of rank 0 between barriers)" % (world, world)}
+                "sharding": "X-SIM by start item x%d, generation by user x%d (host wall-clock of rank 0 between barriers, "
+                            "faster of two passes after one untimed pass)" % (world, world)}
         del plan, xe, res
 
     if rank == 0:
@@ -390,7 +397,8 @@ def main():
                        "parallelism": "item row-blocks x%d, ratings replicated, neighbour records exchanged" % world},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "item pairs/s", "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": float(e2e_s) * 1e3},
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": float(e2e_s) * 1e3,
+                    "steps": n_e2e, "statistic": "median of per-step host wall-clock, max over ranks"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC.get(dom),
