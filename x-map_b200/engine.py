@@ -135,6 +135,23 @@ _PINNED = {}                                                # pinned host buffer
 REC_CNT_LIMIT = 1 << 20                                     # n and mutu are 20-bit fields of a record
 
 
+_REC_POOL = {}                                              # device -> record buffers of finished engines
+
+
+def _rec_buffer(n_records, device):
+    """Record-list storage [n, 2] int64.  The buffer is by far the largest allocation of the stage (12 GB
+    at cfg2); engines hand it back when they die and the next one takes it over, so a sequence of runs
+    does not depend on how the caching allocator happens to split and re-grow a block of that size."""
+    pool = _REC_POOL.setdefault(str(device), [])
+    fit = [t for t in pool if t.shape[0] >= max(n_records, 1)]
+    if fit:
+        t = min(fit, key=lambda x: x.shape[0])
+        pool.remove(t)
+        return t
+    pool.clear()                                          # too small for this problem: let the allocator have them
+    return torch.empty((max(n_records, 1), 2), dtype=torch.int64, device=device)
+
+
 def popularity_order(count):
     """ord[i] = rank of (count(i), i) ascending; the most popular item gets the largest ord."""
     I = int(count.numel())
@@ -190,9 +207,10 @@ class SimEngine:
         total = int(self.rec_ptr[-1].item()) if I else 0
         if rec_budget is None:
             free, _ = torch.cuda.mem_get_info(dev)
-            rec_budget = free // 2
+            pooled = max((t.numel() * 8 for t in _REC_POOL.get(str(dev), [])), default=0)
+            rec_budget = max(free // 2, pooled)
         self.exact_sizing = total * REC_BYTES > rec_budget
-        self.rec = None if self.exact_sizing else torch.empty((max(total, 1), 2), dtype=torch.int64, device=dev)
+        self.rec = None if self.exact_sizing else _rec_buffer(total, dev)
         self.rec_cnt = torch.zeros(I, dtype=torch.int32, device=dev)
         self.bb = torch.zeros(I, dtype=torch.uint8, device=dev)
         self.row_npairs = torch.zeros(I, dtype=torch.int32, device=dev)
@@ -206,6 +224,13 @@ class SimEngine:
         self._side = None
         self._plans = {}
         self.profile = None        # dict kind -> [(start_event, end_event)] when enabled
+
+    def __del__(self):
+        rec = getattr(self, "rec", None)
+        if rec is not None and rec.shape[0] > (1 << 20):
+            pool = _REC_POOL.setdefault(str(rec.device), [])
+            if len(pool) < 2:
+                pool.append(rec)
 
     # -- argument block ----------------------------------------------------
     def _args(self):
@@ -359,7 +384,7 @@ class SimEngine:
         self.rec_ptr[1:] = torch.cumsum(lengths, 0)
         self.rec_cap = lengths
         total = int(self.rec_ptr[-1].item()) if I else 0
-        self.rec = torch.empty((max(total, 1), 2), dtype=torch.int64, device=dev)
+        self.rec = _rec_buffer(total, dev)
         self._plans = {}
         self.reset()
 
