@@ -143,11 +143,9 @@ def _rec_buffer(n_records, device):
     at cfg2); engines hand it back when they die and the next one takes it over, so a sequence of runs
     does not depend on how the caching allocator happens to split and re-grow a block of that size."""
     pool = _REC_POOL.setdefault(str(device), [])
-    fit = [t for t in pool if t.shape[0] >= max(n_records, 1)]
+    fit = [q for q, t in enumerate(pool) if t.shape[0] >= max(n_records, 1)]
     if fit:
-        t = min(fit, key=lambda x: x.shape[0])
-        pool.remove(t)
-        return t
+        return pool.pop(min(fit, key=lambda q: pool[q].shape[0]))      # by position: `in` / remove would compare tensors
     pool.clear()                                          # too small for this problem: let the allocator have them
     return torch.empty((max(n_records, 1), 2), dtype=torch.int64, device=device)
 
