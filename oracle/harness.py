@@ -73,6 +73,7 @@ def load_reference():
             from xmap.core.generator import Generator
             from xmap.core.baselinerClean import BaselinerClean
             from xmap.core.baselinerSplit import BaselinerSplit
+            from xmap.core.recommenderSim import RecommenderSim
             from xmap.utils import assist
     finally:
         sys.path.remove(REFERENCE_CODE)
@@ -81,7 +82,7 @@ def load_reference():
     _ref = dict(pyspark=pyspark, sc=sc, sqlContext=SQLContext(sc),
                 BaselinerSim=BaselinerSim, ExtendSim=ExtendSim,
                 Generator=Generator, BaselinerClean=BaselinerClean,
-                BaselinerSplit=BaselinerSplit, assist=assist)
+                BaselinerSplit=BaselinerSplit, RecommenderSim=RecommenderSim, assist=assist)
     return _ref
 
 
@@ -156,3 +157,25 @@ def run_generate(trainRDD, xsimRDD, private, method="adjust_cosine",
     alter = gen.build_alterEgo(trainRDD, mapping).collect()
     dt = time.perf_counter() - t0
     return pairs, mapping, alter, dt
+
+
+def run_recommender_sim(alter_records, method="cosine_item", num_atleast=50):
+    """assist.py:153-175 (the next row of the scope table): item-item similarity and
+    per-pair local sensitivity on the AlterEgo profile, flat (uid, iid, rating, time) records in the
+    order given (the caller passes them sorted by (uid, iid, rating, time)).
+
+    Returns (sim records ((iid1, iid2), [sim, local sensitivity]) sorted by key,
+             item_info {iid: (average, norm2, count)}, seconds)."""
+    R = load_reference()
+    sc = R["sc"]
+    tool = R["RecommenderSim"](method, num_atleast)
+    profile = sc.parallelize(list(alter_records))
+    t0 = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                  # sqrt of a rounding-negative leave-one-out norm
+        out = R["assist"].recommender_calculate_sim_pipeline(sc, tool, profile)
+        sims = out[6].collect()
+    dt = time.perf_counter() - t0
+    item_info = dict(out[5].value)
+    sims = sorted(((k, [float(v[0]), float(v[1])]) for k, v in sims), key=lambda x: x[0])
+    return sims, item_info, dt

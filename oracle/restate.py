@@ -324,3 +324,74 @@ def build_alterego(user, item, rating, ts, mapping, has_T):
                 ts=np.concatenate([ts[keep_t], ts2[first]]),
                 synthetic=np.concatenate([np.zeros(int(keep_t.sum()), bool),
                                           np.ones(len(uk), bool)]))
+
+
+# --------------------------------------------------------------------------
+# Next row of the scope table: RecommenderSim on the AlterEgo profile
+# (recommenderSim.py:29-62 get_info, :64-75 produce_pairwise, :90-132 cosine_sim + local
+# sensitivity, :186-195 calculate_sim with method "cosine_item").  No product kernel consumes
+# this yet; it pins the semantics (duplicate (user, item) records, self pairs, no filter).
+# --------------------------------------------------------------------------
+def recommender_cosine_item(user, item, rating, n_items, num_atleast=50):
+    """Flat profile records (user, item, rating), in the order the reference receives them
+    (sorted by user; a (user, item) pair may occur twice: a real target rating next to a
+    synthetic one, generator.py:156-157).  Returns every directed item pair with at least one
+    co-rating entry, sorted by (i, j): dict(i, j, n, sim, ls, norm2)."""
+    user = np.asarray(user, dtype=np.int64)
+    item = np.asarray(item, dtype=np.int64)
+    r = np.asarray(rating, dtype=np.float64)
+    norm2 = np.sqrt(np.bincount(item, weights=r * r, minlength=n_items))          # :41-49 over ALL records of the item
+    # co-rating entries: both orders of every 2-combination of a user's records (:64-75)
+    order = np.argsort(user, kind="stable")
+    us, it, rr = user[order], item[order], r[order]
+    starts = np.flatnonzero(np.r_[True, us[1:] != us[:-1]])
+    ends = np.r_[starts[1:], len(us)]
+    ki, kj, ra, rb = [], [], [], []
+    for a, b in zip(starts, ends):
+        d = b - a
+        if d < 2:
+            continue
+        p, q = np.triu_indices(d, 1)
+        # combinations() order: (p, q) then its reverse, interleaved
+        ki.append(np.stack([it[a + p], it[a + q]], 1).ravel()); kj.append(np.stack([it[a + q], it[a + p]], 1).ravel())
+        ra.append(np.stack([rr[a + p], rr[a + q]], 1).ravel()); rb.append(np.stack([rr[a + q], rr[a + p]], 1).ravel())
+    if not ki:
+        z = np.zeros(0)
+        return dict(i=z.astype(np.int64), j=z.astype(np.int64), n=z.astype(np.int64), sim=z, ls=z, norm2=norm2)
+    ki, kj, ra, rb = (np.concatenate(x) for x in (ki, kj, ra, rb))
+    key = ki * n_items + kj
+    o = np.argsort(key, kind="stable")                      # entries of a pair stay in arrival (user) order
+    key, ki, kj, ra, rb = key[o], ki[o], kj[o], ra[o], rb[o]
+    first = np.flatnonzero(np.r_[True, key[1:] != key[:-1]])
+    n = np.diff(np.r_[first, len(key)])
+    seg = np.repeat(np.arange(len(first)), n)
+    prod = ra * rb
+    inner = np.add.reduceat(prod, first)                    # :118
+    pi, pj = ki[first], kj[first]
+    nx, ny = norm2[pi], norm2[pj]
+    N = float(num_atleast)
+
+    def cosine(dot, nn):                                    # :84-88 (a NaN norm product is truthy)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return np.where(nn != 0, 1.0 * dot / nn, 0.0)
+
+    sim = 1.0 * cosine(inner, nx * ny) * np.minimum(n, num_atleast) / N            # :77-82, :121-122
+    # local sensitivity (:98-116): two leave-one-out similarities per co-rating entry
+    m_inner = inner[seg] - prod
+    with np.errstate(invalid="ignore"):
+        m1 = np.sqrt((nx[seg] ** 2 - ra ** 2) * (ny[seg] ** 2))
+        m2 = np.sqrt((nx[seg] ** 2) * (ny[seg] ** 2 - rb ** 2))
+    w = np.minimum(n[seg] - 1, num_atleast)
+    v1 = 1.0 * cosine(m_inner, m1) * w / N
+    v2 = 1.0 * cosine(m_inner, m2) * w / N
+    dev = np.abs(np.stack([v1, v2], 1) - sim[seg][:, None]).ravel()                # result order: v1, v2 per entry
+    first2, seg2 = 2 * first, np.repeat(np.arange(len(first)), 2 * n)
+    ls = np.fmax.reduceat(dev, first2)                       # NaN-free pairs
+    for g in np.unique(seg2[np.isnan(dev)]):                 # Python's max(): a NaN only wins if it comes first
+        vals = dev[first2[g]:first2[g] + 2 * n[g]]
+        res = vals[0]
+        for x in vals[1:]:
+            if x > res:
+                res = x
+        ls[g] = res
+    return dict(i=pi, j=pj, n=n, sim=sim, ls=ls, norm2=norm2)

@@ -70,3 +70,20 @@ def test_harness_runs_the_reference_and_agrees_with_golden():
             "assert all(np.array_equal(o[k],g[k]) for k in g.files if k!='ref_seconds');print('ok')")
     r = subprocess.run([sys.executable, "-c", code], cwd=PT.ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name", PT.GOLDEN_CASES)
+def test_restatement_recommender_sim_vs_reference(name):
+    """Next row of the scope table: RecommenderSim `cosine_item` + local sensitivity on the
+    AlterEgo profile -- the restatement against what the unmodified reference produced
+    (oracle/make_golden_recsim.py).  Pins duplicate (user, item) records, self pairs and the absence of a filter."""
+    g = PT.load_golden(name + "_recsim")
+    nI = int(max(g["ae_item"].max(), g["rs_i"].max(), g["rs_j"].max())) + 1
+    P = RS.recommender_cosine_item(g["ae_user"], g["ae_item"], g["ae_rating"], nI, int(g["num_atleast"]))
+    assert np.array_equal(P["i"], g["rs_i"]) and np.array_equal(P["j"], g["rs_j"])
+    assert int((P["i"] == P["j"]).sum()) > 0                       # a real next to a synthetic rating of one item
+    np.testing.assert_allclose(P["sim"], g["rs_sim"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(P["ls"], g["rs_ls"], rtol=1e-9, atol=1e-13, equal_nan=True)
+    np.testing.assert_allclose(P["norm2"][g["info_item"]], g["info_norm2"], rtol=1e-14)
+    cnt = np.bincount(g["ae_item"], minlength=nI)
+    assert np.array_equal(cnt[g["info_item"]], g["info_count"])
