@@ -52,3 +52,22 @@ def test_no_cpu_fallback_without_gpu():
     from xmap_b200 import engine as E
     with pytest.raises(Exception):
         E.build_layout(np.zeros(1, np.int32), np.zeros(1, np.int32), np.ones(1), 1, 1)
+
+
+def test_engine_host_helpers():
+    """Device-agnostic helpers of the engine: popularity rank, fixed-point head-room, threads per table,
+    and the hand-over pool of record buffers."""
+    import torch
+    from xmap_b200 import engine as E
+    cnt = torch.tensor([3., 1., 3., 7., 1.], dtype=torch.float64)
+    assert E.popularity_order(cnt).tolist() == [2, 0, 3, 4, 1]          # ascending count, ties by index
+    assert E.r2_bits_for("adjust_cosine", 1.0, 5.0) == 5 and E.r2_bits_for("cosine", 0.5, 5.0) == 6
+    assert E.r2_bits_for("cosine", 0.0, 0.0) == 0
+    assert [E._threads_for_cells(c) for c in (32, 256, 512, 1024, 1536, 4096, 12288)] == [32, 32, 64, 128, 192, 512, 512]
+    E._REC_POOL.pop("cpu", None)
+    a = torch.empty((100, 2), dtype=torch.int64); b = torch.empty((1000, 2), dtype=torch.int64)
+    E._REC_POOL["cpu"] = [b, a]
+    assert E._rec_buffer(50, "cpu") is a and E._rec_buffer(500, "cpu") is b and E._REC_POOL["cpu"] == []
+    E._REC_POOL["cpu"] = [a]
+    t = E._rec_buffer(5000, "cpu")
+    assert tuple(t.shape) == (5000, 2) and E._REC_POOL["cpu"] == []     # too small: dropped, a fresh one allocated
