@@ -235,7 +235,7 @@ def main():
     from xmap_b200 import extend as X
     from xmap_b200 import generate as G
     from xmap_b200 import multi as MG
-    from tests.parity import to_device_meta
+    from xmap_b200.engine import to_device_meta
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -302,7 +302,7 @@ def main():
         lay2 = E.build_layout(h_user, h_item, h_rating, wl["n_users"], wl["n_items"], device=dev)
         eng2 = E.SimEngine(lay2, meta, args.method, 50, k)
         t = MG.similarity_step(eng2, MG.similarity_shard(eng2, rank, world))
-        out = eng2.tables_to_host(t)                 # pinned host buffers, synchronises
+        out = eng2.tables_to_host(t, reuse=True)                 # pinned host buffers, synchronises
         return sum(o.numel() * o.element_size() for o in out.values())
     e2e_step()
     n_e2e = max(3, min(args.steps, 7))
@@ -327,7 +327,7 @@ def main():
         plan = X.build_plan(tabs, lay.item_stats[:, 3].contiguous(), meta.has_S, meta.has_T)
         torch.cuda.synchronize(); t1 = time.perf_counter()
         xe = X.XsimEngine(plan, 10)
-        res = MG.allreduce_xsim(xe.run(rank, world))
+        res = xe.run(rank, world)
         barrier(); t2 = time.perf_counter()
         ch = G.choose_mapping(res, "argmax", sim_method=args.method)
         mp = G.invert_mapping(res.start_item, ch, wl["n_items"])

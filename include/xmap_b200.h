@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define XMAP_B200_ABI_VERSION 2
+#define XMAP_B200_ABI_VERSION 3
 #define XMAP_KMAX 64                 /* largest supported top-k (extend_among_topk) */
 #define XMAP_METHOD_ADJUST_COSINE 0  /* baselinerSim.py:144-174 */
 #define XMAP_METHOD_COSINE 1         /* baselinerSim.py:115-142 */
@@ -199,54 +199,66 @@ int xmap_segmented_copy16(const void *src, const int64_t *src_pos, void *dst, co
                           const int64_t *seg_off, int32_t n_seg, int64_t total, void *stream);
 
 /* ---------------------------------------------------------------------------
- * (3) X-SIM extension: masked path composition with fused aggregation.
+ * (3) X-SIM extension: masked path composition with fused aggregation and top-m.
  * Replaces: ExtendSim.sim_extend + get_final_extension (extender.py:46-217).
  * The facade turns the top-k tables into three index structures (all CSR-like):
  *   legs      per start item x: the left segments x -> t   (extender.py:160-168)
  *   partners  per bridge target t: the bridge pairs (t, s) (extender.py:61-81,178)
  *   rsegs     per bridge source s: the right segments s -> y (extender.py:134-138)
- * and this kernel evaluates every (leg, partner, rseg) combination = one
+ * and this entry point evaluates every (leg, partner, rseg) combination = one
  * reference path: s_p = sum(sim*mutu)/sum(mutu), c_p = prod(frac)
  * (extender.py:83-89), accumulating xsim[x,y] = sum(s_p c_p)/sum(c_p)
- * (extender.py:198-201) in a per-start hash table, never materialising paths.
- * One warp owns one start item (or one slice of the legs of a heavy start; slices are merged
- * by a fixed binary tree), so the summation order of every cell is fixed by structure.
+ * (extender.py:198-201) in a SHARED-MEMORY hash table, never materialising paths and never touching a
+ * global accumulator cell.
+ *
+ * Work unit = one CTA = (start, a run of passes).  The end axis is hashed, pi(y) = (uint32)(y * 0x9E3779B1),
+ * and cut into 2^gb tiles by the top gb bits of pi; a pass covers a range of tiles chosen so that its
+ * distinct ends fit the table of 2^cells_lg cells.  Every rseg list is stored sorted by pi and
+ * tile_ptr[s * (2^gb + 1) + g] = number of entries of list s in tiles < g gives the sub-range of a pass
+ * without a search.  A pass that overflows its table is split in two on the device and redone, down to
+ * one tile (then error 2).  Inside a pass the paths are produced by all
+ * warps and routed through shared memory to the warp that owns the end's table region, which applies
+ * them one by one in path order (leg, partner, rseg): no atomics, and the summation order of every
+ * (start, end) is a function of the path structure only, hence bit-identical for any pass split,
+ * table size or number of GPUs.
  * ------------------------------------------------------------------------- */
+#define XMAP_XSIM_MAX_CELLS_LG 13             /* 8192 cells x 20 B + 46 KB of staging = 209 KB of shared memory */
 typedef struct xmap_xsim_args {
-    int32_t n_starts;                         /* start items in this launch */
-    int32_t n_units;                          /* work units: one per start, several (leg slices) per heavy start */
-    const int32_t *start_item;                /* [n_starts] */
-    const int32_t *start_unit;                /* [n_starts] unit whose table holds the start's merged cells */
-    const int64_t *unit_leg_lo, *unit_leg_hi; /* [n_units] leg range of the unit */
-    int64_t *unit_combos;                     /* [n_units] paths evaluated by the unit */
-    const int32_t *leg_t;                     /* index into partner lists */
-    const uint8_t *leg_joint_only;            /* 1: use only joint partners */
-    const double *leg_e1, *leg_m1, *leg_f1, *leg_e2, *leg_m2, *leg_f2;
-    const int64_t *par_ptr;                   /* [n_t+1] */
+    int32_t n_starts;                         /* start items covered by the units */
+    int32_t n_units;                          /* CTAs of this launch */
+    const int32_t *unit_order;                /* [n_units] CTA b runs unit unit_order[b] (NULL: b); ids index the unit arrays */
+    const int64_t *unit_leg_lo, *unit_leg_hi; /* leg range of the unit's start */
+    const int32_t *unit_g0, *unit_g1;         /* the unit's range of hash tiles, 0 <= g0 < g1 <= 2^gb ... */
+    const int32_t *unit_npass;                /* ... which it covers in npass equal passes (<= g1 - g0) */
+    const int32_t *start_unit_ptr;            /* [n_starts + 1] unit id range of every start (merge) */
+    /* legs: left segment folded to (N, D, C); partners [par_base, par_base + npar); lp_ptr = exclusive
+     * scan of npar over ALL legs (lp_ptr[n_legs] = number of (leg, partner) pairs) */
+    const int64_t *lp_ptr; const int64_t *leg_par_base; const int32_t *leg_npar;
+    const double *leg_n, *leg_d, *leg_c;
     const int32_t *par_s;                     /* index into rseg lists */
-    const uint8_t *par_joint;
-    const double *par_e, *par_m, *par_f;
-    const int64_t *rs_ptr;                    /* [n_s+1] */
-    const int32_t *rs_end;
-    const double *rs_n, *rs_d, *rs_c;         /* per right segment: sum sim*mutu, sum mutu, prod frac of its edges */
-    /* per-unit hash region: [hash_off[u], hash_off[u]+hash_size[u]) 32-byte cells {u64 key, f64 num,
-     * f64 den}, size >= 32.  key = epoch << 32 | (end + 1): cells of another epoch are
-     * empty, so the workspace is zeroed once when allocated and every launch passes a fresh epoch >= 1. */
-    const int64_t *hash_off; const int32_t *hash_size;
-    void *hash_cells;
-    uint32_t epoch;
-    /* merge tree of the heavy starts: round r merges pairs [round_ptr_h[r], round_ptr_h[r+1]) */
-    int32_t n_rounds; const int32_t *round_ptr_h;   /* HOST array, n_rounds + 1 entries */
-    const int32_t *pair_dst, *pair_src;       /* unit indices; dst's table is sized for the union */
+    const double *par_e, *par_m, *par_f;      /* the bridge edge: sim*mutu, mutu, frac */
+    const int64_t *rs_ptr;                    /* [n_s + 1] */
+    const int32_t *rs_end;                    /* per right segment: end item, sorted by pi within a list */
+    const double *rs_n, *rs_d, *rs_c;         /* sum sim*mutu, sum mutu, prod frac of its edges */
+    const int32_t *tile_ptr; int32_t gb;
+    int32_t cells_lg;                         /* log2 of the table size, 9 .. XMAP_XSIM_MAX_CELLS_LG */
     int32_t top_m;                            /* <= XMAP_KMAX */
-    int32_t mode;                             /* 0: count + top-m, 2: emit all */
-    int32_t *out_count;                       /* [n_starts] #distinct ends */
+    int32_t merge;                            /* 1: also run the per-start merge of the unit results */
+    /* per unit: distinct ends, paths, top-m by |xsim| (ties to the smaller end) */
+    int32_t *unit_count; int64_t *unit_combos;
+    int32_t *unit_top_end; double *unit_top_xsim; int32_t *unit_top_len;
+    /* per start (merge) */
+    int32_t *out_count; int64_t *out_combos;
     int32_t *top_end; double *top_xsim; int32_t *top_len;   /* [n_starts][top_m] */
+    /* optional: every (end, xsim) of unit u written at emit_ptr[u] + 0 .. unit_count[u]-1 (order unspecified) */
     const int64_t *emit_ptr; int32_t *emit_end; double *emit_xsim;
-    int32_t *error_flag;
+    int32_t *error_flag;                      /* 2: a pass overflowed at the finest split */
 } xmap_xsim_args;
 
+int64_t xmap_xsim_smem_bytes(int32_t cells_lg);
 int xmap_xsim_extend(const xmap_xsim_args *args_h, void *stream);
+/* only the per-start merge (multi-GPU: after the unit results of all ranks have been summed) */
+int xmap_xsim_merge(const xmap_xsim_args *args_h, void *stream);
 
 /* ---------------------------------------------------------------------------
  * (4) AlterEgo generation.

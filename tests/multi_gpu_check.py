@@ -37,7 +37,7 @@ def main():
     cnt = lay.item_stats[:, 3].contiguous()
     plan = X.build_plan(ref, cnt, meta.has_S, meta.has_T)
     res1 = X.XsimEngine(plan, 10).run()
-    resN = MG.allreduce_xsim(X.XsimEngine(X.build_plan(tabs, cnt, meta.has_S, meta.has_T), 10).run(rank, world))
+    resN = X.XsimEngine(X.build_plan(tabs, cnt, meta.has_S, meta.has_T), 10).run(rank, world)
     ok = ok and all(torch.equal(getattr(res1, f), getattr(resN, f)) for f in
                     ("count", "combos", "top_end", "top_xsim", "top_len"))
     mp1 = G.invert_mapping(res1.start_item, G.choose_mapping(res1, "argmax"), case["n_items"])

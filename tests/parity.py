@@ -29,14 +29,8 @@ def golden_meta(g):
 
 
 def to_device_meta(meta, device="cuda"):
-    import torch
-    from xmap_b200.engine import ItemMeta
-    return ItemMeta(
-        prefix_code=torch.as_tensor(meta["prefix_code"], dtype=torch.int32, device=device),
-        dom_code=torch.as_tensor(meta["dom_code"], dtype=torch.uint8, device=device),
-        contains=torch.as_tensor(meta["contains"], dtype=torch.uint8, device=device),
-        has_S=torch.as_tensor(meta["has_S"], dtype=torch.bool, device=device),
-        has_T=torch.as_tensor(meta["has_T"], dtype=torch.bool, device=device))
+    from xmap_b200.engine import to_device_meta as f
+    return f(meta, device)
 
 
 def _case_from_ratings(sr, keep=None, half=False):
@@ -329,15 +323,12 @@ def compare_xsim(start, end, val, ref_start, ref_end, ref_val, rtol=SIM_RTOL):
     return float(rel.max()) if rel.size else 0.0
 
 
-def run_gpu_extend(tabs, lay, meta, top_m=10, hash_budget=None, unit_combos=None):
+def run_gpu_extend(tabs, lay, meta, top_m=10, **engine_kw):
     import torch
     from xmap_b200 import extend as X
     dm = to_device_meta(meta)
     plan = X.build_plan(tabs, lay.item_stats[:, 3].contiguous(), dm.has_S, dm.has_T)
-    kw = {} if hash_budget is None else dict(hash_budget=hash_budget)
-    if unit_combos is not None:
-        kw["unit_combos"] = unit_combos
-    xe = X.XsimEngine(plan, top_m, **kw)
+    xe = X.XsimEngine(plan, top_m, **engine_kw)
     res = xe.run()
     s, e, v = xe.emit(res)
     torch.cuda.synchronize()

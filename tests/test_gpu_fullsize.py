@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 def test_cfg2_properties():
     import torch
     import bench
-    from tests.parity import to_device_meta
+    from xmap_b200.engine import to_device_meta
     from xmap_b200 import engine as E, extend as X
     wl = bench.make_workload("cfg2")
     dev = torch.device("cuda")

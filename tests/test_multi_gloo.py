@@ -99,19 +99,17 @@ def test_record_exchange_world2():
 def _xsim_worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from xmap_b200.multi import allreduce_xsim
-    from xmap_b200.extend import XsimResult
+    from xmap_b200.multi import sum_unit_results
     n, m = 37, 4
     g = torch.Generator().manual_seed(9)
-    full = XsimResult(torch.arange(n, dtype=torch.int32), torch.randint(1, 50, (n,), generator=g, dtype=torch.int32),
-                      torch.randint(1, 500, (n,), generator=g), torch.randint(-1, 90, (n, m), generator=g, dtype=torch.int32),
-                      torch.randn(n, m, generator=g, dtype=torch.float64), torch.randint(0, m + 1, (n,), generator=g, dtype=torch.int32), 0)
-    mine = torch.zeros(n, dtype=torch.bool); mine[rank::world] = True
-    part = XsimResult(full.start_item, torch.where(mine, full.count, 0), torch.where(mine, full.combos, 0),
-                      torch.where(mine[:, None], full.top_end, -1), torch.where(mine[:, None], full.top_xsim, 0.0),
-                      torch.where(mine, full.top_len, 0), 0)
-    out = allreduce_xsim(part)
-    ok = all(torch.equal(getattr(out, f), getattr(full, f)) for f in ("count", "combos", "top_end", "top_xsim", "top_len"))
+    full = (torch.randint(1, 50, (n,), generator=g, dtype=torch.int32), torch.randint(1, 500, (n,), generator=g),
+            torch.randint(0, 90, (n, m), generator=g, dtype=torch.int32),
+            torch.randn(n, m, generator=g, dtype=torch.float64), torch.randint(0, m + 1, (n,), generator=g, dtype=torch.int32))
+    order = torch.randperm(n, generator=g)                   # the descending-work order of the units
+    mine = torch.zeros(n, dtype=torch.bool); mine[order[rank::world]] = True
+    part = tuple(torch.where(mine.view((n,) + (1,) * (t.dim() - 1)), t, torch.zeros_like(t)) for t in full)
+    out = sum_unit_results(part)
+    ok = all(torch.equal(a, b) for a, b in zip(out, full))
     q.put((rank, ok))
     dist.destroy_process_group()
 

@@ -3,7 +3,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bench
 from xmap_b200 import engine as E
-from tests.parity import to_device_meta
+from xmap_b200.engine import to_device_meta
 wl = bench.make_workload("cfg2")
 dev = torch.device("cuda"); meta = to_device_meta(wl["meta"], dev)
 pin = lambda a: torch.from_numpy(a).pin_memory()
@@ -18,6 +18,6 @@ for rep in range(3):
     eng = T("engine_init(tri layout, lists)", lambda: E.SimEngine(lay, meta, "adjust_cosine", 50, wl["k"]), acc)
     T("plan", lambda: eng.plan(), acc)
     tabs = T("stage", lambda: eng.run(), acc)
-    out = T("d2h pinned", lambda: eng.tables_to_host(tabs), acc)
+    out = T("d2h pinned", lambda: eng.tables_to_host(tabs, reuse=True), acc)
     print(rep, {k: round(v, 1) for k, v in acc.items()}, "total %.1f" % sum(acc.values()), flush=True)
     del lay, eng, tabs, out

@@ -2,7 +2,7 @@ import sys, time; sys.path.insert(0, __import__("os").path.dirname(__import__("o
 import numpy as np, torch
 import bench
 from xmap_b200 import engine as E, extend as X
-from tests.parity import to_device_meta
+from xmap_b200.engine import to_device_meta
 wl = bench.make_workload("cfg2")
 dev = torch.device("cuda"); meta = to_device_meta(wl["meta"], dev)
 lay = E.build_layout(wl["user"], wl["item"], wl["rating"], wl["n_users"], wl["n_items"], device=dev)

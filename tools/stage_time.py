@@ -2,7 +2,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bench
 from xmap_b200 import engine as E
-from tests.parity import to_device_meta
+from xmap_b200.engine import to_device_meta
 from xmap_b200 import _native as _N
 print("lib", _N.LIB_PATH, flush=True)
 wl = bench.make_workload("cfg2")

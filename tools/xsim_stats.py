@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 from xmap_b200 import engine as E, extend as X
-from tests.parity import to_device_meta
+from xmap_b200.engine import to_device_meta
 wl = bench.make_workload(sys.argv[1] if len(sys.argv) > 1 else "cfg2")
 dev = torch.device("cuda"); meta = to_device_meta(wl["meta"], dev)
 lay = E.build_layout(wl["user"], wl["item"], wl["rating"], wl["n_users"], wl["n_items"], device=dev)

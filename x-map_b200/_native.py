@@ -11,9 +11,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("XMAP_B200_LIB") or os.path.join(_HERE, "libxmap_b200.so")
 
 KMAX = 64
+XSIM_MAX_CELLS_LG = 13    # XMAP_XSIM_MAX_CELLS_LG
 METHODS = {"adjust_cosine": 0, "cosine": 1}
 SELECT_LONG = 8192            # XMAP_SELECT_LONG
-ABI_VERSION = 2
+ABI_VERSION = 3
 ROW_HDR_BYTES = 48          # XMAP_SIM_ROW_HDR_BYTES
 
 _p = C.c_void_p
@@ -35,17 +36,15 @@ class SimArgs(C.Structure):
 class XsimArgs(C.Structure):
     _fields_ = [
         ("n_starts", C.c_int32), ("n_units", C.c_int32),
-        ("start_item", _p), ("start_unit", _p), ("unit_leg_lo", _p), ("unit_leg_hi", _p), ("unit_combos", _p),
-        ("leg_t", _p), ("leg_joint_only", _p),
-        ("leg_e1", _p), ("leg_m1", _p), ("leg_f1", _p), ("leg_e2", _p), ("leg_m2", _p), ("leg_f2", _p),
-        ("par_ptr", _p), ("par_s", _p), ("par_joint", _p), ("par_e", _p), ("par_m", _p), ("par_f", _p),
-        ("rs_ptr", _p), ("rs_end", _p),
-        ("rs_n", _p), ("rs_d", _p), ("rs_c", _p),
-        ("hash_off", _p), ("hash_size", _p), ("hash_cells", _p), ("epoch", C.c_uint32),
-        ("n_rounds", C.c_int32), ("round_ptr_h", _p), ("pair_dst", _p), ("pair_src", _p),
-        ("top_m", C.c_int32), ("mode", C.c_int32),
-        ("out_count", _p),
-        ("top_end", _p), ("top_xsim", _p), ("top_len", _p),
+        ("unit_order", _p), ("unit_leg_lo", _p), ("unit_leg_hi", _p),
+        ("unit_g0", _p), ("unit_g1", _p), ("unit_npass", _p), ("start_unit_ptr", _p),
+        ("lp_ptr", _p), ("leg_par_base", _p), ("leg_npar", _p), ("leg_n", _p), ("leg_d", _p), ("leg_c", _p),
+        ("par_s", _p), ("par_e", _p), ("par_m", _p), ("par_f", _p),
+        ("rs_ptr", _p), ("rs_end", _p), ("rs_n", _p), ("rs_d", _p), ("rs_c", _p),
+        ("tile_ptr", _p), ("gb", C.c_int32),
+        ("cells_lg", C.c_int32), ("top_m", C.c_int32), ("merge", C.c_int32),
+        ("unit_count", _p), ("unit_combos", _p), ("unit_top_end", _p), ("unit_top_xsim", _p), ("unit_top_len", _p),
+        ("out_count", _p), ("out_combos", _p), ("top_end", _p), ("top_xsim", _p), ("top_len", _p),
         ("emit_ptr", _p), ("emit_end", _p), ("emit_xsim", _p),
         ("error_flag", _p),
     ]
@@ -67,7 +66,9 @@ _SIGS = {
     "xmap_sim_accumulate_split": (C.c_int, [C.POINTER(SimArgs), _p, _p, _p, C.c_int32, C.c_int32, _p, _p, _p]),
     "xmap_sim_select": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, C.c_int32, _p]),
     "xmap_segmented_copy16": (C.c_int, [_p, _p, _p, _p, _p, C.c_int32, C.c_int64, _p]),
+    "xmap_xsim_smem_bytes": (C.c_int64, [C.c_int32]),
     "xmap_xsim_extend": (C.c_int, [C.POINTER(XsimArgs), _p]),
+    "xmap_xsim_merge": (C.c_int, [C.POINTER(XsimArgs), _p]),
     "xmap_choose_mapping": (C.c_int, [_p, _p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_double, C.c_int32, C.c_int32, _p, C.c_uint64, _p, _p]),
     "xmap_invert_mapping": (C.c_int, [_p, _p, C.c_int32, _p, _p]),

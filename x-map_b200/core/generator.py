@@ -5,6 +5,8 @@ behaves under Python 3 (weighted_pick returns index 0 for a `map` object,
 generator.py:66-67), 'exp_mech' is the exponential mechanism the code intends
 (generator.py:42-75, tech report Thm 1).  Draws come from Philox(seed, row) unless
 `uniforms` (one per X-SIM row, ascending target index) are injected."""
+import os
+
 import numpy as np
 import torch
 
@@ -16,13 +18,18 @@ from ..session import session_of
 
 class Generator(object):
     def __init__(self, mapping_range, privacy_epsilon, sim_method, rpo,
-                 private_mode="argmax", seed=0, uniforms=None):
+                 private_mode="argmax", seed=None, uniforms=None):
         self.mapping_range = mapping_range
         self.privacy_epsilon = privacy_epsilon
         self.sim_method = sim_method
         self.rpo = rpo
         self.private_mode = private_mode
-        self.seed = seed
+        # seed=None (default): fresh entropy per tool, and every mapping call advances the Philox key, so
+        # repeated releases are independent like the reference's unseeded np.random (generator.py:60-70);
+        # an explicit seed keeps the draws reproducible (tests)
+        self._fresh = seed is None
+        self.seed = int.from_bytes(os.urandom(8), "little") if seed is None else seed
+        self._calls = 0
         self.uniforms = uniforms
         self.single_candidate_rows = 0     # rows where the reference would raise (generator.py:110)
 
@@ -38,8 +45,12 @@ class Generator(object):
 
     def _map(self, rdd, session, mode):
         xres = self._xres(rdd, session)
+        seed = self.seed
+        if self._fresh:
+            seed = (self.seed + 0x9E3779B97F4A7C15 * self._calls) & (2 ** 64 - 1)
+            self._calls += 1
         ch = G.choose_mapping(xres, mode, self.privacy_epsilon, self.mapping_range, self.sim_method,
-                              self.uniforms, self.seed)
+                              self.uniforms, seed)
         if mode == "nonprivate":
             self.single_candidate_rows = int((xres.top_len == 1).sum().item())
         return xres, ch

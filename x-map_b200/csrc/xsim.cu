@@ -2,162 +2,43 @@
 // combination is one path of the reference's enumeration (extender.py:124-169);
 // its similarity s_p = sum(sim*mutu)/sum(mutu) and certainty c_p = prod(frac)
 // (extender.py:83-89) are accumulated per (start, end) into
-// xsim = sum(s_p c_p) / sum(c_p) (extender.py:198-201) without ever storing a
-// path.  One warp owns one start item and walks its legs and partners in a
-// fixed order, so a cell's sum depends only on the path structure (identical
-// items get bit-identical X-SIM values, which keeps top-k ties deterministic).
+// xsim = sum(s_p c_p) / sum(c_p) (extender.py:198-201) without ever storing a path.
 //
-// Bound by accumulator traffic: each combo reads 3 doubles + 1 int of the
-// right-segment table (coalesced across the warp, L2-resident because a bridge
-// source is shared by many starts) and does one hash-cell read-modify-write.
+// Design: the accumulator of a start never leaves the SM.  One CTA owns one unit = (start item, one or
+// more passes); a pass covers a range of the hashed end axis pi(y) = y * 0x9E3779B1 (every right-segment
+// list is stored sorted by pi, and a per-source pointer table gives the sub-range of a pass without a
+// search), chosen so that the distinct ends of the pass fit a shared-memory hash table.  Inside a pass:
+//
+//   prep      512 (leg, partner) pairs at a time: each thread resolves one pair to a descriptor
+//             {right-segment sub-range, folded (N, D, C) of leg + bridge edge}; a block scan numbers
+//             the products of the macro-batch and compacts the non-empty descriptors;
+//   produce   the products are dealt to the 16 warps in chunks of 32 (chunk c -> warp c mod 16): a lane
+//             finds its descriptor, loads one 28-byte right segment, evaluates the path and leaves
+//             (end, s_p c_p, c_p) in its payload slot; per (owner, producer) lane masks say which slots
+//             belong to which owner warp (owner = 4 bits of pi(end));
+//   consume   warp o walks the slots addressed to it in (producer, lane) order = canonical path order,
+//             combines lanes that hit the same end sequentially in that order, and updates its private
+//             512-cell region of the table with plain loads and stores: no atomics, and the summation
+//             order of every cell is the path order (leg, partner, right segment), a function of the
+//             structure only -- results are bit-identical for any pass split, table size or GPU count.
+//
+// A pass whose table overflows is split in two on the device (the hash range halves) and redone; the top-m
+// of a unit is kept in shared memory across its passes and a small kernel merges the units of a start.
+//
+// Bound: issue rate of the produce/consume instruction stream (~6 warp-instructions per path) and the
+// 28 B right-segment read per path from L2/HBM; accumulator traffic is shared memory only.
 #include "common.cuh"
 
 namespace xmap {
 
-constexpr int XS_THREADS = 256;
-
-// 32-byte accumulator cell, aligned to a DRAM sector, so a probe + update touches exactly one sector each
-// way (a packed 24-byte cell straddles a sector boundary half of the time).  key = epoch << 32 |
-// (end item + 1): a cell whose epoch differs from the launch's epoch is empty, so the workspace never has
-// to be cleared between launches (it is zeroed once when allocated and every launch uses a fresh epoch).
-struct __align__(32) XCell {
-    unsigned long long key;
-    double num, den;
-    unsigned long long pad;
-};
-
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// find-or-insert: returns the cell index or -1 (table full).  Only one warp (accumulate) or one
-// CTA (merge) ever writes a given table; the CAS resolves lanes racing for one empty cell, and the
-// thread whose CAS inserts the key initialises the values.
-__device__ __forceinline__ int table_slot(XCell *tab, int hsize, unsigned long long key, unsigned epoch) {
-    int slot = (int)__umulhi(((unsigned)key - 1u) * 2654435761u, (unsigned)hsize);
-    for (int probe = 0; probe < hsize; ++probe) {
-        unsigned long long cur = *(volatile unsigned long long *)&tab[slot].key;
-        if (cur != key) {
-            if ((unsigned)(cur >> 32) != epoch) {          // empty (stale epoch): try to claim it
-                const unsigned long long old = atomicCAS(&tab[slot].key, cur, key);
-                if (old == cur) { tab[slot].num = 0.0; tab[slot].den = 0.0; return slot; }
-                cur = old;
-                if (cur == key) return slot;
-                if ((unsigned)(cur >> 32) != epoch) { --probe; continue; }   // changed under us but still empty: retry
-            }
-            slot = (slot + 1 == hsize) ? 0 : slot + 1;
-            continue;
-        }
-        return slot;
-    }
-    return -1;
-}
-
-// One warp per work unit (a start item, or a slice of the legs of a heavy start).
-__global__ void __launch_bounds__(XS_THREADS) xsim_accum_kernel(xmap_xsim_args a) {
-    const int x = (blockIdx.x * XS_THREADS + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (x >= a.n_units) return;
-    const int hsize = a.hash_size[x];
-    if (hsize < 32) {                                  // contract: at least 32 cells
-        if (lane == 0) atomicExch(a.error_flag, 3);
-        return;
-    }
-    XCell *tab = reinterpret_cast<XCell *>(a.hash_cells) + a.hash_off[x];
-    const unsigned epoch = a.epoch;
-    const unsigned long long ekey = (unsigned long long)epoch << 32;
-    long long combos = 0;
-
-    for (int64_t lg = a.unit_leg_lo[x]; lg < a.unit_leg_hi[x]; ++lg) {
-        const int t = a.leg_t[lg];
-        const bool joint_only = a.leg_joint_only[lg] != 0;
-        // sums in path order (extender.py:85-88): left edges first
-        const double Nl = __dadd_rn(a.leg_e1[lg], a.leg_e2[lg]);
-        const double Dl = __dadd_rn(a.leg_m1[lg], a.leg_m2[lg]);
-        const double Cl = __dmul_rn(a.leg_f1[lg], a.leg_f2[lg]);
-        for (int64_t pp = a.par_ptr[t]; pp < a.par_ptr[t + 1]; ++pp) {
-            if (joint_only && !a.par_joint[pp]) continue;
-            const int s = a.par_s[pp];
-            const double Nm = __dadd_rn(Nl, a.par_e[pp]);
-            const double Dm = __dadd_rn(Dl, a.par_m[pp]);
-            const double Cm = __dmul_rn(Cl, a.par_f[pp]);
-            const int64_t rb = a.rs_ptr[s], re = a.rs_ptr[s + 1];
-            // right-segment data of the next 32 paths is requested before the table update of the current ones
-            int y_n = -1;
-            double n_n = 0.0, d_n = 0.0, c_n = 0.0;
-            if (rb + lane < re) {
-                const int64_t r = rb + lane;
-                y_n = a.rs_end[r];
-                n_n = a.rs_n[r]; d_n = a.rs_d[r]; c_n = a.rs_c[r];
-                prefetch_l2(&tab[__umulhi((unsigned)y_n * 2654435761u, (unsigned)hsize)]);
-            }
-            for (int64_t r0 = rb; r0 < re; r0 += 32) {
-                const bool valid = r0 + lane < re;
-                const int y = y_n;
-                const double rn = n_n, rd = d_n, rc = c_n;
-                y_n = -1;
-                if (r0 + 32 + lane < re) {
-                    const int64_t r = r0 + 32 + lane;
-                    y_n = a.rs_end[r];
-                    n_n = a.rs_n[r]; d_n = a.rs_d[r]; c_n = a.rs_c[r];
-                    // pull the home cell of the next step's end towards L2 while this step updates the table
-                    prefetch_l2(&tab[__umulhi((unsigned)y_n * 2654435761u, (unsigned)hsize)]);
-                }
-                double num = 0.0, den = 0.0;
-                if (valid) {
-                    const double Nn = __dadd_rn(Nm, rn);
-                    const double Dd = __dadd_rn(Dm, rd);
-                    const double cp = __dmul_rn(Cm, rc);
-                    const double sp = (Dd != 0.0) ? __ddiv_rn(Nn, Dd) : 0.0;
-                    num = __dmul_rn(sp, cp);
-                    den = cp;
-                    ++combos;
-                }
-                // lanes that hit the same end: the lowest lane adds the terms in lane order
-                const unsigned grp = __match_any_sync(0xffffffffu, y);
-                const bool leader = valid && ((__ffs(grp) - 1) == lane);
-                unsigned rem = leader ? grp : 0u;
-                double an = 0.0, ad = 0.0;
-                while (__any_sync(0xffffffffu, rem != 0u)) {
-                    const int src = rem ? (__ffs(rem) - 1) : lane;
-                    const double n2 = __shfl_sync(0xffffffffu, num, src);
-                    const double d2 = __shfl_sync(0xffffffffu, den, src);
-                    if (rem) { an = __dadd_rn(an, n2); ad = __dadd_rn(ad, d2); rem &= rem - 1u; }
-                }
-                if (leader) {
-                    const int slot = table_slot(tab, hsize, ekey | (unsigned)(y + 1), epoch);
-                    if (slot < 0) atomicExch(a.error_flag, 2);
-                    else { tab[slot].num = __dadd_rn(tab[slot].num, an); tab[slot].den = __dadd_rn(tab[slot].den, ad); }
-                }
-                __syncwarp();
-            }
-        }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) combos += __shfl_xor_sync(0xffffffffu, combos, off);
-    if (lane == 0) a.unit_combos[x] = combos;
-}
-
-// One CTA per (dst, src) pair of a merge round: dst[y] += src[y] for every cell of src.
-// The rounds form a fixed binary tree over the slices of a heavy start, so the summation order of
-// every cell is a function of the path structure only.
-__global__ void __launch_bounds__(XS_THREADS) xsim_merge_kernel(xmap_xsim_args a, const int32_t *__restrict__ pair_dst,
-                                                                const int32_t *__restrict__ pair_src) {
-    const int d = pair_dst[blockIdx.x], sx = pair_src[blockIdx.x];
-    const int dsize = a.hash_size[d], ssize = a.hash_size[sx];
-    XCell *dt = reinterpret_cast<XCell *>(a.hash_cells) + a.hash_off[d];
-    const XCell *st = reinterpret_cast<const XCell *>(a.hash_cells) + a.hash_off[sx];
-    const unsigned epoch = a.epoch;
-    for (int q = threadIdx.x; q < ssize; q += XS_THREADS) {
-        const unsigned long long key = st[q].key;
-        if ((unsigned)(key >> 32) != epoch) continue;
-        const int slot = table_slot(dt, dsize, key, epoch);
-        if (slot < 0) { atomicExch(a.error_flag, 2); continue; }
-        dt[slot].num = __dadd_rn(dt[slot].num, st[q].num);
-        dt[slot].den = __dadd_rn(dt[slot].den, st[q].den);
-    }
-}
-
+constexpr int XT = 512;                       // threads per CTA
+constexpr int XW = XT / 32;                   // warps = owners
+constexpr int XMB = 512;                      // (leg, partner) pairs per macro-batch
+constexpr unsigned XGOLD2 = 0x85EBCA6Bu;      // second multiplicative hash of the end: owner warp and home cell
+                                              // (the first one, pi(y) = y * 0x9E3779B1, orders the lists: host side)
+constexpr int XSTACK = 48;
 constexpr int XF_BINS = 256;
-constexpr int XF_BUF = 224;                   // survivors; 224 * 12 B >= XF_BINS * 4 B
+constexpr int XSURV = 512;
 
 // 16 sub-bins per octave for |xsim| in [2^-16, 2) (see sim_bin in sim.cu)
 __device__ __forceinline__ int xsim_bin(unsigned long long key_bits) {
@@ -166,120 +47,451 @@ __device__ __forceinline__ int xsim_bin(unsigned long long key_bits) {
     return max(0, min(XF_BINS - 1, hi - base));
 }
 
-// One warp per start: count the ends and pick the top-m (two passes over the table: a histogram of
-// |xsim| to find the threshold bin, then the survivors), or emit every (end, xsim).
-__global__ void __launch_bounds__(XS_THREADS) xsim_finalize_kernel(xmap_xsim_args a) {
-    __shared__ __align__(16) unsigned char s_sel[XS_THREADS / 32][XF_BUF * 12];
-    const int x = (blockIdx.x * XS_THREADS + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (x >= a.n_starts) return;
-    const int u = a.start_unit[x];                    // the unit whose table holds the merged result
-    const int hsize = a.hash_size[u];
-    const XCell *tab = reinterpret_cast<const XCell *>(a.hash_cells) + a.hash_off[u];
-    const unsigned epoch = a.epoch;
+struct XShared {
+    // fixed part (the table follows, sized at launch)
+    double d_N[XMB], d_D[XMB], d_C[XMB];      // descriptors of the macro-batch (compacted, non-empty)
+    long long d_base[XMB];
+    double p_num[2][XW][32], p_den[2][XW][32];   // payload slots, double-buffered; finalize scratch aliases them
+    int d_cum[XMB + 4];                        // exclusive product prefix, d_cum[n_desc] = total
+    int s_lp[XMB + 4];
+    int p_y[2][XW][32];
+    unsigned p_mask[2][XW][XW];                // [owner][producer]
+    unsigned long long s_wsum[XW];
+    unsigned long long best_key[XMAP_KMAX];    // running top-m of the unit over its finished passes
+    double best_x[XMAP_KMAX];
+    int best_end[XMAP_KMAX];
+    int best_len;
+    int stack_g0[XSTACK], stack_g1[XSTACK];
+    int stack_n, next_pass, cur_g0, cur_g1;
+    int s_nd, s_total, s_overflow;
+    long long s_nextleg;
+    int s_cnt, s_nsurv, s_bstar, s_emit;
+    int status;
+    unsigned long long r_key[XW]; int r_tie[XW], r_pos[XW];   // block arg-best exchange (fallback path)
+};
 
-    if (a.mode == 2) {  // emit every (end, xsim) of this start
-        int64_t base = a.emit_ptr[x];
-        int written = 0;
-        for (int s0 = 0; s0 < hsize; s0 += 32) {
-            XCell c{0ull, 0.0, 0.0, 0ull};
-            if (s0 + lane < hsize) c = tab[s0 + lane];
-            const bool occ = (unsigned)(c.key >> 32) == epoch;
-            const unsigned m = __ballot_sync(0xffffffffu, occ);
-            if (occ) {
-                const int64_t p = base + written + __popc(m & ((1u << lane) - 1u));
-                a.emit_end[p] = int((unsigned)c.key) - 1;
-                a.emit_xsim[p] = __ddiv_rn(c.num, c.den);
-            }
-            written += __popc(m);
-        }
-        return;
-    }
+struct Fetched {
+    double N, D, C, rn, rd, rc;
+    int y;
+    bool valid;
+};
 
-    // pass 1: count + histogram of |xsim|
-    unsigned *hist = reinterpret_cast<unsigned *>(s_sel[threadIdx.x >> 5]);
-    for (int b = lane; b < XF_BINS; b += 32) hist[b] = 0u;
-    __syncwarp();
-    int cnt = 0;
-    for (int s = lane; s < hsize; s += 32) {
-        const XCell c = tab[s];
-        if ((unsigned)(c.key >> 32) != epoch) continue;
-        ++cnt;
-        atomicAdd(&hist[xsim_bin((unsigned long long)__double_as_longlong(__ddiv_rn(c.num, c.den)))], 1u);
-    }
+// products [32 c, 32 c + 32) of the macro-batch: descriptor lookup + the right-segment loads
+__device__ __forceinline__ Fetched fetch_chunk(const xmap_xsim_args &a, const XShared &S, int c, int nd, int total,
+                                               int lane) {
+    Fetched f;
+    f.valid = false; f.y = 0; f.N = f.D = f.C = f.rn = f.rd = f.rc = 0.0;
+    const int base_p = c << 5;
+    if (base_p >= total) return f;
+    // descriptor holding product base_p: largest d with d_cum[d] <= base_p (two 16-way steps)
+    const int i1 = lane << 4;
+    const unsigned m1 = __ballot_sync(0xffffffffu, i1 < nd && S.d_cum[i1] <= base_p);
+    const int coarse = (__popc(m1) - 1) << 4;
+    const int i2 = coarse + (lane & 15);
+    const unsigned m2 = __ballot_sync(0xffffffffu, lane < 16 && i2 < nd && S.d_cum[i2] <= base_p);
+    const int d0 = coarse + __popc(m2) - 1;
+    // inclusive product ends of the 32 descriptors from d0 on (every descriptor holds >= 1 product)
+    const int e = S.d_cum[min(d0 + 1 + lane, nd)];
+    const int p = base_p + lane;
+    int l = 0;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
-    __syncwarp();
-    if (lane == 0) a.out_count[x] = cnt;
-    const int M = min(a.top_m, cnt);
-    int bstar = 0;
-    {
-        int run = 0;
-        bool found = false;
-        for (int hb = XF_BINS - 32; hb >= 0 && !found && M > 0; hb -= 32) {
-            unsigned suf = hist[hb + lane];
+    for (int step = 16; step >= 1; step >>= 1) {
+        const int v = __shfl_sync(0xffffffffu, e, l + step - 1);
+        if (v <= p) l += step;
+    }
+    const int eprev = __shfl_sync(0xffffffffu, e, (l + 31) & 31);
+    const int d0cum = S.d_cum[d0];
+    if (p < total) {
+        const int di = d0 + l;
+        const int excl = l == 0 ? d0cum : eprev;
+        const long long r = S.d_base[di] + (long long)(p - excl);
+        f.valid = true;
+        f.N = S.d_N[di]; f.D = S.d_D[di]; f.C = S.d_C[di];
+        f.y = __ldg(a.rs_end + r);
+        f.rn = __ldg(a.rs_n + r); f.rd = __ldg(a.rs_d + r); f.rc = __ldg(a.rs_c + r);
+    }
+    return f;
+}
+
+__global__ void __launch_bounds__(XT, 1) xsim_tile_kernel(xmap_xsim_args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    XShared &S = *reinterpret_cast<XShared *>(smem_raw);
+    const int C = 1 << a.cells_lg;
+    const int RB = a.cells_lg - 4;                         // log2 of an owner's region
+    double2 *vals = reinterpret_cast<double2 *>(smem_raw + ((sizeof(XShared) + 15) & ~(size_t)15));
+    volatile int *keys = reinterpret_cast<volatile int *>(vals + C);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int u = a.unit_order ? a.unit_order[blockIdx.x] : (int)blockIdx.x;
+    const long long leg_lo = a.unit_leg_lo[u], leg_hi = a.unit_leg_hi[u];
+    const long long q_lo = a.lp_ptr[leg_lo], q_hi = a.lp_ptr[leg_hi];
+    const int G = 1 << a.gb, G1 = G + 1;
+    const int ug0 = a.unit_g0[u], ug1 = a.unit_g1[u], unpass = a.unit_npass[u];
+    const int M = a.top_m;
+    long long combos = 0;                                  // identical in every thread
+    int unit_count = 0;
+    unsigned ss = 0;                                       // superstep counter (payload buffer parity)
+    if (tid == 0) {
+        S.best_len = 0; S.stack_n = 0; S.next_pass = 0; S.status = 0; S.s_emit = 0;
+    }
+    __syncthreads();
+
+    for (;;) {
+        // ---- next pass: a split half if one is pending, else the unit's next own pass --------------------
+        if (tid == 0) {
+            if (S.stack_n > 0) { --S.stack_n; S.cur_g0 = S.stack_g0[S.stack_n]; S.cur_g1 = S.stack_g1[S.stack_n]; }
+            else if (S.next_pass < unpass) {
+                const long long w = ug1 - ug0;             // the unit's tile range cut into unpass equal passes
+                S.cur_g0 = ug0 + (int)(w * S.next_pass / unpass);
+                S.cur_g1 = ug0 + (int)(w * (S.next_pass + 1) / unpass);
+                ++S.next_pass;
+            } else S.cur_g0 = -1;
+            S.s_overflow = 0; S.s_cnt = 0; S.s_nsurv = 0;
+        }
+        for (int c = tid; c < C; c += XT) keys[c] = 0;
+        __syncthreads();
+        const int g0 = S.cur_g0, g1 = S.cur_g1;
+        if (g0 < 0) break;
+        const bool whole = g0 == 0 && g1 == G;
+
+        // =================== accumulate ======================================================
+        long long q0 = q_lo, cur_leg = leg_lo;
+        long long pass_combos = 0;
+        while (q0 < q_hi) {
+            const int nq = (int)min((long long)XMB, q_hi - q0);
+            const int nl = (int)min((long long)XMB, leg_hi - cur_leg);
+            if (tid < nl) {
+                const long long v = __ldg(a.lp_ptr + cur_leg + tid) - q0;
+                S.s_lp[tid] = (int)max(-(1ll << 30), min(1ll << 30, v));
+            }
+            __syncthreads();
+            if (S.s_overflow) break;                       // uniform: nobody writes the flag before the next barrier
+            int len = 0;
+            long long b = 0;
+            double Nm = 0.0, Dm = 0.0, Cm = 0.0;
+            if (tid < nq) {
+                int lo = 0, hi = nl;                       // largest leg slot with first pair <= tid
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (S.s_lp[mid] <= tid) lo = mid; else hi = mid;
+                }
+                const long long L = cur_leg + lo;
+                const int pidx = tid - S.s_lp[lo];
+                const long long p = __ldg(a.leg_par_base + L) + pidx;
+                const int s = __ldg(a.par_s + p);
+                Nm = __dadd_rn(__ldg(a.leg_n + L), __ldg(a.par_e + p));      // sums in path order (extender.py:85-88)
+                Dm = __dadd_rn(__ldg(a.leg_d + L), __ldg(a.par_m + p));
+                Cm = __dmul_rn(__ldg(a.leg_c + L), __ldg(a.par_f + p));
+                const long long rb = __ldg(a.rs_ptr + s);
+                if (whole) { b = rb; len = (int)(__ldg(a.rs_ptr + s + 1) - rb); }
+                else {
+                    const int32_t *tp = a.tile_ptr + (size_t)s * G1;
+                    const int b0 = __ldg(tp + g0), b1 = __ldg(tp + g1);
+                    b = rb + b0; len = b1 - b0;
+                }
+                if (tid == nq - 1) S.s_nextleg = (pidx + 1 == __ldg(a.leg_npar + L)) ? L + 1 : L;
+            }
+            // block scan of (non-empty flag, len)
+            const unsigned long long mine = (len > 0 ? (1ull << 40) : 0ull) | (unsigned long long)len;
+            unsigned long long incl = mine;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
-                const unsigned t = __shfl_down_sync(0xffffffffu, suf, off);
-                if (lane + off < 32) suf += t;
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += t;
             }
-            const unsigned hit = __ballot_sync(0xffffffffu, run + (int)suf >= M);
-            if (hit) { bstar = hb + (31 - __clz(hit)); found = true; }
-            else run += (int)__shfl_sync(0xffffffffu, suf, 0);
+            if (lane == 31) S.s_wsum[warp] = incl;
+            __syncthreads();
+            unsigned long long ws = lane < XW ? S.s_wsum[lane] : 0ull, wi = ws;
+#pragma unroll
+            for (int off = 1; off < XW; off <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, wi, off);
+                if (lane >= off) wi += t;
+            }
+            const unsigned long long tot = __shfl_sync(0xffffffffu, wi, XW - 1);
+            const unsigned long long woff = __shfl_sync(0xffffffffu, wi - ws, warp);
+            const unsigned long long excl = woff + incl - mine;
+            if (len > 0) {
+                const int c = (int)(excl >> 40);
+                S.d_cum[c] = (int)(excl & ((1ull << 40) - 1ull));
+                S.d_base[c] = b; S.d_N[c] = Nm; S.d_D[c] = Dm; S.d_C[c] = Cm;
+            }
+            const int nd = (int)(tot >> 40), total = (int)(tot & ((1ull << 40) - 1ull));
+            if (tid == 0) S.d_cum[nd] = total;
+            __syncthreads();
+            cur_leg = S.s_nextleg; q0 += nq;
+            pass_combos += total;
+
+            // ---- supersteps: 16 chunks of 32 products, one per warp -------------------------------
+            const int nchunk = (total + 31) >> 5;
+            Fetched nxt = fetch_chunk(a, S, warp, nd, total, lane);
+            for (int k = 0; k * XW < nchunk; ++k) {
+                const Fetched cur = nxt;
+                nxt = fetch_chunk(a, S, (k + 1) * XW + warp, nd, total, lane);
+                const int buf = ss & 1u; ++ss;
+                // produce
+                int owner = XW;
+                if (cur.valid) {
+                    const double Nn = __dadd_rn(cur.N, cur.rn);
+                    const double Dd = __dadd_rn(cur.D, cur.rd);
+                    const double cp = __dmul_rn(cur.C, cur.rc);
+                    const double sp = (Dd != 0.0) ? __ddiv_rn(Nn, Dd) : 0.0;      // extender.py:88-89
+                    S.p_num[buf][warp][lane] = __dmul_rn(sp, cp);
+                    S.p_den[buf][warp][lane] = cp;
+                    S.p_y[buf][warp][lane] = cur.y;
+                    owner = (int)(((unsigned)cur.y * XGOLD2) >> 28);
+                }
+                if (lane < XW) S.p_mask[buf][lane][warp] = 0u;
+                __syncwarp();
+                const unsigned grp = __match_any_sync(0xffffffffu, owner);
+                if (cur.valid && (__ffs(grp) - 1) == lane) S.p_mask[buf][owner][warp] = grp;
+                __syncthreads();
+                // consume: the slots addressed to owner `warp`, in (producer, lane) order
+                const unsigned pm = lane < XW ? S.p_mask[buf][warp][lane] : 0u;
+                const int cntl = __popc(pm);
+                int incl_i = cntl;
+#pragma unroll
+                for (int off = 1; off < XW; off <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl_i, off);
+                    if (lane >= off) incl_i += t;
+                }
+                const int tot_o = __shfl_sync(0xffffffffu, incl_i, XW - 1);
+                const int region = warp << RB;
+                for (int i0 = 0; i0 < tot_o; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool valid = i < tot_o;
+                    int pr = 0;                            // smallest producer with incl > i
+#pragma unroll
+                    for (int step = XW / 2; step >= 1; step >>= 1) {
+                        const int v = __shfl_sync(0xffffffffu, incl_i, pr + step - 1);
+                        if (v <= i) pr += step;
+                    }
+                    pr = min(pr, XW - 1);
+                    const int before = __shfl_sync(0xffffffffu, incl_i - cntl, pr);
+                    const unsigned mk = __shfl_sync(0xffffffffu, pm, pr);
+                    int y = -1 - lane;
+                    double num = 0.0, den = 0.0;
+                    if (valid) {
+                        const int src = __fns(mk, 0, i - before + 1);
+                        y = S.p_y[buf][pr][src];
+                        num = S.p_num[buf][pr][src]; den = S.p_den[buf][pr][src];
+                    }
+                    const unsigned g2 = __match_any_sync(0xffffffffu, y);
+                    const bool leader = valid && (__ffs(g2) - 1) == lane;
+                    // find-or-insert in the owner's region (write-then-verify resolves lanes racing for one empty cell)
+                    int slot = -1;
+                    bool isnew = false;
+                    {
+                        int pos = (int)((((unsigned)y * XGOLD2) << 4) >> (32 - RB));
+                        bool pending = leader;
+                        int probes = 0;
+                        while (__any_sync(0xffffffffu, pending)) {
+                            bool tried = false;
+                            if (pending) {
+                                const int kcur = keys[region + pos];
+                                if (kcur == y + 1) { slot = region + pos; pending = false; }
+                                else if (kcur == 0) { keys[region + pos] = y + 1; tried = true; }
+                                else {
+                                    pos = (pos + 1) & ((1 << RB) - 1);
+                                    if (++probes >= (1 << RB)) { pending = false; S.s_overflow = 1; }
+                                }
+                            }
+                            __syncwarp();
+                            if (tried && keys[region + pos] == y + 1) { slot = region + pos; isnew = true; pending = false; }
+                            __syncwarp();
+                        }
+                    }
+                    // terms of one end are added one by one, in lane (= path) order
+                    double an = 0.0, ad = 0.0;
+                    if (leader && slot >= 0 && !isnew) { const double2 v = vals[slot]; an = v.x; ad = v.y; }
+                    unsigned rem = leader ? g2 : 0u;
+                    while (__any_sync(0xffffffffu, rem != 0u)) {
+                        const int src = rem ? (__ffs(rem) - 1) : lane;
+                        const double n2 = __shfl_sync(0xffffffffu, num, src);
+                        const double d2 = __shfl_sync(0xffffffffu, den, src);
+                        if (rem) { an = __dadd_rn(an, n2); ad = __dadd_rn(ad, d2); rem &= rem - 1u; }
+                    }
+                    if (leader && slot >= 0) vals[slot] = make_double2(an, ad);
+                }
+            }
         }
+        __syncthreads();
+        if (S.s_overflow) {
+            // the pass does not fit: halve its hash range and redo both halves (nothing of it was published)
+            if (tid == 0) {
+                if (g1 - g0 < 2 || S.stack_n + 2 > XSTACK) S.status = 1;
+                else {
+                    const int mid = (g0 + g1) >> 1;
+                    S.stack_g0[S.stack_n] = mid; S.stack_g1[S.stack_n] = g1; ++S.stack_n;
+                    S.stack_g0[S.stack_n] = g0; S.stack_g1[S.stack_n] = mid; ++S.stack_n;
+                }
+            }
+            __syncthreads();
+            continue;
+        }
+        combos += pass_combos;
+
+        // =================== finalize the pass ==============================================
+        unsigned *hist = reinterpret_cast<unsigned *>(&S.p_num[0][0][0]);                       // 1 KB
+        unsigned long long *sv_key = reinterpret_cast<unsigned long long *>(&S.p_den[0][0][0]); // 4 KB
+        double *sv_x = reinterpret_cast<double *>(&S.p_den[1][0][0]);                           // 4 KB
+        int *sv_end = reinterpret_cast<int *>(&S.p_num[1][0][0]);                               // 2 KB
+        for (int bq = tid; bq < XF_BINS; bq += XT) hist[bq] = 0u;
+        __syncthreads();
+        int mycnt = 0;
+        for (int c0 = warp * 32; c0 < C; c0 += XT) {
+            const int c = c0 + lane;
+            const int kk = keys[c];
+            const bool occ = kk != 0;
+            double x = 0.0;
+            if (occ) {
+                const double2 v = vals[c];
+                x = __ddiv_rn(v.x, v.y);                   // extender.py:198-201
+                vals[c].x = x;
+                atomicAdd(&hist[xsim_bin(abs_key(x))], 1u);
+                ++mycnt;
+            }
+            if (a.emit_ptr) {
+                const unsigned mo = __ballot_sync(0xffffffffu, occ);
+                int base = 0;
+                if (lane == 0 && mo) base = atomicAdd(&S.s_emit, __popc(mo));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (occ) {
+                    const long long o = a.emit_ptr[u] + base + __popc(mo & ((1u << lane) - 1u));
+                    a.emit_end[o] = kk - 1; a.emit_xsim[o] = x;
+                }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) mycnt += __shfl_xor_sync(0xffffffffu, mycnt, off);
+        if (lane == 0 && mycnt) atomicAdd(&S.s_cnt, mycnt);
+        __syncthreads();
+        const int cnt_pass = S.s_cnt;
+        unit_count += cnt_pass;
+        const int want = min(M, cnt_pass);
+        if (warp == 0) {
+            // largest bin b* such that #(bin >= b*) >= want
+            int bstar = 0, run = 0;
+            bool found = false;
+            for (int hb = XF_BINS - 32; hb >= 0 && !found && want > 0; hb -= 32) {
+                unsigned suf = hist[hb + lane];
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const unsigned t = __shfl_down_sync(0xffffffffu, suf, off);
+                    if (lane + off < 32) suf += t;
+                }
+                const unsigned hit = __ballot_sync(0xffffffffu, run + (int)suf >= want);
+                if (hit) { bstar = hb + (31 - __clz(hit)); found = true; }
+                else run += (int)__shfl_sync(0xffffffffu, suf, 0);
+            }
+            if (lane == 0) S.s_bstar = bstar;
+        }
+        __syncthreads();
+        const int bstar = S.s_bstar;
+        // survivors: cells at or above the threshold bin, plus the running best of the earlier passes
+        for (int c = tid; c < C && want > 0; c += XT) {
+            const int kk = keys[c];
+            if (kk == 0) continue;
+            const double x = vals[c].x;
+            const unsigned long long ak = abs_key(x);
+            if (xsim_bin(ak) < bstar) continue;
+            const int pos = atomicAdd(&S.s_nsurv, 1);
+            if (pos < XSURV) { sv_key[pos] = ak; sv_x[pos] = x; sv_end[pos] = kk - 1; }
+        }
+        const int nbest = S.best_len;
+        __syncthreads();
+        int nsurv = S.s_nsurv;
+        const int newlen = min(M, cnt_pass + nbest);
+        if (nsurv + nbest <= XSURV) {
+            if (tid < nbest) { sv_key[nsurv + tid] = S.best_key[tid]; sv_x[nsurv + tid] = S.best_x[tid]; sv_end[nsurv + tid] = S.best_end[tid]; }
+            __syncthreads();
+            nsurv += nbest;
+            if (tid < nsurv) {
+                const unsigned long long mk = sv_key[tid];
+                const int me = sv_end[tid];
+                int rank = 0;
+                for (int t = 0; t < nsurv; ++t) rank += better(sv_key[t], sv_end[t], mk, me) ? 1 : 0;
+                if (rank < newlen) { S.best_key[rank] = mk; S.best_x[rank] = sv_x[tid]; S.best_end[rank] = me; }
+            }
+            if (tid == 0) S.best_len = newlen;
+        } else {
+            // one bin holds too many equal values: plain rounds over every cell and the running best
+            // (new list built in sv_*; every round picks the best candidate strictly after the last)
+            __syncthreads();
+            unsigned long long last_k = ~0ull; int last_t = -1;
+            for (int r = 0; r < newlen; ++r) {
+                unsigned long long bk = 0ull; int bt = 0x7FFFFFFF, bp = -1;
+                for (int c = tid; c < C + nbest; c += XT) {
+                    unsigned long long ak; int ee;
+                    if (c < C) { const int kk = keys[c]; if (kk == 0) continue; ak = abs_key(vals[c].x); ee = kk - 1; }
+                    else { ak = S.best_key[c - C]; ee = S.best_end[c - C]; }
+                    if (r > 0 && !better(last_k, last_t, ak, ee)) continue;
+                    if (bp < 0 || better(ak, ee, bk, bt)) { bk = ak; bt = ee; bp = c; }
+                }
+                warp_argbest(bk, bt, bp);
+                if (lane == 0) { S.r_key[warp] = bk; S.r_tie[warp] = bt; S.r_pos[warp] = bp; }
+                __syncthreads();
+                bk = lane < XW ? S.r_key[lane] : 0ull; bt = lane < XW ? S.r_tie[lane] : 0x7FFFFFFF; bp = lane < XW ? S.r_pos[lane] : -1;
+                warp_argbest(bk, bt, bp);
+                if (tid == 0 && bp >= 0) {
+                    sv_key[r] = bk; sv_end[r] = bt;
+                    sv_x[r] = bp < C ? vals[bp].x : S.best_x[bp - C];
+                }
+                last_k = bk; last_t = bt;
+                __syncthreads();
+            }
+            if (tid < newlen) { S.best_key[tid] = sv_key[tid]; S.best_x[tid] = sv_x[tid]; S.best_end[tid] = sv_end[tid]; }
+            if (tid == 0) S.best_len = newlen;
+        }
+        __syncthreads();
     }
-    __syncwarp();
-    // pass 2: survivors (bin >= b*), or, if one bin holds too many equal values, plain rounds
-    unsigned long long *bkey = reinterpret_cast<unsigned long long *>(s_sel[threadIdx.x >> 5]);
-    int *bslot = reinterpret_cast<int *>(bkey + XF_BUF);
-    int nb = 0;
-    bool overflow = false;
-    for (int s0 = 0; s0 < hsize && M > 0; s0 += 32) {
-        XCell c{0ull, 0.0, 0.0, 0ull};
-        if (s0 + lane < hsize) c = tab[s0 + lane];
-        bool take = false;
-        unsigned long long kk = 0ull;
-        if ((unsigned)(c.key >> 32) == epoch) {
-            kk = abs_key(__ddiv_rn(c.num, c.den));
-            take = xsim_bin(kk) >= bstar;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, take);
-        if (nb + __popc(m) > XF_BUF) { overflow = true; break; }
-        if (take) {
-            const int pos = nb + __popc(m & ((1u << lane) - 1u));
-            bkey[pos] = kk; bslot[pos] = s0 + lane;
-        }
-        nb += __popc(m);
+
+    // ---- publish the unit ------------------------------------------------------------------------
+    if (tid == 0) {
+        a.unit_count[u] = unit_count;
+        a.unit_combos[u] = combos;
+        a.unit_top_len[u] = S.best_len;
+        if (S.status) atomicExch(a.error_flag, 2);
     }
-    __syncwarp();
+    if (tid < S.best_len) {
+        a.unit_top_end[(size_t)u * M + tid] = S.best_end[tid];
+        a.unit_top_xsim[(size_t)u * M + tid] = S.best_x[tid];
+    }
+}
+
+// One warp per start: distinct ends and paths are the sums over its units, its top-m the best m of the units' lists
+// (the units of a start cover disjoint ends).
+__global__ void __launch_bounds__(256) xsim_merge_kernel(xmap_xsim_args a) {
+    const int x = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (x >= a.n_starts) return;
+    const int u0 = a.start_unit_ptr[x], u1 = a.start_unit_ptr[x + 1];
+    const int M = a.top_m;
+    int cnt = 0; long long comb = 0;
+    for (int u = u0 + lane; u < u1; u += 32) { cnt += a.unit_count[u]; comb += a.unit_combos[u]; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        comb += __shfl_xor_sync(0xffffffffu, comb, off);
+    }
+    if (lane == 0) { a.out_count[x] = cnt; a.out_combos[x] = comb; }
     unsigned long long last_k = ~0ull;
     int last_t = -1, got = 0;
+    const int ncand = (u1 - u0) * M;
     for (int r = 0; r < M; ++r) {
-        unsigned long long bk = 0;
-        int bt = 0x7FFFFFFF, bp = -1;
-        if (!overflow) {
-            for (int q = lane; q < nb; q += 32) {
-                const unsigned long long kk = bkey[q];
-                const int sl = bslot[q];
-                const int tt = int((unsigned)tab[sl].key) - 1;
-                if (r > 0 && !better(last_k, last_t, kk, tt)) continue;
-                if (bp < 0 || better(kk, tt, bk, bt)) { bk = kk; bt = tt; bp = sl; }
-            }
-        } else {
-            for (int s = lane; s < hsize; s += 32) {
-                const XCell c = tab[s];
-                if ((unsigned)(c.key >> 32) != epoch) continue;
-                const unsigned long long kk = abs_key(__ddiv_rn(c.num, c.den));
-                const int tt = int((unsigned)c.key) - 1;
-                if (r > 0 && !better(last_k, last_t, kk, tt)) continue;    // strictly after the previous winner
-                if (bp < 0 || better(kk, tt, bk, bt)) { bk = kk; bt = tt; bp = s; }
-            }
+        unsigned long long bk = 0ull; int bt = 0x7FFFFFFF, bp = -1;
+        for (int q = lane; q < ncand; q += 32) {
+            const int u = u0 + q / M, p = q % M;
+            if (p >= a.unit_top_len[u]) continue;
+            const size_t o = (size_t)u * M + p;
+            const unsigned long long ak = abs_key(a.unit_top_xsim[o]);
+            const int ee = a.unit_top_end[o];
+            if (r > 0 && !better(last_k, last_t, ak, ee)) continue;
+            if (bp < 0 || better(ak, ee, bk, bt)) { bk = ak; bt = ee; bp = (int)(o - (size_t)u0 * M); }
         }
         warp_argbest(bk, bt, bp);
         if (bp < 0) break;
         if (lane == 0) {
-            a.top_end[(size_t)x * a.top_m + r] = bt;
-            a.top_xsim[(size_t)x * a.top_m + r] = __ddiv_rn(tab[bp].num, tab[bp].den);
+            a.top_end[(size_t)x * M + r] = bt;
+            a.top_xsim[(size_t)x * M + r] = a.unit_top_xsim[(size_t)u0 * M + bp];
         }
         last_k = bk; last_t = bt;
         got = r + 1;
@@ -291,23 +503,33 @@ __global__ void __launch_bounds__(XS_THREADS) xsim_finalize_kernel(xmap_xsim_arg
 
 using namespace xmap;
 
+extern "C" int64_t xmap_xsim_smem_bytes(int32_t cells_lg) {
+    return (int64_t)((sizeof(XShared) + 15) & ~(size_t)15) + ((int64_t)20 << cells_lg);
+}
+
 extern "C" int xmap_xsim_extend(const xmap_xsim_args *args_h, void *stream_) {
     const xmap_xsim_args &a = *args_h;
     if (a.n_starts <= 0 || a.n_units <= 0) return 0;
     if (a.top_m < 1 || a.top_m > XMAP_KMAX) return fail_msg("xmap_xsim_extend: top_m out of range");
-    if (a.mode != 0 && a.mode != 2) return fail_msg("xmap_xsim_extend: bad mode");
+    if (a.cells_lg < 9 || a.cells_lg > XMAP_XSIM_MAX_CELLS_LG) return fail_msg("xmap_xsim_extend: cells_lg out of range");
+    if (a.gb < 0 || a.gb > 16) return fail_msg("xmap_xsim_extend: gb out of range");
     cudaStream_t st = (cudaStream_t)stream_;
-    const int wpc = XS_THREADS / 32;
-    xsim_accum_kernel<<<(unsigned)((a.n_units + wpc - 1) / wpc), XS_THREADS, 0, st>>>(a);
+    const size_t smem = (size_t)xmap_xsim_smem_bytes(a.cells_lg);
+    XMAP_CUDA(cudaFuncSetAttribute(xsim_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    xsim_tile_kernel<<<(unsigned)a.n_units, XT, smem, st>>>(a);
     XMAP_LAUNCH_CHECK();
-    for (int r = 0; r < a.n_rounds; ++r) {
-        const int lo = a.round_ptr_h[r], hi = a.round_ptr_h[r + 1];
-        if (hi > lo) {
-            xsim_merge_kernel<<<(unsigned)(hi - lo), XS_THREADS, 0, st>>>(a, a.pair_dst + lo, a.pair_src + lo);
-            XMAP_LAUNCH_CHECK();
-        }
+    if (a.merge) {
+        xsim_merge_kernel<<<(unsigned)((a.n_starts + 7) / 8), 256, 0, st>>>(a);
+        XMAP_LAUNCH_CHECK();
     }
-    xsim_finalize_kernel<<<(unsigned)((a.n_starts + wpc - 1) / wpc), XS_THREADS, 0, st>>>(a);
+    return 0;
+}
+
+extern "C" int xmap_xsim_merge(const xmap_xsim_args *args_h, void *stream_) {
+    const xmap_xsim_args &a = *args_h;
+    if (a.n_starts <= 0) return 0;
+    if (a.top_m < 1 || a.top_m > XMAP_KMAX) return fail_msg("xmap_xsim_merge: top_m out of range");
+    xsim_merge_kernel<<<(unsigned)((a.n_starts + 7) / 8), 256, 0, (cudaStream_t)stream_>>>(a);
     XMAP_LAUNCH_CHECK();
     return 0;
 }

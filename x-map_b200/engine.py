@@ -35,6 +35,13 @@ class ItemMeta:
     has_T: torch.Tensor           # bool   "T:" in iid
 
 
+def to_device_meta(meta, device="cuda"):
+    """dict of host arrays (encode.item_codes order: prefix_code, dom_code, contains, has_S, has_T) -> ItemMeta."""
+    T = lambda key, dt: torch.as_tensor(meta[key], dtype=dt, device=device)
+    return ItemMeta(prefix_code=T("prefix_code", torch.int32), dom_code=T("dom_code", torch.uint8),
+                    contains=T("contains", torch.uint8), has_S=T("has_S", torch.bool), has_T=T("has_T", torch.bool))
+
+
 @dataclass
 class Layout:
     n_users: int
@@ -202,6 +209,7 @@ class SimEngine:
         self.rec_ptr = torch.zeros(I + 1, dtype=torch.int64, device=dev)
         self.rec_ptr[1:] = torch.cumsum(cap, 0)
         self.rec_cap = cap
+        self.rec_cap_bound = cap       # rank-invariant upper bound (rec_cap becomes rank-specific after exact sizing)
         total = int(self.rec_ptr[-1].item()) if I else 0
         if rec_budget is None:
             free, _ = torch.cuda.mem_get_info(dev)
@@ -230,6 +238,15 @@ class SimEngine:
             if len(pool) < 2:
                 pool.append(rec)
 
+    def release_lists(self):
+        """Drop the record storage so that the next stage sizes the lists exactly (multi-GPU: decided collectively)."""
+        rec, self.rec = self.rec, None
+        if rec is not None and rec.shape[0] > (1 << 20):
+            pool = _REC_POOL.setdefault(str(rec.device), [])
+            if len(pool) < 2:
+                pool.append(rec)
+        self.exact_sizing = True
+
     # -- argument block ----------------------------------------------------
     def _args(self):
         lay, m = self.lay, self.meta
@@ -255,7 +272,12 @@ class SimEngine:
         cells_cap, threads_per_row, in_global_memory, row headers)], long_candidates = rows whose record
         list can exceed XMAP_SELECT_LONG, split = segment arrays of the rows whose rater list is
         cut over several CTAs (or None)."""
-        key = None if rows is None else (int(rows[0]) if rows.numel() else -1, int(rows.numel()))
+        key = None
+        if rows is not None:
+            n = int(rows.numel())
+            lo = int(rows[0]) if n else -1
+            contiguous = n == 0 or (int(rows[-1]) == lo + n - 1 and bool((rows[1:] - rows[:-1] == 1).all()))
+            key = (lo, n) if contiguous else ("set", hash(tuple(rows.cpu().tolist())))
         if key in self._plans:
             return self._plans[key]
         dev, I = self.device, self.lay.n_items
@@ -467,17 +489,23 @@ class SimEngine:
                          self.tab_idx, self.tab_sim, self.tab_mutu, self.tab_n, self.tab_len,
                          self.launches, stats or {})
 
-    def tables_to_host(self, tabs=None):
-        """Neighbour tables + BB flags in pinned host memory (allocated once per shape, reused):
+    def tables_to_host(self, tabs=None, reuse=False):
+        """Neighbour tables + BB flags in pinned host memory (reuse=True: module-level buffers that the next
+        call overwrites; default: buffers owned by the caller):
         the device -> host read of the stage's result (the reference's collectAsMap, assist.py:121-129)."""
         tabs = tabs or self.tables()
         src = dict(row_flags=tabs.row_flags, tab_len=tabs.tab_len, tab_idx=tabs.tab_idx, tab_sim=tabs.tab_sim,
                    tab_mutu=tabs.tab_mutu, tab_n=tabs.tab_n)
         key = tuple((k, tuple(v.shape), v.dtype) for k, v in src.items())
-        if key not in _PINNED:                      # page-locking is slow: keep the buffers for the next engine
-            _PINNED.clear()
-            _PINNED[key] = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in src.items()}
-        host = _PINNED[key]
+        if reuse:
+            # benchmark fast path: one module-level set of pinned buffers (page-locking is slow), shared by
+            # every engine of the same shapes -- the previous result is overwritten
+            if key not in _PINNED:
+                _PINNED.clear()
+                _PINNED[key] = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in src.items()}
+            host = _PINNED[key]
+        else:
+            host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in src.items()}
         for k, v in src.items():
             host[k].copy_(v, non_blocking=True)
         torch.cuda.current_stream().synchronize()

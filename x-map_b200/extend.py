@@ -26,8 +26,6 @@ import torch
 
 from . import _native as N
 
-XSIM_HASH_BUDGET = 48 << 30     # bytes of per-unit hash tables per launch
-XSIM_UNIT_COMBOS = 1 << 20      # a start with more paths than this is cut into leg slices
 
 
 def _excl_cumsum(x):
@@ -228,14 +226,13 @@ def build_plan(tabs, item_count, has_S, has_T):
         t_items=t_items, s_items=s_items)
 
 
-def _pow2_at_least(x):
-    """Smallest power of two >= x, in exact integer arithmetic (float pow / log2 on the
-    device are not exact and a table size of 2^k - 1 breaks the probe mask)."""
-    x = torch.clamp(x.long(), min=1)
-    p = torch.ones_like(x)
-    for _ in range(62):
-        p = torch.where(p < x, p * 2, p)
-    return p
+PI_MULT = 0x9E3779B1            # pi(y) = (y * PI_MULT) mod 2^32 orders every right-segment list (csrc/xsim.cu)
+XSIM_CELLS_LG = N.XSIM_MAX_CELLS_LG     # 8192-cell shared-memory table per CTA
+XSIM_LOAD = 0.62                # target fill of the table (16 owner regions of cells / 16 each)
+XSIM_RHO = 1.25                 # assumed paths per distinct end when a start's pass count is chosen
+                                # (measured at cfg2: 10 % quantile 1.30, median 1.62; a pass that turns out
+                                # too full is split on the device)
+XSIM_UNIT_WORK = 1 << 21        # paths per CTA: heavier starts are cut into several units (disjoint end ranges)
 
 
 @dataclass
@@ -247,203 +244,191 @@ class XsimResult:
     top_xsim: torch.Tensor
     top_len: torch.Tensor
     launches: int
+    unit_count: torch.Tensor = None   # int32 [n_units] distinct ends per work unit (sizes the emit pass)
 
 
 class XsimEngine:
-    """Runs the extension kernels over an XsimPlan.
+    """Runs the extension kernels over an XsimPlan (C ABI section 3).
 
-    Work units: a start whose path count exceeds `unit_combos` is cut, at leg granularity, into
-    slices that run as independent warps with private hash tables; the slices are then merged by
-    a fixed binary tree (slice g absorbs g + 2^r in round r), so every cell's summation order is
-    a function of the path structure only -- results do not depend on launch batching."""
+    The accumulator of a start lives in shared memory.  The end axis is hashed (pi) and cut into 2^gb
+    tiles; a start evaluates its paths in passes over tile ranges small enough for the table, a CTA
+    ("unit") runs one or more passes of one start, heavy starts are spread over several units.  Every
+    (start, end) sum is formed in path order (leg, partner, right segment), so results are bit-identical
+    for any table size, pass split, unit split or number of GPUs."""
 
-    def __init__(self, plan, top_m=10, hash_budget=XSIM_HASH_BUDGET, unit_combos=XSIM_UNIT_COMBOS):
+    def __init__(self, plan, top_m=10, cells_lg=XSIM_CELLS_LG, rho=XSIM_RHO, unit_work=XSIM_UNIT_WORK,
+                 load=XSIM_LOAD):
         if not (1 <= top_m <= N.KMAX):
             raise ValueError("top_m must be in [1, %d]" % N.KMAX)
-        self.plan, self.top_m, self.hash_budget = plan, int(top_m), hash_budget
+        if not (9 <= cells_lg <= N.XSIM_MAX_CELLS_LG):
+            raise ValueError("cells_lg must be in [9, %d]" % N.XSIM_MAX_CELLS_LG)
+        self.plan, self.top_m, self.cells_lg = plan, int(top_m), int(cells_lg)
         p = plan
         dev = self.device = p.start_item.device
         self.launches = 0
-        n = p.start_item.numel()
-        self.error_flag = torch.zeros(1, dtype=torch.int32, device=dev)
-        i64 = torch.int64
-        lc = p.leg_ptr[1:] - p.leg_ptr[:-1]
-        leg_start = _segment_ids(lc)
-        # slice id of a leg = (paths of the start before this leg) // unit_combos
-        before = torch.cumsum(p.ub_leg, 0) - p.ub_leg
-        start_base = torch.zeros(n, dtype=i64, device=dev)
-        if n:
-            start_base = before[p.leg_ptr[:-1].clamp(max=max(before.numel() - 1, 0))] if before.numel() else start_base
-        gid = (before - start_base[leg_start]) // int(unit_combos) if before.numel() else before
-        ukey = leg_start * (1 << 24) + gid
-        _, ucnt = torch.unique_consecutive(ukey, return_counts=True)
-        self.unit_leg_hi = torch.cumsum(ucnt, 0)
-        self.unit_leg_lo = self.unit_leg_hi - ucnt
-        self.unit_start = leg_start[self.unit_leg_lo] if ucnt.numel() else leg_start
-        n_units = int(ucnt.numel())
-        unit_ub = torch.zeros(n_units, dtype=i64, device=dev)
-        if n_units:
-            unit_ub.index_add_(0, _segment_ids(ucnt), p.ub_leg)
-        self.G = torch.bincount(self.unit_start, minlength=n) if n_units else torch.zeros(n, dtype=i64, device=dev)
-        self.u0 = torch.cumsum(self.G, 0) - self.G
-        g = torch.arange(n_units, device=dev) - self.u0[self.unit_start] if n_units else unit_ub
-        self.unit_g = g
-        # table of slice g must hold the union of its merge subtree [g, g + lowbit(g)) (all for g == 0)
-        lowbit = torch.where(g > 0, g & (-g), self.G[self.unit_start] if n_units else g)
-        hi = torch.minimum(g + lowbit, self.G[self.unit_start]) if n_units else g
-        P = torch.zeros(n_units + 1, dtype=i64, device=dev)
-        P[1:] = torch.cumsum(unit_ub, 0)
-        base_u = self.u0[self.unit_start] if n_units else g
-        sub_ub = P[base_u + hi] - P[base_u + g] if n_units else unit_ub
-        end_cap = int(torch.unique(p.rs_end).numel()) if p.rs_end.numel() else 1
-        # distinct ends <= min(paths, reachable ends): a table of >= 1.25x that bound never fills up
-        # (worst-case load 0.8; typical load ~0.25 because several paths share an end)
-        self.hsize = torch.clamp((5 * torch.clamp(sub_ub, max=end_cap) + 3) // 4, min=32)
-        self.start_bytes = torch.zeros(n, dtype=i64, device=dev)
-        if n_units:
-            self.start_bytes.index_add_(0, self.unit_start, self.hsize * 32)
-        # the two edges of a right segment folded into one (N, D, C) triple: 28 instead of 60 bytes per
-        # path (the sums are reassociated by at most one rounding; D is an exact integer either way)
-        e1, m1, f1, e2, m2, f2 = p.rs_vals
-        # ... and every list ordered by end (stable), so that right segments of one source that end at the
-        # same item sit in the same 32-path step and are combined before they reach the table
+        i64, i32 = torch.int64, torch.int32
+        n = int(p.start_item.numel())
+        self.error_flag = torch.zeros(1, dtype=i32, device=dev)
+        # ---- legs: left segment folded in path order (edge (x,n) first, then (n,t)) ---------------------
+        e1, m1, f1, e2, m2, f2 = p.leg_vals
+        self.leg_n, self.leg_d, self.leg_c = (e1 + e2).contiguous(), (m1 + m2).contiguous(), (f1 * f2).contiguous()
+        # ---- partners: the joint ones first within every bridge target, so that a joint-only leg (the
+        # reference's inner join, extender.py:178) uses a prefix of the list ----------------------------
+        par_cnt = p.par_ptr[1:] - p.par_ptr[:-1]
+        t_of_par = _segment_ids(par_cnt)
+        joint = p.par_joint.long()
+        perm = torch.argsort(t_of_par * 2 + (1 - joint), stable=True) if joint.numel() else joint
+        self.par_s = p.par_s[perm].contiguous()
+        self.par_e, self.par_m, self.par_f = (v[perm].contiguous() for v in p.par_vals)
+        jcnt = torch.zeros_like(par_cnt)
+        if joint.numel():
+            jcnt.index_add_(0, t_of_par, joint)
+        lt = p.leg_t.long()
+        self.leg_npar = torch.where(p.leg_joint_only.bool(), jcnt[lt], par_cnt[lt]).to(i32).contiguous() \
+            if lt.numel() else torch.zeros(0, dtype=i32, device=dev)
+        self.leg_par_base = p.par_ptr[lt].contiguous() if lt.numel() else torch.zeros(0, dtype=i64, device=dev)
+        self.lp_ptr = torch.zeros(lt.numel() + 1, dtype=i64, device=dev)
+        self.lp_ptr[1:] = torch.cumsum(self.leg_npar.long(), 0)
+        # ---- right segments: the two edges folded into one (N, D, C) triple (the sums are reassociated
+        # by at most one rounding; D is an exact integer either way), every list ordered by pi(end) ------
+        r1, rm1, rf1, r2, rm2, rf2 = p.rs_vals
         rl = p.rs_ptr[1:] - p.rs_ptr[:-1]
+        n_s = int(rl.numel())
+        if n_s and int(rl.max()) >= (1 << 22):
+            raise N.NativeError("a right-segment list has >= 2^22 entries: the per-batch product counter is 32-bit")
         seg = _segment_ids(rl)
-        perm = torch.argsort(seg * int(p.n_items) + p.rs_end.long(), stable=True) if seg.numel() else seg
+        pi = (p.rs_end.long() * PI_MULT) & 0xFFFFFFFF
+        perm = torch.argsort(seg * (1 << 32) + pi, stable=True) if seg.numel() else seg
         self.rs_end = p.rs_end[perm].contiguous()
-        self.rs_ndc = ((e1 + e2)[perm].contiguous(), (m1 + m2)[perm].contiguous(), (f1 * f2)[perm].contiguous())
-        self.order = torch.argsort(p.ub, descending=True, stable=True)
-        self.n_units = n_units
-        self._cells = None
-        self.epoch = 0
+        self.rs_ndc = ((r1 + r2)[perm].contiguous(), (rm1 + rm2)[perm].contiguous(), (rf1 * rf2)[perm].contiguous())
+        pi = pi[perm] if seg.numel() else pi
+        self.end_cap = int(torch.unique(p.rs_end).numel()) if p.rs_end.numel() else 1
+        # ---- passes per start: enough for the estimated distinct ends, and enough units for its paths ---
+        cap = max(16.0, load * (1 << self.cells_lg))
+        ub = p.ub.double()
+        e_est = torch.clamp(ub / float(rho), max=float(self.end_cap))
+        T = torch.clamp(torch.ceil(e_est / cap), min=1).long()
+        n_units_x = torch.clamp(torch.ceil(ub / float(unit_work)), min=1).long()
+        n_units_x = torch.minimum(n_units_x, torch.clamp(T * 4, min=1))         # a few passes' worth of splitting at most
+        T = torch.maximum(T, n_units_x)
+        t_max = int(T.max().item()) if n else 1
+        # 2^gb tiles: at least twice the largest pass count (so pass boundaries fall close to the ideal cut)
+        # and one more level for device-side splits
+        self.gb = min(12, max(2, (2 * t_max - 1).bit_length() + 1))
+        G = 1 << self.gb
+        T = torch.clamp(T, max=G)
+        n_units_x = torch.clamp(n_units_x, max=G)
+        ppu = (T + n_units_x - 1) // n_units_x                                 # passes per unit
+        tile = (pi >> (32 - self.gb)) if self.gb else torch.zeros_like(pi)
+        cnt = torch.bincount(seg * G + tile, minlength=n_s * G).view(n_s, G) if seg.numel() else \
+            torch.zeros((n_s, G), dtype=i64, device=dev)
+        self.tile_ptr = torch.zeros((n_s, G + 1), dtype=i32, device=dev)
+        self.tile_ptr[:, 1:] = torch.cumsum(cnt, 1).to(i32)
+        del cnt
+        # ---- units -------------------------------------------------------------------------------------
+        self.start_unit_ptr = torch.zeros(n + 1, dtype=i32, device=dev)
+        self.start_unit_ptr[1:] = torch.cumsum(n_units_x, 0).to(i32)
+        self.n_units = int(self.start_unit_ptr[-1].item()) if n else 0
+        us = _segment_ids(n_units_x)
+        kq = torch.arange(self.n_units, device=dev) - self.start_unit_ptr[:-1].long()[us]
+        nu = n_units_x[us]
+        self.unit_start = us
+        self.unit_g0 = (kq * G // nu).to(i32).contiguous()
+        self.unit_g1 = ((kq + 1) * G // nu).to(i32).contiguous()
+        self.unit_npass = torch.minimum(ppu[us], (self.unit_g1 - self.unit_g0).long()).to(i32).contiguous()
+        self.unit_leg_lo = p.leg_ptr[:-1][us].contiguous()
+        self.unit_leg_hi = p.leg_ptr[1:][us].contiguous()
+        unit_work_est = ub[us] / nu.double()
+        self.unit_order = torch.argsort(unit_work_est, descending=True, stable=True).to(i32).contiguous()
+        self.T, self.n_units_x = T, n_units_x
 
     # ------------------------------------------------------------------
-    def _workspace(self, n_cells):
-        """Persistent cell workspace (32 B cells), zeroed once; launches are told apart by epoch."""
-        need = n_cells * 4
-        if self._cells is None or self._cells.numel() < need:
-            self._cells = None
-            self._cells = torch.zeros(need, dtype=torch.int64, device=self.device)
-        return self._cells
-
-    def _batches(self, rank=0, world=1):
-        """Starts of this rank (every world-th start of the descending-work order, so the ranks'
-        loads match), cut into launches bounded by the hash budget."""
-        order = self.order[rank::world] if world > 1 else self.order
-        if order.numel() == 0:
-            return
-        cum = torch.cumsum(self.start_bytes[order], 0).cpu()
-        lo, n = 0, order.numel()
-        while lo < n:
-            base = int(cum[lo - 1]) if lo else 0
-            hi = int(torch.searchsorted(cum, torch.tensor(base + self.hash_budget)))
-            hi = min(max(hi, lo + 1), n)
-            yield order[lo:hi]
-            lo = hi
-
-    def _launch(self, sel, mode, out, emit=None):
-        """Run accumulate -> merge rounds -> finalize over the starts `sel` (plan indices)."""
-        L = N.lib()
-        p, dev = self.plan, self.device
-        ns = int(sel.numel())
-        G = self.G[sel]
-        units = torch.repeat_interleave(self.u0[sel], G) + \
-            (torch.arange(int(G.sum().item()), device=dev) - torch.repeat_interleave(torch.cumsum(G, 0) - G, G))
-        nu = int(units.numel())
-        first_unit = torch.cumsum(G, 0) - G                       # batch-local index of each start's slice 0
-        hs = self.hsize[units]
-        hoff = torch.cumsum(hs, 0) - hs
-        total = int(hs.sum().item())
-        cells = self._workspace(total)
-        # merge tree
-        g = self.unit_g[units]
-        Gu = torch.repeat_interleave(G, G)
-        loc = torch.arange(nu, device=dev)
-        rounds, pd, ps = [0], [], []
-        r, gmax = 0, int(G.max().item()) if ns else 1
-        while (1 << r) < gmax:
-            m = ((g % (1 << (r + 1))) == 0) & (g + (1 << r) < Gu)
-            d = loc[m]
-            pd.append(d); ps.append(d + (1 << r))
-            rounds.append(rounds[-1] + int(d.numel()))
-            r += 1
-        pair_dst = torch.cat(pd).to(torch.int32) if pd else torch.zeros(0, dtype=torch.int32, device=dev)
-        pair_src = torch.cat(ps).to(torch.int32) if ps else torch.zeros(0, dtype=torch.int32, device=dev)
-        import ctypes as C
-        round_ptr = (C.c_int32 * len(rounds))(*rounds)
+    def _args(self, keep):
+        p = self.plan
         a = N.XsimArgs()
-        keep = [round_ptr]
 
         def P(t):
             t = t.contiguous()
             keep.append(t)
             return N.ptr(t)
-        a.n_starts, a.n_units = ns, nu
-        a.start_item = P(p.start_item[sel]); a.start_unit = P(first_unit.to(torch.int32))
-        a.unit_leg_lo, a.unit_leg_hi = P(self.unit_leg_lo[units]), P(self.unit_leg_hi[units])
-        ucomb = torch.zeros(nu, dtype=torch.int64, device=dev)
-        a.unit_combos = P(ucomb)
-        a.leg_t, a.leg_joint_only = P(p.leg_t), P(p.leg_joint_only)
-        (a.leg_e1, a.leg_m1, a.leg_f1, a.leg_e2, a.leg_m2, a.leg_f2) = [P(v) for v in p.leg_vals]
-        a.par_ptr = P(p.par_ptr); a.par_s = P(p.par_s); a.par_joint = P(p.par_joint)
-        a.par_e, a.par_m, a.par_f = [P(v) for v in p.par_vals]
-        a.rs_ptr = P(p.rs_ptr); a.rs_end = P(self.rs_end)
+        a.n_starts = int(p.start_item.numel())
+        a.unit_leg_lo, a.unit_leg_hi = P(self.unit_leg_lo), P(self.unit_leg_hi)
+        a.unit_g0, a.unit_g1, a.unit_npass = P(self.unit_g0), P(self.unit_g1), P(self.unit_npass)
+        a.start_unit_ptr = P(self.start_unit_ptr)
+        a.lp_ptr, a.leg_par_base, a.leg_npar = P(self.lp_ptr), P(self.leg_par_base), P(self.leg_npar)
+        a.leg_n, a.leg_d, a.leg_c = P(self.leg_n), P(self.leg_d), P(self.leg_c)
+        a.par_s, a.par_e, a.par_m, a.par_f = P(self.par_s), P(self.par_e), P(self.par_m), P(self.par_f)
+        a.rs_ptr, a.rs_end = P(p.rs_ptr), P(self.rs_end)
         a.rs_n, a.rs_d, a.rs_c = [P(v) for v in self.rs_ndc]
-        a.hash_off = P(hoff); a.hash_size = P(hs.to(torch.int32))
-        a.hash_cells = N.ptr(cells)
-        self.epoch += 1
-        a.epoch = self.epoch
-        a.n_rounds = len(rounds) - 1
-        a.round_ptr_h = C.cast(round_ptr, C.c_void_p)
-        a.pair_dst, a.pair_src = P(pair_dst), P(pair_src)
-        a.top_m, a.mode = self.top_m, mode
-        cnt = torch.zeros(ns, dtype=torch.int32, device=dev)
-        te = torch.full((ns, self.top_m), -1, dtype=torch.int32, device=dev)
-        tx = torch.zeros((ns, self.top_m), dtype=torch.float64, device=dev)
-        tl = torch.zeros(ns, dtype=torch.int32, device=dev)
-        a.out_count = P(cnt)
-        a.top_end, a.top_xsim, a.top_len = P(te), P(tx), P(tl)
-        if emit is not None:
-            a.emit_ptr, a.emit_end, a.emit_xsim = P(emit[0]), P(emit[1]), P(emit[2])
+        a.tile_ptr, a.gb = P(self.tile_ptr), self.gb
+        a.cells_lg, a.top_m = self.cells_lg, self.top_m
         a.error_flag = N.ptr(self.error_flag)
-        N.check(L.xmap_xsim_extend(a, torch.cuda.current_stream().cuda_stream), "xmap_xsim_extend")
-        self.launches += 2 + a.n_rounds
-        if mode == 0:
-            comb = torch.zeros(ns, dtype=torch.int64, device=dev)
-            comb.index_add_(0, torch.repeat_interleave(torch.arange(ns, device=dev), G), ucomb)
-            out["count"][sel] = cnt; out["combos"][sel] = comb
-            out["top_end"][sel] = te; out["top_xsim"][sel] = tx; out["top_len"][sel] = tl
-        torch.cuda.current_stream().synchronize()      # the batch's temporaries die here
-        if int(self.error_flag.item()):
-            raise N.NativeError("X-SIM kernel error %d (2: hash overflow, 3: bad table size)"
-                                % int(self.error_flag.item()))
+        return a
 
-    def run(self, rank=0, world=1):
-        """count + top-m for every start of the plan (world > 1: only this rank's starts are filled in;
-        multi.allreduce_xsim assembles the full result on every rank)."""
-        p, dev, n = self.plan, self.device, self.plan.start_item.numel()
-        out = dict(count=torch.zeros(n, dtype=torch.int32, device=dev),
-                   combos=torch.zeros(n, dtype=torch.int64, device=dev),
-                   top_end=torch.full((n, self.top_m), -1, dtype=torch.int32, device=dev),
-                   top_xsim=torch.zeros((n, self.top_m), dtype=torch.float64, device=dev),
-                   top_len=torch.zeros(n, dtype=torch.int32, device=dev))
-        for sel in self._batches(rank, world):
-            self._launch(sel, 0, out)
-        return XsimResult(p.start_item, out["count"], out["combos"], out["top_end"], out["top_xsim"],
-                          out["top_len"], self.launches)
+    def _check(self):
+        e = int(self.error_flag.item())
+        if e:
+            self.error_flag.zero_()
+            raise N.NativeError("X-SIM kernel error %d (2: a pass overflows its table even at one hash tile)" % e)
+
+    def run(self, rank=0, world=1, group=None):
+        """count + top-m for every start of the plan.  world > 1: this rank runs every world-th unit of the
+        descending-work order, the unit results are summed across ranks (each is non-zero on one rank) and
+        every rank merges them, so all ranks return the full, identical result."""
+        L = N.lib()
+        p, dev, n, nu, m = self.plan, self.device, int(self.plan.start_item.numel()), self.n_units, self.top_m
+        keep = []
+        a = self._args(keep)
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+        ucount, ucombos = z(nu, torch.int32), z(nu, torch.int64)
+        ute, utx, utl = z((nu, m), torch.int32), z((nu, m), torch.float64), z(nu, torch.int32)
+        cnt, comb = z(n, torch.int32), z(n, torch.int64)
+        te = torch.full((n, m), -1, dtype=torch.int32, device=dev)
+        tx, tl = z((n, m), torch.float64), z(n, torch.int32)
+        a.unit_count, a.unit_combos = N.ptr(ucount), N.ptr(ucombos)
+        a.unit_top_end, a.unit_top_xsim, a.unit_top_len = N.ptr(ute), N.ptr(utx), N.ptr(utl)
+        a.out_count, a.out_combos = N.ptr(cnt), N.ptr(comb)
+        a.top_end, a.top_xsim, a.top_len = N.ptr(te), N.ptr(tx), N.ptr(tl)
+        order = self.unit_order if world == 1 else self.unit_order[rank::world].contiguous()
+        a.unit_order, a.n_units = N.ptr(order), int(order.numel())
+        a.merge = 1 if world == 1 else 0
+        st = torch.cuda.current_stream().cuda_stream
+        if n and nu:
+            N.check(L.xmap_xsim_extend(a, st), "xmap_xsim_extend")
+            self.launches += 1 + a.merge
+            if world > 1:
+                from .multi import sum_unit_results
+                sum_unit_results((ucount, ucombos, ute, utx, utl), group)
+                N.check(L.xmap_xsim_merge(a, st), "xmap_xsim_merge")
+                self.launches += 1
+        self._check()
+        return XsimResult(p.start_item, cnt, comb, te, tx, tl, self.launches, ucount)
 
     def emit(self, res):
         """Every (start, end, xsim), sorted by (start, end): the materialised return
         value of extender_pipeline (assist.py:80-102)."""
-        p, dev = self.plan, self.device
-        n = p.start_item.numel()
-        ptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
-        ptr[1:] = torch.cumsum(res.count.long(), 0)
-        total = int(ptr[-1].item()) if n else 0
+        L = N.lib()
+        p, dev, nu = self.plan, self.device, self.n_units
+        ptr = torch.zeros(nu + 1, dtype=torch.int64, device=dev)
+        ptr[1:] = torch.cumsum(res.unit_count.long(), 0)
+        total = int(ptr[-1].item()) if nu else 0
         e_end = torch.empty(total, dtype=torch.int32, device=dev)
         e_x = torch.empty(total, dtype=torch.float64, device=dev)
-        for sel in self._batches():
-            self._launch(sel, 2, None, emit=(ptr[:-1][sel].contiguous(), e_end, e_x))
-        start = torch.repeat_interleave(p.start_item.long(), res.count.long())
+        if total:
+            keep = []
+            a = self._args(keep)
+            m = self.top_m
+            z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+            scratch = [z(nu, torch.int32), z(nu, torch.int64), z((nu, m), torch.int32), z((nu, m), torch.float64),
+                       z(nu, torch.int32)]
+            a.unit_count, a.unit_combos, a.unit_top_end, a.unit_top_xsim, a.unit_top_len = [N.ptr(t) for t in scratch]
+            a.unit_order, a.n_units, a.merge = N.ptr(self.unit_order), nu, 0
+            a.emit_ptr, a.emit_end, a.emit_xsim = N.ptr(ptr), N.ptr(e_end), N.ptr(e_x)
+            N.check(L.xmap_xsim_extend(a, torch.cuda.current_stream().cuda_stream), "xmap_xsim_extend(emit)")
+            self.launches += 1
+            self._check()
+            if not torch.equal(scratch[0], res.unit_count):
+                raise N.NativeError("X-SIM emit pass disagrees with the counting pass")
+        start = torch.repeat_interleave(p.start_item.long()[self.unit_start], res.unit_count.long())
         o = torch.argsort(start * p.n_items + e_end.long())
         return start[o], e_end[o].long(), e_x[o]

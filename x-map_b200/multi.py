@@ -15,10 +15,11 @@ the gathers the reference performs as collect + broadcast:
   3. all-gather of the neighbour tables after selection (the collectAsMap +
      broadcast of assist.py:121-132) -- n_items * 2k * 20 bytes.
 
-X-SIM extension shards by start item (starts are independent; every rank builds
-the same plan from the gathered tables and evaluates every world-th start of the
-descending-work order); the per-start top-m rows are summed across ranks (each
-row is non-zero on exactly one rank).  Generation shards by user: the item map is
+X-SIM extension shards by work unit (a start, or one range of the hashed end axis
+of a heavy start: units are independent; every rank builds the same plan from the
+gathered tables and runs every world-th unit of the descending-work order); the
+per-unit results are summed across ranks (each is non-zero on exactly one rank)
+and every rank merges them per start.  Generation shards by user: the item map is
 tiny and replicated, every rank rewrites the ratings of a contiguous block of
 users holding an equal share of the ratings, and the AlterEgo records stay
 sharded (the reference's result is an RDD) unless the caller gathers them.
@@ -190,12 +191,20 @@ def exchange_records(rec, rec_ptr, rec_cnt, shard, group=None):
 def similarity_shard(engine, rank=0, world=1):
     """Row blocks balanced by the cost of both phases: the products a row evaluates (accumulate,
     ~30 ps each) and the records it will have to select from (~1/6 of its list capacity at ~18 ps)."""
-    return RowShard(engine.tri_work + engine.rec_cap // 6, rank, world)
+    return RowShard(engine.tri_work + engine.rec_cap_bound // 6, rank, world)
 
 
 def similarity_step(engine, shard, group=None):
     """Triangular rows of the owned block -> record exchange -> BB flags -> selection -> gather."""
     rows = None if shard.world == 1 else shard.rows(engine.device)
+    if shard.world > 1 and not getattr(engine, "_sizing_agreed", False):
+        # whether the exact-sizing branch (which holds an all-reduce) runs must be the same decision on
+        # every rank: each rank judged its own free memory, so any rank that needs it forces it everywhere
+        need = torch.tensor([1 if engine.rec is None else 0], dtype=torch.int32, device=engine.device)
+        dist.all_reduce(need, op=dist.ReduceOp.MAX, group=group)
+        if int(need.item()) and engine.rec is not None:
+            engine.release_lists()
+        engine._sizing_agreed = True
     if engine.rec is None and shard.world > 1:
         # exact list sizing: a rank's lists hold its own records for every row, plus, for the rows it
         # owns, the records the other ranks will send
@@ -219,15 +228,15 @@ def similarity_step(engine, shard, group=None):
     return engine.tables(dict(accumulate=stats, rows=(shard.lo, shard.hi)), row_nkept=nkept)
 
 
-def allreduce_xsim(res, group=None):
-    """XsimResult filled for this rank's starts only -> the full result on every rank."""
+def sum_unit_results(tensors, group=None):
+    """X-SIM work units are dealt to the ranks (every world-th unit of the descending-work order); a unit's
+    result (distinct ends, paths, top-m list) is non-zero on exactly one rank, so a sum assembles the full
+    unit tables on every rank.  Device-agnostic (NCCL on the GPUs, gloo in the CPU tests)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return res
-    res.top_end.add_(1)                                   # -1 fill -> 0 so that a sum assembles the rows
-    for t in (res.count, res.combos, res.top_end, res.top_xsim, res.top_len):
+        return tensors
+    for t in tensors:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-    res.top_end.sub_(1)
-    return res
+    return tensors
 
 
 class UserShard(object):
