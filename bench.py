@@ -32,7 +32,9 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (users, items/domain, draws, domains, overlap, k)
-    "cfg2": (1_000_000, 200_000, 20_000_000, 2, 0.05, 10),
+    "cfg2": (1_000_000, 200_000, 20_000_000, 2, 0.05, 10),         # BASELINE.json configs[1]
+    "cfg4": (2_000_000, 250_000, 80_000_000, 4, 0.05, 10),         # configs[3]: one source->target pipeline per source domain
+    "cfg4_small": (200_000, 25_000, 8_000_000, 4, 0.05, 10),
     "cfg2_small": (100_000, 20_000, 2_000_000, 2, 0.05, 10),
     "tiny": (20_000, 3_000, 400_000, 2, 0.05, 10),
 }
@@ -43,26 +45,45 @@ NCU_TRAFFIC = {"tri_cta_kernel": 5.857e9 / 14}   # (2.883 GB read + 2.974 GB wri
                                                  # profiles/r1_ncu_full_cfg2.csv; per launch like `achieved`
 
 
-def make_workload(name):
+def _compact(name, sr, keep, k, tag):
+    """One two-domain problem cut from the rating set: users / items renumbered in sorted-id order."""
     from xmap_b200 import synth
     from xmap_b200.encode import item_codes
-    nu, ni, nd, ndom, ov, k = WORKLOADS[name]
-    sr = synth.make_ratings(nu, ni, nd, n_domains=ndom, overlap=ov)
-    present = np.unique(sr.item)
+    user, item, rating, ts = (sr.user, sr.item, sr.rating, sr.ts) if keep is None else \
+        (sr.user[keep], sr.item[keep], sr.rating[keep], sr.ts[keep])
+    present = np.unique(item)
     iids = np.array([synth.item_id(int(g), sr.n_items_per_domain, sr.labels) for g in present])
     order = np.argsort(iids)
     present, iids = present[order], iids[order]
-    imap = np.full(int(sr.item.max()) + 1, -1, dtype=np.int64)
+    imap = np.full(int(item.max()) + 1, -1, dtype=np.int64)
     imap[present] = np.arange(len(present))
-    uu = np.unique(sr.user)
-    umap = np.full(int(sr.user.max()) + 1, -1, dtype=np.int64)
+    uu = np.unique(user)
+    umap = np.full(int(user.max()) + 1, -1, dtype=np.int64)
     umap[uu] = np.arange(len(uu))
     pc, dc, ct, hs, ht = item_codes(iids)
-    du = np.bincount(umap[sr.user]).astype(np.int64)
-    return dict(name=name, user=umap[sr.user].astype(np.int32), item=imap[sr.item].astype(np.int32),
-                rating=sr.rating.astype(np.float32), ts=sr.ts, n_users=len(uu), n_items=len(iids), k=k,
+    du = np.bincount(umap[user]).astype(np.int64)
+    return dict(name=name + tag, user=umap[user].astype(np.int32), item=imap[item].astype(np.int32),
+                rating=rating.astype(np.float32), ts=ts, n_users=len(uu), n_items=len(iids), k=k,
                 meta=dict(prefix_code=pc, dom_code=dc, contains=ct, has_S=hs, has_T=ht),
-                nnz=int(len(sr.user)), W=int((du * (du - 1)).sum()))
+                nnz=int(len(user)), W=int((du * (du - 1)).sum()))
+
+
+def make_pipelines(name):
+    """The two-domain problems of a workload: one for a two-domain shape; for a multi-domain shape one
+    source -> target problem per source domain, cut from ONE rating set, exactly as multidomain_demo.py:101-128
+    runs them (independent pipelines whose AlterEgo records are unioned)."""
+    from xmap_b200 import synth
+    nu, ni, nd, ndom, ov, k = WORKLOADS[name]
+    sr = synth.make_ratings(nu, ni, nd, n_domains=ndom, overlap=ov)
+    if ndom == 2:
+        return [_compact(name, sr, None, k, "")]
+    tgt = ndom - 1
+    return [_compact(name, sr, (sr.domain == d) | (sr.domain == tgt), k, "[%s->T:]" % sr.labels[d]) for d in range(tgt)]
+
+
+def make_workload(name):
+    """First (for a two-domain shape: the only) pipeline of a workload."""
+    return make_pipelines(name)[0]
 
 
 def workload_label(wl, method):
@@ -185,7 +206,7 @@ def run_reference_arm(args, emit):
         return
     wl = make_workload(args.workload)
     vals, secs = [], []
-    cores = min(os.cpu_count() or 1, 32)
+    cores = min(os.cpu_count() or 1, 16)           # fixed ceiling: the denominator must not move with the box size
     for s in range(args.warmup + args.steps):
         t0 = time.perf_counter()
         cb = cpu_baseline(wl, method=args.method, target_ratings=150_000, cores=cores)
@@ -245,12 +266,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    wl = make_workload(args.workload)
-    k = wl["k"]
-    meta = to_device_meta(wl["meta"], dev)
+    pipes = make_pipelines(args.workload)
+    k = pipes[0]["k"]
     pin = lambda a: torch.from_numpy(a).pin_memory()
-    h_user, h_item, h_rating = pin(wl["user"]), pin(wl["item"]), pin(wl["rating"])
-    h2d_bytes = h_user.numel() * 4 * 3
+    for wl in pipes:
+        wl["dmeta"] = to_device_meta(wl["meta"], dev)
+        wl["h"] = (pin(wl["user"]), pin(wl["item"]), pin(wl["rating"]))
+    h2d_bytes = sum(wl["h"][0].numel() * 4 * 3 for wl in pipes)
+    W_total, nnz_total, I_total = (sum(wl[q] for wl in pipes) for q in ("W", "nnz", "n_items"))
 
     def barrier():
         torch.cuda.synchronize()
@@ -258,52 +281,81 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # resident layout for the device-timed metric
-    lay = E.build_layout(h_user, h_item, h_rating, wl["n_users"], wl["n_items"], device=dev)
-    eng = E.SimEngine(lay, meta, args.method, 50, k)
-    shard = MG.similarity_shard(eng, rank, world)
+    # resident layouts + engines for the device-timed metric (one per source -> target pipeline); the record lists of
+    # several engines must fit together, so each gets an equal share of the free memory (else: exact sizing pass)
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    budget = None if len(pipes) == 1 else int(free_b * 0.6 / len(pipes))
+    for wl in pipes:
+        wl["lay"] = E.build_layout(*wl["h"], wl["n_users"], wl["n_items"], device=dev)
+        wl["eng"] = E.SimEngine(wl["lay"], wl["dmeta"], args.method, 50, k, rec_budget=budget)
+        wl["shard"] = MG.similarity_shard(wl["eng"], rank, world)
 
-    def sim_step(engine):
-        return MG.similarity_step(engine, shard)
+    def sim_step():
+        return [MG.similarity_step(wl["eng"], wl["shard"]) for wl in pipes]
 
     for _ in range(args.warmup):
-        sim_step(eng)
+        sim_step()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    l0 = eng.launches
+    l0 = sum(wl["eng"].launches for wl in pipes)
     barrier()
     for s in range(args.steps):
         ev[s][0].record()
-        tabs = sim_step(eng)
+        tabs_all = sim_step()
         ev[s][1].record()
     barrier()
     clocks = sampler.summary()
-    eng._check_error()
-    launches = (eng.launches - l0)
+    for wl in pipes:
+        wl["eng"]._check_error()
+    launches = sum(wl["eng"].launches for wl in pipes) - l0
     # per-kernel CUDA-event times: a second set of steps with every launch serialised on one stream
-    eng.enable_profile()
+    for wl in pipes:
+        wl["eng"].enable_profile()
     for s in range(args.steps):
-        sim_step(eng)
-    prof = eng.profile_ms()
-    eng.profile = None
+        sim_step()
+    prof = {}
+    for wl in pipes:
+        for kk, (n, ms_k) in wl["eng"].profile_ms().items():
+            prof[kk] = (prof.get(kk, (0, 0.0))[0] + n, prof.get(kk, (0, 0.0))[1] + ms_k)
+        wl["eng"].profile = None
     barrier()
     ms = torch.tensor([a.elapsed_time(b) for a, b in ev], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms.mean())
-    P_total = tabs.n_pairs_total
-    P_kept = int(tabs.row_nkept.sum().item())
+    P_total = sum(t.n_pairs_total for t in tabs_all)
+    P_kept = sum(int(t.row_nkept.sum().item()) for t in tabs_all)
     value = P_total / (ms_step * 1e-3)
+
+    # multi-GPU parity, carried in the line: rank 0 runs the single-GPU stage (untimed) on the first pipeline and
+    # compares every table, later the X-SIM top-m and the item map, bit for bit
+    multi_parity, ref_tabs = None, None
+    if world > 1:
+        ok = True
+        if rank == 0:
+            wl = pipes[0]
+            ref_eng = E.SimEngine(wl["lay"], wl["dmeta"], args.method, 50, k, rec_budget=budget)
+            ref_tabs = ref_eng.run()
+            ok = all(torch.equal(getattr(ref_tabs, f), getattr(tabs_all[0], f)) for f in
+                     ("row_flags", "row_npairs", "row_nkept", "tab_len", "tab_idx", "tab_sim", "tab_mutu", "tab_n"))
+            ref_eng._give_back()
+            del ref_eng
+        multi_parity = {"similarity_tables": bool(ok)}
+        barrier()
 
     # e2e: host triples -> layout -> similarity -> neighbour tables back on the host
     def e2e_step():
-        lay2 = E.build_layout(h_user, h_item, h_rating, wl["n_users"], wl["n_items"], device=dev)
-        eng2 = E.SimEngine(lay2, meta, args.method, 50, k)
-        t = MG.similarity_step(eng2, MG.similarity_shard(eng2, rank, world))
-        out = eng2.tables_to_host(t, reuse=True)                 # pinned host buffers, synchronises
-        return sum(o.numel() * o.element_size() for o in out.values())
+        nb = 0
+        for wl in pipes:
+            lay2 = E.build_layout(*wl["h"], wl["n_users"], wl["n_items"], device=dev)
+            eng2 = E.SimEngine(lay2, wl["dmeta"], args.method, 50, k, rec_budget=budget)
+            t = MG.similarity_step(eng2, MG.similarity_shard(eng2, rank, world))
+            out = eng2.tables_to_host(t, reuse=True)     # pinned host buffers, synchronises
+            nb += sum(o.numel() * o.element_size() for o in out.values())
+            eng2._give_back()
+        return nb
     e2e_step()
     n_e2e = max(3, min(args.steps, 7))
     e2e_times = []
@@ -319,47 +371,70 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_val = P_total / float(e2e_s)
 
-    # pipeline wall-time: similarity + X-SIM extension (sharded by start) + generation (sharded by user)
+    # pipeline wall-time: similarity + X-SIM extension (sharded by work unit) + generation (sharded by user), per
+    # source -> target pipeline, summed
     pipe = None
     for timed in ((False, True, True) if not args.no_pipeline else ()):  # one untimed pass, then the faster of two
-        barrier()
-        t0 = time.perf_counter()
-        plan = X.build_plan(tabs, lay.item_stats[:, 3].contiguous(), meta.has_S, meta.has_T)
-        torch.cuda.synchronize(); t1 = time.perf_counter()
-        xe = X.XsimEngine(plan, 10)
-        res = xe.run(rank, world)
-        barrier(); t2 = time.perf_counter()
-        ch = G.choose_mapping(res, "argmax", sim_method=args.method)
-        mp = G.invert_mapping(res.start_item, ch, wl["n_items"])
-        ou, oi, orr, ot = MG.build_alterego_sharded(lay, wl["ts"], mp, MG.UserShard(lay.csr_ptr, rank, world))
-        n_rec = torch.tensor([ou.numel()], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(n_rec)
-        barrier(); t3 = time.perf_counter()
-        combos = int(res.combos.sum().item())
-        if not timed or (pipe is not None and pipe["alterego_pipeline_ms"] <= ms_step + (t3 - t0) * 1e3):
+        acc = dict(plan=0.0, xsim=0.0, xsim_kernel=0.0, gen=0.0, combos=0, starts=0, pairs=0, recs=0, src=0, joint=0, units=0)
+        for q, wl in enumerate(pipes):
+            lay, meta, tabs = wl["lay"], wl["dmeta"], tabs_all[q]
+            barrier()
+            t0 = time.perf_counter()
+            plan = X.build_plan(tabs, lay.item_stats[:, 3].contiguous(), meta.has_S, meta.has_T)
+            torch.cuda.synchronize(); t1 = time.perf_counter()
+            xe = X.XsimEngine(plan, 10)
+            torch.cuda.synchronize(); t1b = time.perf_counter()
+            res = xe.run(rank, world)
+            barrier(); t2 = time.perf_counter()
+            ch = G.choose_mapping(res, "argmax", sim_method=args.method)
+            mp = G.invert_mapping(res.start_item, ch, wl["n_items"])
+            ou, oi, orr, ot = MG.build_alterego_sharded(lay, wl["ts"], mp, MG.UserShard(lay.csr_ptr, rank, world))
+            n_rec = torch.tensor([ou.numel()], dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.all_reduce(n_rec)
+            barrier(); t3 = time.perf_counter()
+            acc["plan"] += t1 - t0; acc["xsim"] += t2 - t1; acc["xsim_kernel"] += t2 - t1b; acc["gen"] += t3 - t2
+            acc["combos"] += int(res.combos.sum().item()); acc["starts"] += int(res.start_item.numel())
+            acc["pairs"] += int(res.count.sum().item()); acc["recs"] += int(n_rec.item())
+            acc["src"] += plan.n_src; acc["joint"] += plan.n_joint; acc["units"] += xe.n_units
+            if world > 1 and q == 0 and multi_parity is not None and "xsim_top_m" not in multi_parity:
+                ok = True
+                if rank == 0:
+                    plan1 = X.build_plan(ref_tabs, lay.item_stats[:, 3].contiguous(), meta.has_S, meta.has_T)
+                    res1 = X.XsimEngine(plan1, 10).run()
+                    ok = all(torch.equal(getattr(res1, f), getattr(res, f)) for f in
+                             ("count", "combos", "top_end", "top_xsim", "top_len"))
+                    mp1 = G.invert_mapping(res1.start_item, G.choose_mapping(res1, "argmax", sim_method=args.method), wl["n_items"])
+                    multi_parity["item_map"] = bool(torch.equal(mp1, mp))
+                    del plan1, res1
+                multi_parity["xsim_top_m"] = bool(ok)
+                barrier()
             del plan, xe, res
+        total_ms = ms_step + (acc["plan"] + acc["xsim"] + acc["gen"]) * 1e3
+        if not timed or (pipe is not None and pipe["alterego_pipeline_ms"] <= total_ms):
             continue
-        pipe = {"similarity_ms": ms_step, "extend_plan_ms": (t1 - t0) * 1e3, "extend_kernel_ms": (t2 - t1) * 1e3,
-                "generate_ms": (t3 - t2) * 1e3,
-                "alterego_pipeline_ms": ms_step + (t3 - t0) * 1e3,
-                "xsim_paths": combos, "xsim_paths_per_s": combos / max(t2 - t1, 1e-9),
-                "xsim_starts": int(res.start_item.numel()), "xsim_pairs": int(res.count.sum().item()),
-                "alterego_synthetic_records": int(n_rec.item()), "bridge_pairs": plan.n_src,
-                "joint_pairs": plan.n_joint,
-                "sharding": "X-SIM by start item x%d, generation by user x%d (host wall-clock of rank 0 between barriers, "
+        pipe = {"similarity_ms": ms_step, "extend_plan_ms": acc["plan"] * 1e3, "extend_kernel_ms": acc["xsim"] * 1e3,
+                "extend_engine_build_ms": (acc["xsim"] - acc["xsim_kernel"]) * 1e3, "xsim_kernels_ms": acc["xsim_kernel"] * 1e3,
+                "generate_ms": acc["gen"] * 1e3, "alterego_pipeline_ms": total_ms,
+                "xsim_paths": acc["combos"], "xsim_paths_per_s": acc["combos"] / max(acc["xsim_kernel"], 1e-9),
+                "xsim_starts": acc["starts"], "xsim_pairs": acc["pairs"], "xsim_units": acc["units"],
+                "alterego_synthetic_records": acc["recs"], "bridge_pairs": acc["src"], "joint_pairs": acc["joint"],
+                "pipelines": len(pipes),
+                "sharding": "X-SIM by work unit x%d, generation by user x%d (host wall-clock of rank 0 between barriers, "
                             "faster of two passes after one untimed pass)" % (world, world)}
-        del plan, xe, res
+    if multi_parity is not None:
+        flag = torch.tensor([1 if all(multi_parity.values()) else 0], device=dev)
+        dist.broadcast(flag, 0)
+        multi_parity["all"] = bool(flag.item())
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
         # the stage evaluates every unordered pair once: W/2 products of 8 B, one pass over the CSC
-        # (24 B per rating: entry + suffix extent + rater mean), 2 x 16 B records written and read back per kept pair,
+        # (24 B per rating: entry + suffix extent + rater mean), 2 x 20 B records written and read back per kept pair,
         # and the tables out
-        alg_bytes = 8.0 * (wl["W"] / 2) + 24.0 * wl["nnz"] + 32.0 * P_kept + 80.0 * k * wl["n_items"]
+        alg_bytes = 8.0 * (W_total / 2) + 24.0 * nnz_total + 40.0 * P_kept + 80.0 * k * I_total
         stage_gbs = alg_bytes / (ms_step * 1e-3) / 1e9
         # kernels: the accumulate launches are one kernel function per group width
-        launches_plan, _, split_plan = eng.plan(None if world == 1 else shard.rows(dev))
         fam_ms, fam_n, fam_bytes = {}, {}, {}
         for kk, (n, ms_k) in prof.items():
             if kk.startswith("accumulate_c") or kk.startswith("accumulate_g"):
@@ -374,16 +449,20 @@ def main():
                 fam = kk
             fam_ms[fam] = fam_ms.get(fam, 0.0) + ms_k
             fam_n[fam] = fam_n.get(fam, 0) + n
-        for r, cells_cap, threads, in_gmem, _hdr in launches_plan:
-            fam = "tri_gmem_kernel" if in_gmem else ("tri_warp_kernel" if threads == 32 else "tri_cta_kernel")
-            fam_bytes[fam] = fam_bytes.get(fam, 0.0) + 8.0 * float(eng.tri_work[r.long()].sum().item())
-        if split_plan is not None:
-            fam_bytes["tri_split_kernel"] = 8.0 * float(eng.tri_work[split_plan["rows"].long()].sum().item())
-        long_rows = tabs.row_nkept > 8192
-        fam_bytes["select_cta_kernel"] = 16.0 * float(tabs.row_nkept[long_rows].sum().item())
-        fam_bytes["select_warp_kernel"] = 16.0 * float(tabs.row_nkept[~long_rows].sum().item())
+        for q, wl in enumerate(pipes):
+            eng, tabs = wl["eng"], tabs_all[q]
+            launches_plan, _, split_plan = eng.plan(None if world == 1 else wl["shard"].rows(dev))
+            for r, cells_cap, threads, in_gmem, _hdr in launches_plan:
+                fam = "tri_gmem_kernel" if in_gmem else ("tri_warp_kernel" if threads == 32 else "tri_cta_kernel")
+                fam_bytes[fam] = fam_bytes.get(fam, 0.0) + 8.0 * float(eng.tri_work[r.long()].sum().item())
+            if split_plan is not None:
+                fam_bytes["tri_split_kernel"] = fam_bytes.get("tri_split_kernel", 0.0) + \
+                    8.0 * float(eng.tri_work[split_plan["rows"].long()].sum().item())
+            long_rows = tabs.row_nkept > 8192
+            fam_bytes["select_cta_kernel"] = fam_bytes.get("select_cta_kernel", 0.0) + 16.0 * float(tabs.row_nkept[long_rows].sum().item())
+            fam_bytes["select_warp_kernel"] = fam_bytes.get("select_warp_kernel", 0.0) + 16.0 * float(tabs.row_nkept[~long_rows].sum().item())
         kinds = {kk: (fam_n[kk], fam_ms[kk]) for kk in fam_ms}
-        dom = max(kinds, key=lambda kk: kinds[kk][1])
+        dom = max((kk for kk in kinds if kk in fam_bytes), key=lambda kk: kinds[kk][1])
         dom_bytes_step = fam_bytes.get(dom, 0.0)
         dom_ms_step = kinds[dom][1] / args.steps
         achieved = dom_bytes_step / (dom_ms_step * 1e-3) / 1e9 if dom_ms_step > 0 else 0.0
@@ -391,7 +470,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "item pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64 epilogue over i64 fixed-point accumulators", "data": "synthetic",
-            "config": {"workload": workload_label(wl, args.method),
+            "config": {"workload": " + ".join(workload_label(wl, args.method) for wl in pipes),
                        "pairs_evaluated": P_total, "pairs_kept": P_kept,
                        "l2_policy": "inputs (CSR+CSC+tables) larger than L2; no explicit flush",
                        "parallelism": "item row-blocks x%d, ratings replicated, neighbour records exchanged" % world},
@@ -413,11 +492,24 @@ def main():
                                    "side stream" % args.steps,
                          "note": "achieved = algorithmic bytes of the kernel (8 B per co-rating product for the "
                                  "accumulate kernels, 16 B per neighbour record for the selection kernels) / its "
-                                 "CUDA-event time; stage figure = (8*W/2 + 24*nnz + 32*P_kept + 80*k*I) / step time"},
+                                 "CUDA-event time; stage figure = (8*W/2 + 24*nnz + 40*P_kept + 80*k*I) / step time"},
             "pipeline": pipe,
         }
+        if pipe is not None:
+            # the X-SIM kernel is the other half of BASELINE.json's metric (pipeline wall-time): SURVEY.md 8(d) counts
+            # 16 B of accumulator read-modify-write per path; here the accumulators never leave shared memory, so the
+            # figure is an equivalent-traffic rate, next to the 28 B right-segment read each path really makes
+            xk = pipe["xsim_kernels_ms"] * 1e-3
+            gb16, gb28 = 16.0 * pipe["xsim_paths"] / xk / 1e9, 28.0 * pipe["xsim_paths"] / xk / 1e9
+            line["pipeline_roofline"] = {"kernel": "xsim_warp_kernel", "bound": "hbm", "achieved": gb16, "peak": peaks["hbm_gbs"],
+                                         "unit": "GB/s", "frac": gb16 / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC.get("xsim_warp_kernel"),
+                                         "algorithmic_bytes_per_path": 16, "paths": pipe["xsim_paths"],
+                                         "kernel_ms": pipe["xsim_kernels_ms"], "right_segment_read_gbs": gb28,
+                                         "note": "host wall-clock around the kernel launches + merge (max over ranks via the barrier)"}
+        if multi_parity is not None:
+            line["multi_parity"] = multi_parity
         if not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(wl, args.method)
+            line["cpu_baseline"] = cpu_baseline(pipes[0], args.method)
         emit(line)
     if world > 1:
         dist.barrier()

@@ -16,7 +16,7 @@
  *     return without synchronising unless stated;
  *   - return value 0 = ok, otherwise an error whose text xmap_last_error()
  *     returns (thread-local);
- *   - items and users are dense int32 indices; item index < 2^24.
+ *   - items and users are dense int32 indices; item index < 2^24 (the 8-byte rating entries carry 24-bit items).
  */
 #ifndef XMAP_B200_H
 #define XMAP_B200_H
@@ -108,9 +108,11 @@ int xmap_build_tri_layout(const int32_t *csr_ptr, const uint64_t *csr_ent,
  * co-rated with i, accumulates over the common raters n_ij, the mutuality count
  * and the inner product (64-bit fixed point, order-independent), computes
  * sim / mutu, applies the reference's filter (sim != 0 and mutu != 0) and
- * appends one 16-byte neighbour record to the list of row i AND to the list of
+ * appends one neighbour record to the list of row i AND to the list of
  * row j (sim(i,j) == sim(j,i) bitwise, so the pair is never evaluated twice):
- *   rec[rec_ptr[r] + p] = { bits of sim (f64) , other_item | n<<24 | mutu<<44 }
+ *   rec[rec_ptr[r] + p]   = { bits of sim (f64) , other_item | mutu<<32 }   (16 bytes)
+ *   rec_n[rec_ptr[r] + p] = n  (co-rating count; a parallel int32 array that only the winners of the
+ *                               selection read, so item index, n and mutu are full 32-bit values)
  *   p = atomic cursor rec_cnt[r]; order within a list is unspecified.
  * The lists are the materialised return value of baseliner_calculate_sim_pipeline
  * (assist.py:66-77).  bb[r] is set to 1 for both ends of a kept cross-domain pair
@@ -135,6 +137,7 @@ typedef struct xmap_sim_args {
     const int32_t *csc_ptr; const uint64_t *csc_ent; const void *csc_aux;
     const uint64_t *tcsr_ent;
     const void *ostat; const int32_t *ord; const int64_t *tri_work;
+    const int32_t *ord_item;       /* [n_items] inverse of ord: the item ranked o-th by popularity */
     /* per-item codes (host-computed from the id strings) */
     const uint8_t *dom_code;       /* iid[-2:] -- extender.py:29     */
     const uint8_t *contains;       /* bit d: label d is a substring of iid -- extender.py:32,34 */
@@ -144,7 +147,8 @@ typedef struct xmap_sim_args {
     /* neighbour-record lists */
     const int64_t *rec_ptr;        /* [n_items + 1] list extents (capacity) */
     int32_t *rec_cnt;              /* [n_items] cursors = list lengths */
-    void *rec;                     /* 16-byte records */
+    void *rec;                     /* 16-byte records {f64 sim, u32 other item | u32 mutu << 32} */
+    int32_t *rec_n;                /* co-rating count n of every record (same extents as rec) */
     uint8_t *bb;                   /* [n_items] bridge-item flags */
     int32_t *row_npairs;           /* [n_items] */
     /* selection output: tables [n_items][2][k] */
@@ -197,6 +201,9 @@ int xmap_sim_select(const xmap_sim_args *args_h, const int32_t *rows, int32_t n_
  * reduceByKey shuffle of baselinerSim.py:210-211, 232-233. */
 int xmap_segmented_copy16(const void *src, const int64_t *src_pos, void *dst, const int64_t *dst_pos,
                           const int64_t *seg_off, int32_t n_seg, int64_t total, void *stream);
+/* the same for 4-byte elements (the rec_n array travels with the records) */
+int xmap_segmented_copy4(const void *src, const int64_t *src_pos, void *dst, const int64_t *dst_pos,
+                         const int64_t *seg_off, int32_t n_seg, int64_t total, void *stream);
 
 /* ---------------------------------------------------------------------------
  * (3) X-SIM extension: masked path composition with fused aggregation and top-m.
@@ -211,22 +218,23 @@ int xmap_segmented_copy16(const void *src, const int64_t *src_pos, void *dst, co
  * (extender.py:198-201) in a SHARED-MEMORY hash table, never materialising paths and never touching a
  * global accumulator cell.
  *
- * Work unit = one CTA = (start, a run of passes).  The end axis is hashed, pi(y) = (uint32)(y * 0x9E3779B1),
- * and cut into 2^gb tiles by the top gb bits of pi; a pass covers a range of tiles chosen so that its
- * distinct ends fit the table of 2^cells_lg cells.  Every rseg list is stored sorted by pi and
- * tile_ptr[s * (2^gb + 1) + g] = number of entries of list s in tiles < g gives the sub-range of a pass
- * without a search.  A pass that overflows its table is split in two on the device and redone, down to
- * one tile (then error 2).  Inside a pass the paths are produced by all
- * warps and routed through shared memory to the warp that owns the end's table region, which applies
- * them one by one in path order (leg, partner, rseg): no atomics, and the summation order of every
- * (start, end) is a function of the path structure only, hence bit-identical for any pass split,
- * table size or number of GPUs.
+ * Work unit = (start, a run of passes), run by ONE WARP with a private table of 2^cells_lg cells in
+ * shared memory.  The end axis is hashed, pi(y) = (uint32)(y * 0x9E3779B1), and cut into 2^gb tiles by the
+ * top gb bits of pi; a pass covers a range of tiles chosen so that its distinct ends fit the table.  Every
+ * rseg list is stored sorted by pi and tile_ptr[s * (2^gb + 1) + g] = number of entries of list s in
+ * tiles < g gives the sub-range of a pass without a search.  A pass that overflows its table is split in
+ * two on the device and redone, down to one tile (then error 2).  Lanes that hit the same end in one
+ * 32-path step are combined in lane (= path) order by the lowest lane, which updates the cell with plain
+ * loads and stores: no atomics on values, no block barrier, and the summation order of every (start, end)
+ * is a function of the path structure and the pass plan only, hence bit-identical for any number of GPUs.
  * ------------------------------------------------------------------------- */
-#define XMAP_XSIM_MAX_CELLS_LG 13             /* 8192 cells x 20 B + 46 KB of staging = 209 KB of shared memory */
+#define XMAP_XSIM_MAX_CELLS_LG 13             /* per-warp table: warps x (2^cells_lg x 20 B + 2.9 KB) <= 227 KB */
 typedef struct xmap_xsim_args {
     int32_t n_starts;                         /* start items covered by the units */
-    int32_t n_units;                          /* CTAs of this launch */
-    const int32_t *unit_order;                /* [n_units] CTA b runs unit unit_order[b] (NULL: b); ids index the unit arrays */
+    int32_t n_units;                          /* units of this launch */
+    const int32_t *unit_order;                /* [n_units] the q-th unit fetched is unit_order[q] (NULL: q); ids index the unit arrays */
+    int32_t *unit_counter;                    /* device int: the fetch counter (zeroed by the call) */
+    int32_t warps;                            /* warps per CTA, warps * 32 <= 640 */
     const int64_t *unit_leg_lo, *unit_leg_hi; /* leg range of the unit's start */
     const int32_t *unit_g0, *unit_g1;         /* the unit's range of hash tiles, 0 <= g0 < g1 <= 2^gb ... */
     const int32_t *unit_npass;                /* ... which it covers in npass equal passes (<= g1 - g0) */
@@ -241,7 +249,10 @@ typedef struct xmap_xsim_args {
     const int32_t *rs_end;                    /* per right segment: end item, sorted by pi within a list */
     const double *rs_n, *rs_d, *rs_c;         /* sum sim*mutu, sum mutu, prod frac of its edges */
     const int32_t *tile_ptr; int32_t gb;
-    int32_t cells_lg;                         /* log2 of the table size, 9 .. XMAP_XSIM_MAX_CELLS_LG */
+    int32_t cells_lg;                         /* log2 of a warp's shared-memory table size, 6 .. XMAP_XSIM_MAX_CELLS_LG */
+    const int32_t *unit_clg;                  /* [n_units] log2 of the table a unit wants (NULL: cells_lg); a unit wanting more
+                                               * than cells_lg runs with its table in the warp's slot of the global workspace */
+    void *gws; int32_t gcells_lg;             /* workspace: (SMs x warps) slots of 20 B << gcells_lg (NULL: shared memory only) */
     int32_t top_m;                            /* <= XMAP_KMAX */
     int32_t merge;                            /* 1: also run the per-start merge of the unit results */
     /* per unit: distinct ends, paths, top-m by |xsim| (ties to the smaller end) */
@@ -255,7 +266,7 @@ typedef struct xmap_xsim_args {
     int32_t *error_flag;                      /* 2: a pass overflowed at the finest split */
 } xmap_xsim_args;
 
-int64_t xmap_xsim_smem_bytes(int32_t cells_lg);
+int64_t xmap_xsim_smem_bytes(int32_t cells_lg, int32_t warps);
 int xmap_xsim_extend(const xmap_xsim_args *args_h, void *stream);
 /* only the per-start merge (multi-GPU: after the unit results of all ranks have been summed) */
 int xmap_xsim_merge(const xmap_xsim_args *args_h, void *stream);

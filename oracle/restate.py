@@ -104,6 +104,48 @@ def sim_pairs(user, item, rating, n_users, n_items, prefix_code,
                 i_all=i, j_all=j, stats=st)
 
 
+def sim_rows(user, item, rating, n_users, n_items, prefix_code, rows,
+             method="adjust_cosine", num_atleast=50):
+    """sim_pairs restricted to the directed pairs (i, j) with i in `rows` (a 1-D array of item indices):
+    the same arithmetic on R^T R[rows, :], so that a full-size input (BASELINE.json configs[1]) can be
+    checked on a sample of item rows within host memory.  Returns the kept pairs sorted by (i, j) and,
+    per sampled row, the number of co-rated columns (pre-filter)."""
+    rows = np.unique(np.asarray(rows, dtype=np.int64))
+    order = np.lexsort((item, user))
+    user, item, rating = user[order], item[order], rating[order]
+    st = user_item_stats(user, item, rating, n_users, n_items)
+    r = rating.astype(np.float64)
+    shape = (n_users, n_items)
+    if method == "adjust_cosine":
+        val, den = r - st["mu"][user], st["adj_norm2"]
+    elif method == "cosine":
+        val, den = r, st["norm2"]
+    else:
+        raise ValueError(method)
+    a = (r >= st["avg"][item]).astype(np.float64)
+    mk = lambda v: sp.csr_matrix((v, (user, item)), shape=shape)
+    M, C, A, B = mk(np.ones(len(user))), mk(val), mk(a), mk(1.0 - a)
+    sub = lambda X: X.tocsc()[:, rows].T.tocsr()                     # [len(rows), n_users]
+    N = (sub(M) @ M).tocoo()
+    ri, j = N.row.astype(np.int64), N.col.astype(np.int64)
+    i = rows[ri]
+    keep = i != j
+    ri, i, j, n = ri[keep], i[keep], j[keep], np.rint(N.data[keep])
+    o = np.lexsort((j, i))
+    ri, i, j, n = ri[o], i[o], j[o], n[o]
+    inner = np.asarray((sub(C) @ C).tocsr()[ri, j]).ravel()
+    mutu = np.rint(np.asarray((sub(A) @ A + sub(B) @ B).tocsr()[ri, j]).ravel())
+    dd = den[i] * den[j]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        cosv = np.where(dd != 0, 1.0 * inner / dd, 0.0)
+    sim = 1.0 * cosv * np.minimum(n, num_atleast) / num_atleast
+    frac = 1.0 * mutu / (st["count"][i] + st["count"][j] - n)
+    kept = (sim != 0.0) & (mutu != 0.0) & (frac != 0.0)
+    label = (prefix_code[i] != prefix_code[j]).astype(np.int32)
+    return dict(rows=rows, i=i[kept], j=j[kept], sim=sim[kept], mutu=mutu[kept], n=n[kept], frac=frac[kept],
+                label=label[kept], n_cols=np.bincount(ri, minlength=len(rows)), stats=st)
+
+
 def _matmul_keep_zeros(At, B):
     """At @ B where stored zeros in the operands do not change the pattern of
     interest; returns a CSR matrix that can be fancy-indexed."""

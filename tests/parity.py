@@ -314,6 +314,43 @@ def eval_plan_numpy(plan):
     return np.array(S)[o], np.array(E)[o], np.array(X)[o], combos
 
 
+def eval_plan_starts(plan, starts):
+    """X-SIM rows of a few starts (plan indices) evaluated in numpy straight from the plan arrays, one start
+    at a time with the terms of a cell in path order: {start index: (ends sorted, xsim, n_paths)}.  Checks
+    the kernel at sizes where the whole extension cannot be evaluated on the host."""
+    p = plan
+    g = lambda t: t.cpu().numpy()
+    leg_ptr, leg_t, leg_jo = g(p.leg_ptr), g(p.leg_t), g(p.leg_joint_only)
+    lv = [g(v) for v in p.leg_vals]
+    par_ptr, par_s, par_j = g(p.par_ptr), g(p.par_s), g(p.par_joint)
+    pv = [g(v) for v in p.par_vals]
+    rs_ptr, rs_end = g(p.rs_ptr), g(p.rs_end)
+    rv = [g(v) for v in p.rs_vals]
+    rN, rD, rC = rv[0] + rv[3], rv[1] + rv[4], rv[2] * rv[5]
+    out = {}
+    for x in starts:
+        Y, NUM, DEN = [], [], []
+        for lg in range(leg_ptr[x], leg_ptr[x + 1]):
+            t = leg_t[lg]
+            Nl = lv[0][lg] + lv[3][lg]; Dl = lv[1][lg] + lv[4][lg]; Cl = lv[2][lg] * lv[5][lg]
+            for pp in range(par_ptr[t], par_ptr[t + 1]):
+                if leg_jo[lg] and not par_j[pp]:
+                    continue
+                s = par_s[pp]
+                a, b = rs_ptr[s], rs_ptr[s + 1]
+                Nn = (Nl + pv[0][pp]) + rN[a:b]
+                Dd = (Dl + pv[1][pp]) + rD[a:b]
+                cp = (Cl * pv[2][pp]) * rC[a:b]
+                with np.errstate(invalid="ignore", divide="ignore"):
+                    sp = np.where(Dd != 0, Nn / Dd, 0.0)
+                Y.append(rs_end[a:b]); NUM.append(sp * cp); DEN.append(cp)
+        Y = np.concatenate(Y); NUM = np.concatenate(NUM); DEN = np.concatenate(DEN)
+        o = np.argsort(Y, kind="stable")
+        uy, first = np.unique(Y[o], return_index=True)
+        out[int(x)] = (uy, np.add.reduceat(NUM[o], first) / np.add.reduceat(DEN[o], first), len(Y))
+    return out
+
+
 def compare_xsim(start, end, val, ref_start, ref_end, ref_val, rtol=SIM_RTOL):
     """(start, end) key set identical; values within rtol."""
     assert len(start) == len(ref_start), "X-SIM pair count %d != %d" % (len(start), len(ref_start))

@@ -67,12 +67,17 @@ def test_xsim_vs_restatement_and_pass_splits():
     assert int(res.combos.sum()) == X["combos"]
     assert np.array_equal(np.bincount(np.searchsorted(res.start_item.cpu().numpy(), X["start"]),
                                       minlength=len(res.count)), res.count.cpu().numpy())
-    variants = dict(small_tables=dict(cells_lg=9), many_units=dict(unit_work=500),
-                    device_splits=dict(cells_lg=9, rho=1e9), both=dict(cells_lg=10, unit_work=300, rho=3.0))
+    variants = dict(small_tables=dict(cells_lg=6, max_passes=10 ** 9), many_units=dict(unit_work=500),
+                    global_tables=dict(cells_lg=6, max_passes=1), big_tables=dict(cells_lg=11, warps=4),
+                    device_splits=dict(cells_lg=6, rho=1e9, max_passes=10 ** 9),
+                    global_splits=dict(cells_lg=6, rho=1e9, max_passes=2),
+                    both=dict(cells_lg=7, unit_work=300, rho=3.0, warps=5))
     for name, kw in variants.items():
         plan2, xe2, res2, (s2, e2, v2) = PT.run_gpu_extend(out["tabs"], out["lay"], case["meta"], **kw)
         if name == "small_tables":
-            assert int(xe2.T.max()) > 1
+            assert int(xe2.T.max()) > 1 and xe2.gws is None
+        if name == "global_tables":
+            assert xe2.gws is not None and int(xe2.T.max()) == 1
         if name == "many_units":
             assert xe2.n_units > plan2.start_item.numel()
         assert np.array_equal(s, s2) and np.array_equal(e, e2), name

@@ -65,9 +65,13 @@ def test_engine_host_helpers():
     assert E.r2_bits_for("cosine", 0.0, 0.0) == 0
     assert [E._threads_for_cells(c) for c in (32, 256, 512, 1024, 1536, 4096, 12288)] == [32, 32, 64, 128, 192, 512, 512]
     E._REC_POOL.pop("cpu", None)
-    a = torch.empty((100, 2), dtype=torch.int64); b = torch.empty((1000, 2), dtype=torch.int64)
+    a = torch.empty(E._rec_words(100), dtype=torch.int64); b = torch.empty(E._rec_words(1000), dtype=torch.int64)
     E._REC_POOL["cpu"] = [b, a]
     assert E._rec_buffer(50, "cpu") is a and E._rec_buffer(500, "cpu") is b and E._REC_POOL["cpu"] == []
     E._REC_POOL["cpu"] = [a]
     t = E._rec_buffer(5000, "cpu")
-    assert tuple(t.shape) == (5000, 2) and E._REC_POOL["cpu"] == []     # too small: dropped, a fresh one allocated
+    assert t.numel() == E._rec_words(5000) and E._REC_POOL["cpu"] == []     # too small: dropped, a fresh one allocated
+    rec, rec_n = E._rec_views(t, 5000)                                       # [n, 2] records + their int32 counts, disjoint
+    assert tuple(rec.shape) == (5000, 2) and tuple(rec_n.shape) == (5000,) and rec_n.dtype == torch.int32
+    rec.fill_(-1); rec_n.fill_(7)
+    assert int((rec != -1).sum()) == 0 and int((rec_n != 7).sum()) == 0

@@ -66,17 +66,20 @@ def _exchange_worker(rank, world, port, q):
         return torch.minimum((torch.arange(I) * 7 + r) % 5, cap // world)
     cnt = produced(rank).to(torch.int32)
     rec = torch.full((int(ptr[-1]) + 1, 2), -1, dtype=torch.int64)
+    rec_n = torch.full((int(ptr[-1]) + 1,), -1, dtype=torch.int32)     # the counts travel with their records
     for i in range(I):
         for p in range(int(cnt[i])):
             rec[int(ptr[i]) + p, 0] = i * 1000 + rank * 100 + p
             rec[int(ptr[i]) + p, 1] = rank
-    exchange_records(rec, ptr, cnt, sh)
+            rec_n[int(ptr[i]) + p] = (i * 1000 + rank * 100 + p) % 977
+    exchange_records(rec, ptr, cnt, sh, rec_n=rec_n)
     ok = True
     for i in range(I):
         want = sorted(i * 1000 + r * 100 + p for r in range(world) for p in range(int(produced(r)[i]))) \
             if sh.lo <= i < sh.hi else []
-        got = sorted(rec[int(ptr[i]):int(ptr[i]) + int(cnt[i]), 0].tolist())
-        ok = ok and got == want
+        a, b = int(ptr[i]), int(ptr[i]) + int(cnt[i])
+        got = sorted(rec[a:b, 0].tolist())
+        ok = ok and got == want and (rec[a:b, 0] % 977).tolist() == rec_n[a:b].tolist()
     q.put((rank, ok))
     dist.destroy_process_group()
 

@@ -87,3 +87,18 @@ def test_restatement_recommender_sim_vs_reference(name):
     np.testing.assert_allclose(P["norm2"][g["info_item"]], g["info_norm2"], rtol=1e-14)
     cnt = np.bincount(g["ae_item"], minlength=nI)
     assert np.array_equal(cnt[g["info_item"]], g["info_count"])
+
+
+def test_sim_rows_restriction_equals_sim_pairs():
+    """restate.sim_rows (the sampled-row oracle of the full-size GPU test) is bit-equal to sim_pairs on its rows."""
+    from tests import parity as PT
+    case = PT.synth_case(1500, 400, 20000, 0.05, seed=5)
+    args = (case["user"], case["item"], case["rating"], case["n_users"], case["n_items"], case["meta"]["prefix_code"])
+    for method in ("adjust_cosine", "cosine"):
+        P = RS.sim_pairs(*args, method, 50)
+        rows = np.array([0, 3, 17, 100, 250, 398, 399, 399])
+        Q = RS.sim_rows(*args, rows, method, 50)
+        m = np.isin(P["i"], rows)
+        assert m.sum() > 100
+        for key in ("i", "j", "sim", "mutu", "n", "frac", "label"):
+            assert np.array_equal(P[key][m], Q[key]), key

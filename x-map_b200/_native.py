@@ -23,11 +23,11 @@ _p = C.c_void_p
 class SimArgs(C.Structure):
     _fields_ = [
         ("csc_ptr", _p), ("csc_ent", _p), ("csc_aux", _p), ("tcsr_ent", _p),
-        ("ostat", _p), ("ord", _p), ("tri_work", _p),
+        ("ostat", _p), ("ord", _p), ("tri_work", _p), ("ord_item", _p),
         ("dom_code", _p), ("contains", _p),
         ("n_items", C.c_int32), ("method", C.c_int32), ("num_atleast", C.c_int32),
         ("k", C.c_int32), ("r2_bits", C.c_int32), ("count_only", C.c_int32),
-        ("rec_ptr", _p), ("rec_cnt", _p), ("rec", _p), ("bb", _p), ("row_npairs", _p),
+        ("rec_ptr", _p), ("rec_cnt", _p), ("rec", _p), ("rec_n", _p), ("bb", _p), ("row_npairs", _p),
         ("tab_idx", _p), ("tab_sim", _p), ("tab_mutu", _p), ("tab_n", _p), ("tab_len", _p),
         ("error_flag", _p),
     ]
@@ -36,13 +36,14 @@ class SimArgs(C.Structure):
 class XsimArgs(C.Structure):
     _fields_ = [
         ("n_starts", C.c_int32), ("n_units", C.c_int32),
-        ("unit_order", _p), ("unit_leg_lo", _p), ("unit_leg_hi", _p),
+        ("unit_order", _p), ("unit_counter", _p), ("warps", C.c_int32), ("unit_leg_lo", _p), ("unit_leg_hi", _p),
         ("unit_g0", _p), ("unit_g1", _p), ("unit_npass", _p), ("start_unit_ptr", _p),
         ("lp_ptr", _p), ("leg_par_base", _p), ("leg_npar", _p), ("leg_n", _p), ("leg_d", _p), ("leg_c", _p),
         ("par_s", _p), ("par_e", _p), ("par_m", _p), ("par_f", _p),
         ("rs_ptr", _p), ("rs_end", _p), ("rs_n", _p), ("rs_d", _p), ("rs_c", _p),
         ("tile_ptr", _p), ("gb", C.c_int32),
-        ("cells_lg", C.c_int32), ("top_m", C.c_int32), ("merge", C.c_int32),
+        ("cells_lg", C.c_int32), ("unit_clg", _p), ("gws", _p), ("gcells_lg", C.c_int32),
+        ("top_m", C.c_int32), ("merge", C.c_int32),
         ("unit_count", _p), ("unit_combos", _p), ("unit_top_end", _p), ("unit_top_xsim", _p), ("unit_top_len", _p),
         ("out_count", _p), ("out_combos", _p), ("top_end", _p), ("top_xsim", _p), ("top_len", _p),
         ("emit_ptr", _p), ("emit_end", _p), ("emit_xsim", _p),
@@ -66,7 +67,8 @@ _SIGS = {
     "xmap_sim_accumulate_split": (C.c_int, [C.POINTER(SimArgs), _p, _p, _p, C.c_int32, C.c_int32, _p, _p, _p]),
     "xmap_sim_select": (C.c_int, [C.POINTER(SimArgs), _p, C.c_int32, C.c_int32, _p]),
     "xmap_segmented_copy16": (C.c_int, [_p, _p, _p, _p, _p, C.c_int32, C.c_int64, _p]),
-    "xmap_xsim_smem_bytes": (C.c_int64, [C.c_int32]),
+    "xmap_segmented_copy4": (C.c_int, [_p, _p, _p, _p, _p, C.c_int32, C.c_int64, _p]),
+    "xmap_xsim_smem_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "xmap_xsim_extend": (C.c_int, [C.POINTER(XsimArgs), _p]),
     "xmap_xsim_merge": (C.c_int, [C.POINTER(XsimArgs), _p]),
     "xmap_choose_mapping": (C.c_int, [_p, _p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -48,19 +48,18 @@ struct __align__(16) Cell {
     unsigned key, cnt, lo, hi;
 };
 
-// 16-byte neighbour record: bits of sim, other_item | n << 24 | mutu << 44
+// 16-byte neighbour record: bits of sim, other_item | mutu << 32; the co-rating count n of the record at
+// position p lives in the parallel array rec_n[p] (only the winners of the selection ever read it), so the item
+// index and both counts are full 32-bit values.
 struct __align__(16) Rec {
     unsigned long long sim;
     unsigned long long pack;
 };
-constexpr int REC_CNT_BITS = 20;
-constexpr unsigned long long REC_CNT_MASK = (1ull << REC_CNT_BITS) - 1ull;
-__device__ __forceinline__ unsigned long long rec_pack(unsigned item, unsigned n, unsigned mutu) {
-    return (unsigned long long)item | ((unsigned long long)n << 24) | ((unsigned long long)mutu << 44);
+__device__ __forceinline__ unsigned long long rec_pack(unsigned item, unsigned mutu) {
+    return (unsigned long long)item | ((unsigned long long)mutu << 32);
 }
-__device__ __forceinline__ int rec_item(unsigned long long p) { return int(p & 0xFFFFFFull); }
-__device__ __forceinline__ int rec_n(unsigned long long p) { return int((p >> 24) & REC_CNT_MASK); }
-__device__ __forceinline__ int rec_mutu(unsigned long long p) { return int((p >> 44) & REC_CNT_MASK); }
+__device__ __forceinline__ int rec_item(unsigned long long p) { return int((unsigned)p); }
+__device__ __forceinline__ int rec_mutu(unsigned long long p) { return int((unsigned)(p >> 32)); }
 
 // Everything a row's group needs before it can start, gathered once at planning time into one
 // 48-byte record per launch slot (one load instead of a chain of dependent gathers).
@@ -325,8 +324,10 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__res
     if (gtid == 0 && n_ent) a.row_npairs[row] += n_ent;     // this row's group is the only writer
 
     // ---- epilogue pass 1: similarity, filter, label of every occupied cell, in place ---------------
-    // baselinerSim.py:163-173 / :125-141, :89, :95, :191, :207.  A kept cell becomes the 16-byte
-    // neighbour record of row `row` ({pack, sim bits}); a dropped one becomes zero.
+    // baselinerSim.py:163-173 / :125-141, :89, :95, :191, :207.  A kept cell becomes
+    //   hash row   : {other item, n << 16 | mutu, sim bits}     (n < 2^16: checked at entry)
+    //   direct row : {mutu, n, sim bits}                        (the other item follows from the slot)
+    // and a dropped one becomes zero.
     constexpr int EU = 2;
     int nkept = 0;
     for (int i0 = gtid; i0 < n_ent; i0 += gthreads * EU) {
@@ -361,9 +362,9 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__res
             const double sim = __ddiv_rn(__dmul_rn(cosv, (double)mn), (double)a.num_atleast);
             if (sim != 0.0 && mutu[u] != 0u) {
                 ++nkept;
-                const unsigned long long pk = rec_pack(sj[u].item, n[u], mutu[u]);
                 const unsigned long long sb = (unsigned long long)__double_as_longlong(sim);
-                out = make_uint4((unsigned)pk, (unsigned)(pk >> 32), (unsigned)sb, (unsigned)(sb >> 32));
+                out = direct ? make_uint4(mutu[u], n[u], (unsigned)sb, (unsigned)(sb >> 32))
+                             : make_uint4(sj[u].item, (n[u] << 16) | mutu[u], (unsigned)sb, (unsigned)(sb >> 32));
                 if ((sj[u].prefix_cls >> 8) != prefix_i) { a.bb[row] = 1; a.bb[sj[u].item] = 1; }
             }
             T4[sidx[u]] = out;
@@ -383,8 +384,9 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__res
     wbase = __shfl_sync(0xffffffffu, wbase, 0);
     if (a.count_only) {                                    // sizing pass: only the list lengths are wanted
         for (int i = gw * 32 + lane; i < n_ent; i += gthreads) {
-            const uint4 cv = T4[occ_list[i]];
-            if ((cv.z | cv.w) != 0u) atomicAdd(a.rec_cnt + int(cv.x & 0xFFFFFFu), 1);
+            const int sl = (int)occ_list[i];
+            const uint4 cv = T4[sl];
+            if ((cv.z | cv.w) != 0u) atomicAdd(a.rec_cnt + (direct ? __ldg(a.ord_item + (top_ord - sl)) : (int)cv.x), 1);
         }
         return;
     }
@@ -396,31 +398,41 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__res
         uint4 cv[EU];
         bool keep[EU];
         long long base_j[EU];
-        int cap_j[EU], p2[EU];
+        int cap_j[EU], p2[EU], jit[EU];
+        unsigned nn[EU], mu[EU];
 #pragma unroll
         for (int u = 0; u < EU; ++u) {
             const int i = i0 + u * gthreads + lane;
-            cv[u] = (i < n_ent) ? T4[occ_list[i]] : make_uint4(0u, 0u, 0u, 0u);
+            int sl = 0;
+            cv[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < n_ent) { sl = (int)occ_list[i]; cv[u] = T4[sl]; }
             keep[u] = (cv[u].z | cv[u].w) != 0u;
+            jit[u] = 0; nn[u] = mu[u] = 0u;
+            if (keep[u]) {
+                if (direct) { jit[u] = __ldg(a.ord_item + (top_ord - sl)); mu[u] = cv[u].x; nn[u] = cv[u].y; }
+                else { jit[u] = (int)cv[u].x; nn[u] = cv[u].y >> 16; mu[u] = cv[u].y & 0xFFFFu; }
+            }
         }
 #pragma unroll
         for (int u = 0; u < EU; ++u) {
             if (keep[u]) {
-                const int jitem = int(cv[u].x & 0xFFFFFFu);
-                base_j[u] = a.rec_ptr[jitem];
-                cap_j[u] = (int)(a.rec_ptr[jitem + 1] - base_j[u]);
-                p2[u] = atomicAdd(a.rec_cnt + jitem, 1);
+                base_j[u] = a.rec_ptr[jit[u]];
+                cap_j[u] = (int)(a.rec_ptr[jit[u] + 1] - base_j[u]);
+                p2[u] = atomicAdd(a.rec_cnt + jit[u], 1);
             }
         }
 #pragma unroll
         for (int u = 0; u < EU; ++u) {
             const unsigned m = __ballot_sync(0xffffffffu, keep[u]);
             if (keep[u]) {
-                const unsigned long long pk = ((unsigned long long)cv[u].y << 32) | cv[u].x;
                 const unsigned long long sb = ((unsigned long long)cv[u].w << 32) | cv[u].z;
-                rec[base_i + wbase + __popc(m & lt_mask)] = Rec{sb, pk};
-                if (p2[u] < cap_j[u]) rec[base_j[u] + p2[u]] = Rec{sb, (pk & ~0xFFFFFFull) | (unsigned long long)row};
-                else atomicExch(a.error_flag, 2);
+                const long long own = base_i + wbase + __popc(m & lt_mask);
+                rec[own] = Rec{sb, rec_pack((unsigned)jit[u], mu[u])};
+                a.rec_n[own] = (int)nn[u];
+                if (p2[u] < cap_j[u]) {
+                    rec[base_j[u] + p2[u]] = Rec{sb, rec_pack((unsigned)row, mu[u])};
+                    a.rec_n[base_j[u] + p2[u]] = (int)nn[u];
+                } else atomicExch(a.error_flag, 2);
             }
             wbase += __popc(m);
         }
@@ -527,6 +539,7 @@ __global__ void __launch_bounds__(128) select_warp_kernel(xmap_sim_args a, const
         return;
     }
     const Rec *__restrict__ R = reinterpret_cast<const Rec *>(a.rec) + a.rec_ptr[row];
+    const int32_t *__restrict__ RN = a.rec_n + a.rec_ptr[row];
     const bool bb_i = a.bb[row] != 0;
     const int dom_i = a.dom_code[row];
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -555,12 +568,12 @@ __global__ void __launch_bounds__(128) select_warp_kernel(xmap_sim_args a, const
         if ((lb & 1u) && rank0 < K) {
             const size_t o = ((size_t)row * 2 + 0) * K + rank0;
             a.tab_idx[o] = j; a.tab_sim[o] = __longlong_as_double((long long)sbits);
-            a.tab_mutu[o] = rec_mutu(pack); a.tab_n[o] = rec_n(pack);
+            a.tab_mutu[o] = rec_mutu(pack); a.tab_n[o] = RN[lane];
         }
         if ((lb & 2u) && rank1 < K) {
             const size_t o = ((size_t)row * 2 + 1) * K + rank1;
             a.tab_idx[o] = j; a.tab_sim[o] = __longlong_as_double((long long)sbits);
-            a.tab_mutu[o] = rec_mutu(pack); a.tab_n[o] = rec_n(pack);
+            a.tab_mutu[o] = rec_mutu(pack); a.tab_n[o] = RN[lane];
         }
         if (lane == 0) {
             a.tab_len[(size_t)row * 2 + 0] = min(n0, K);
@@ -682,13 +695,13 @@ __global__ void __launch_bounds__(128) select_warp_kernel(xmap_sim_args a, const
                 const Rec v = R[m0.q];
                 a.tab_idx[o + r0] = m0.j;
                 a.tab_sim[o + r0] = __longlong_as_double((long long)v.sim);
-                a.tab_mutu[o + r0] = rec_mutu(v.pack); a.tab_n[o + r0] = rec_n(v.pack);
+                a.tab_mutu[o + r0] = rec_mutu(v.pack); a.tab_n[o + r0] = RN[m0.q];
             }
             if (lane + 32 < n && r1 < want[list]) {
                 const Rec v = R[m1.q];
                 a.tab_idx[o + r1] = m1.j;
                 a.tab_sim[o + r1] = __longlong_as_double((long long)v.sim);
-                a.tab_mutu[o + r1] = rec_mutu(v.pack); a.tab_n[o + r1] = rec_n(v.pack);
+                a.tab_mutu[o + r1] = rec_mutu(v.pack); a.tab_n[o + r1] = RN[m1.q];
             }
             if (lane == 0) a.tab_len[(size_t)row * 2 + list] = want[list];
             continue;
@@ -717,7 +730,7 @@ __global__ void __launch_bounds__(128) select_warp_kernel(xmap_sim_args a, const
                 const Rec v = R[bp];
                 a.tab_idx[o + rr] = bt;
                 a.tab_sim[o + rr] = __longlong_as_double((long long)v.sim);
-                a.tab_mutu[o + rr] = rec_mutu(v.pack); a.tab_n[o + rr] = rec_n(v.pack);
+                a.tab_mutu[o + rr] = rec_mutu(v.pack); a.tab_n[o + rr] = RN[bp];
             }
             last_k = bk; last_t = bt;
             got = rr + 1;
@@ -870,6 +883,7 @@ __global__ void __launch_bounds__(FIN_THREADS) select_cta_kernel(xmap_sim_args a
     const int m = a.rec_cnt[row];
     if (m <= XMAP_SELECT_LONG) return;
     const Rec *__restrict__ R = reinterpret_cast<const Rec *>(a.rec) + a.rec_ptr[row];
+    const int32_t *__restrict__ RN = a.rec_n + a.rec_ptr[row];
     const bool bb_i = a.bb[row] != 0;
     const int dom_i = a.dom_code[row];
     const int K = a.k;
@@ -903,7 +917,7 @@ __global__ void __launch_bounds__(FIN_THREADS) select_cta_kernel(xmap_sim_args a
                 const int p = atomicAdd(&S.ncand, 1);
                 S.skey[p] = (lst == 0 ? LIST0_BIT : 0ull) | key;
                 S.spay[p] = (v[u].sim & LIST0_BIT) | ((unsigned long long)j << 16) | (unsigned)p;
-                S.c_mutu[p] = rec_mutu(v[u].pack); S.c_n[p] = rec_n(v[u].pack);
+                S.c_mutu[p] = rec_mutu(v[u].pack); S.c_n[p] = RN[base + u * FIN_THREADS + tid];
             }
         }
         __syncthreads();

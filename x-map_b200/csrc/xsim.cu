@@ -4,70 +4,49 @@
 // (extender.py:83-89) are accumulated per (start, end) into
 // xsim = sum(s_p c_p) / sum(c_p) (extender.py:198-201) without ever storing a path.
 //
-// Design: the accumulator of a start never leaves the SM.  One CTA owns one unit = (start item, one or
-// more passes); a pass covers a range of the hashed end axis pi(y) = y * 0x9E3779B1 (every right-segment
-// list is stored sorted by pi, and a per-source pointer table gives the sub-range of a pass without a
-// search), chosen so that the distinct ends of the pass fit a shared-memory hash table.  Inside a pass:
+// Design: the accumulator of a start never leaves the SM, and no two warps ever share a cell.
+// One WARP owns one unit = (start item, a run of passes) at a time and a private hash table in shared
+// memory; a pass covers a range of the hashed end axis pi(y) = y * 0x9E3779B1 (every right-segment list
+// is stored sorted by pi, and a per-source pointer table gives the sub-range of a pass without a search),
+// chosen so that the distinct ends of the pass fit the table.  Inside a pass the warp walks the
+// (leg, partner) pairs of its start 32 at a time: each lane resolves one pair to a descriptor
+// {right-segment sub-range, folded (N, D, C) of leg + bridge edge}, a shuffle scan numbers the products
+// of the batch and they are dealt to the lanes in chunks of 32 whatever the sub-range lengths.  A lane
+// loads one 28-byte right segment (the next chunk's loads are issued before the current chunk is
+// processed), evaluates the path, lanes that hit the same end are grouped (MATCH.ANY) and the group's
+// lowest lane adds the terms one by one in lane (= path) order to the cell: plain shared-memory loads
+// and stores, no atomics on values, no block barrier.  The summation order of a (start, end) cell is a
+// function of the path structure and the pass plan only, so results are bit-identical from run to run
+// and for any number of GPUs (every rank builds the same plan).
 //
-//   prep      512 (leg, partner) pairs at a time: each thread resolves one pair to a descriptor
-//             {right-segment sub-range, folded (N, D, C) of leg + bridge edge}; a block scan numbers
-//             the products of the macro-batch and compacts the non-empty descriptors;
-//   produce   the products are dealt to the 16 warps in chunks of 32 (chunk c -> warp c mod 16): a lane
-//             finds its descriptor, loads one 28-byte right segment, evaluates the path and leaves
-//             (end, s_p c_p, c_p) in its payload slot; per (owner, producer) lane masks say which slots
-//             belong to which owner warp (owner = 4 bits of pi(end));
-//   consume   warp o walks the slots addressed to it in (producer, lane) order = canonical path order,
-//             combines lanes that hit the same end sequentially in that order, and updates its private
-//             512-cell region of the table with plain loads and stores: no atomics, and the summation
-//             order of every cell is the path order (leg, partner, right segment), a function of the
-//             structure only -- results are bit-identical for any pass split, table size or GPU count.
-//
-// A pass whose table overflows is split in two on the device (the hash range halves) and redone; the top-m
+// A pass whose table overflows is split in two on the device (the tile range halves) and redone; the top-m
 // of a unit is kept in shared memory across its passes and a small kernel merges the units of a start.
+// Units are fetched from a global counter in descending-work order (results do not depend on which warp
+// runs a unit).
 //
-// Bound: issue rate of the produce/consume instruction stream (~6 warp-instructions per path) and the
-// 28 B right-segment read per path from L2/HBM; accumulator traffic is shared memory only.
+// Bound: issue rate of the per-path instruction stream and the 28 B right-segment read per path from
+// L2/HBM; accumulator traffic is shared memory only.
 #include "common.cuh"
 
 namespace xmap {
 
-constexpr int XT = 512;                       // threads per CTA
-constexpr int XW = XT / 32;                   // warps = owners
-constexpr int XMB = 512;                      // (leg, partner) pairs per macro-batch
+constexpr int XT_MAX = 640;                   // threads per CTA (a multiple of 32, chosen at launch)
 constexpr unsigned XGOLD2 = 0x85EBCA6Bu;      // second multiplicative hash of the end: owner warp and home cell
                                               // (the first one, pi(y) = y * 0x9E3779B1, orders the lists: host side)
-constexpr int XSTACK = 48;
-constexpr int XF_BINS = 256;
-constexpr int XSURV = 512;
+constexpr int XSTACK = 16;                    // pending halves of split passes (depth <= gb + 1)
+constexpr int XSV = 64;                       // candidates of a top-m merge: survivors (<= 32) + running best (<= 32)
 
-// 16 sub-bins per octave for |xsim| in [2^-16, 2) (see sim_bin in sim.cu)
-__device__ __forceinline__ int xsim_bin(unsigned long long key_bits) {
-    const int hi = int((key_bits & 0x7FFFFFFFFFFFFFFFull) >> 48);
-    const int base = (1023 - 16) << 4;
-    return max(0, min(XF_BINS - 1, hi - base));
-}
-
-struct XShared {
-    // fixed part (the table follows, sized at launch)
-    double d_N[XMB], d_D[XMB], d_C[XMB];      // descriptors of the macro-batch (compacted, non-empty)
-    long long d_base[XMB];
-    double p_num[2][XW][32], p_den[2][XW][32];   // payload slots, double-buffered; finalize scratch aliases them
-    int d_cum[XMB + 4];                        // exclusive product prefix, d_cum[n_desc] = total
-    int s_lp[XMB + 4];
-    int p_y[2][XW][32];
-    unsigned p_mask[2][XW][XW];                // [owner][producer]
-    unsigned long long s_wsum[XW];
+// Per-warp staging (shared memory).  `sv` doubles as the chunk staging of the in-order combine
+// (accumulate phase) and as the survivor list of the top-m selection (finalize phase).
+struct __align__(16) WarpScratch {
+    union {
+        struct { double c_num[32], c_den[32]; } acc;
+        struct { unsigned long long key[XSV]; double x[XSV]; int end[XSV]; } sv;
+    } u;
     unsigned long long best_key[XMAP_KMAX];    // running top-m of the unit over its finished passes
     double best_x[XMAP_KMAX];
     int best_end[XMAP_KMAX];
-    int best_len;
     int stack_g0[XSTACK], stack_g1[XSTACK];
-    int stack_n, next_pass, cur_g0, cur_g1;
-    int s_nd, s_total, s_overflow;
-    long long s_nextleg;
-    int s_cnt, s_nsurv, s_bstar, s_emit;
-    int status;
-    unsigned long long r_key[XW]; int r_tie[XW], r_pos[XW];   // block arg-best exchange (fallback path)
 };
 
 struct Fetched {
@@ -76,384 +55,327 @@ struct Fetched {
     bool valid;
 };
 
-// products [32 c, 32 c + 32) of the macro-batch: descriptor lookup + the right-segment loads
-__device__ __forceinline__ Fetched fetch_chunk(const xmap_xsim_args &a, const XShared &S, int c, int nd, int total,
-                                               int lane) {
+// products [32 c, 32 c + 32) of the batch: the lane's descriptor by a shuffle search over the inclusive
+// product counts (empty descriptors are skipped by construction), then the right-segment loads
+__device__ __forceinline__ Fetched fetch_chunk(const xmap_xsim_args &a, int c, int total, int incl, int len,
+                                               long long base, double dN, double dD, double dC, int lane) {
     Fetched f;
-    f.valid = false; f.y = 0; f.N = f.D = f.C = f.rn = f.rd = f.rc = 0.0;
-    const int base_p = c << 5;
-    if (base_p >= total) return f;
-    // descriptor holding product base_p: largest d with d_cum[d] <= base_p (two 16-way steps)
-    const int i1 = lane << 4;
-    const unsigned m1 = __ballot_sync(0xffffffffu, i1 < nd && S.d_cum[i1] <= base_p);
-    const int coarse = (__popc(m1) - 1) << 4;
-    const int i2 = coarse + (lane & 15);
-    const unsigned m2 = __ballot_sync(0xffffffffu, lane < 16 && i2 < nd && S.d_cum[i2] <= base_p);
-    const int d0 = coarse + __popc(m2) - 1;
-    // inclusive product ends of the 32 descriptors from d0 on (every descriptor holds >= 1 product)
-    const int e = S.d_cum[min(d0 + 1 + lane, nd)];
-    const int p = base_p + lane;
-    int l = 0;
+    const int p = (c << 5) + lane;
+    int l = 0;                                              // smallest lane with incl > p
 #pragma unroll
     for (int step = 16; step >= 1; step >>= 1) {
-        const int v = __shfl_sync(0xffffffffu, e, l + step - 1);
+        const int v = __shfl_sync(0xffffffffu, incl, l + step - 1);
         if (v <= p) l += step;
     }
-    const int eprev = __shfl_sync(0xffffffffu, e, (l + 31) & 31);
-    const int d0cum = S.d_cum[d0];
-    if (p < total) {
-        const int di = d0 + l;
-        const int excl = l == 0 ? d0cum : eprev;
-        const long long r = S.d_base[di] + (long long)(p - excl);
-        f.valid = true;
-        f.N = S.d_N[di]; f.D = S.d_D[di]; f.C = S.d_C[di];
+    const int excl = __shfl_sync(0xffffffffu, incl - len, l);
+    const long long b = __shfl_sync(0xffffffffu, base, l);
+    f.N = __shfl_sync(0xffffffffu, dN, l);
+    f.D = __shfl_sync(0xffffffffu, dD, l);
+    f.C = __shfl_sync(0xffffffffu, dC, l);
+    f.valid = p < total;
+    f.y = 0; f.rn = f.rd = f.rc = 0.0;
+    if (f.valid) {
+        const long long r = b + (long long)(p - excl);
         f.y = __ldg(a.rs_end + r);
         f.rn = __ldg(a.rs_n + r); f.rd = __ldg(a.rs_d + r); f.rc = __ldg(a.rs_c + r);
     }
     return f;
 }
 
-__global__ void __launch_bounds__(XT, 1) xsim_tile_kernel(xmap_xsim_args a) {
+// One warp = one unit at a time (fetched from a global counter in descending-work order); the warps of a
+// CTA are independent: no block barrier anywhere.
+__global__ void __launch_bounds__(XT_MAX, 1) xsim_warp_kernel(xmap_xsim_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    XShared &S = *reinterpret_cast<XShared *>(smem_raw);
-    const int C = 1 << a.cells_lg;
-    const int RB = a.cells_lg - 4;                         // log2 of an owner's region
-    double2 *vals = reinterpret_cast<double2 *>(smem_raw + ((sizeof(XShared) + 15) & ~(size_t)15));
-    volatile int *keys = reinterpret_cast<volatile int *>(vals + C);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int u = a.unit_order ? a.unit_order[blockIdx.x] : (int)blockIdx.x;
-    const long long leg_lo = a.unit_leg_lo[u], leg_hi = a.unit_leg_hi[u];
-    const long long q_lo = a.lp_ptr[leg_lo], q_hi = a.lp_ptr[leg_hi];
+    const int nw = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int CS = 1 << a.cells_lg;                        // cells of a warp's shared-memory table
+    WarpScratch &W = reinterpret_cast<WarpScratch *>(smem_raw)[warp];
+    double2 *s_vals = reinterpret_cast<double2 *>(smem_raw + (size_t)nw * sizeof(WarpScratch)) + (size_t)warp * CS;
+    int *s_keys = reinterpret_cast<int *>(smem_raw + (size_t)nw * sizeof(WarpScratch) + (size_t)nw * CS * sizeof(double2)) +
+                  (size_t)warp * CS;
+    // units whose ends do not fit the shared-memory table use this warp's slot of the global workspace
+    // (L2-resident while the unit runs): 2^gcells_lg cells, vals first
+    unsigned char *gslot = a.gws ? reinterpret_cast<unsigned char *>(a.gws) +
+                                       ((size_t)blockIdx.x * nw + warp) * ((size_t)20 << a.gcells_lg) : nullptr;
     const int G = 1 << a.gb, G1 = G + 1;
-    const int ug0 = a.unit_g0[u], ug1 = a.unit_g1[u], unpass = a.unit_npass[u];
     const int M = a.top_m;
-    long long combos = 0;                                  // identical in every thread
-    int unit_count = 0;
-    unsigned ss = 0;                                       // superstep counter (payload buffer parity)
-    if (tid == 0) {
-        S.best_len = 0; S.stack_n = 0; S.next_pass = 0; S.status = 0; S.s_emit = 0;
-    }
-    __syncthreads();
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     for (;;) {
-        // ---- next pass: a split half if one is pending, else the unit's next own pass --------------------
-        if (tid == 0) {
-            if (S.stack_n > 0) { --S.stack_n; S.cur_g0 = S.stack_g0[S.stack_n]; S.cur_g1 = S.stack_g1[S.stack_n]; }
-            else if (S.next_pass < unpass) {
+        int uq = 0;
+        if (lane == 0) uq = atomicAdd(a.unit_counter, 1);
+        uq = __shfl_sync(0xffffffffu, uq, 0);
+        if (uq >= a.n_units) break;
+        const int u = a.unit_order ? __ldg(a.unit_order + uq) : uq;
+        const long long leg_lo = a.unit_leg_lo[u], leg_hi = a.unit_leg_hi[u];
+        const long long q_lo = a.lp_ptr[leg_lo], q_hi = a.lp_ptr[leg_hi];
+        const int ug0 = a.unit_g0[u], ug1 = a.unit_g1[u], unpass = a.unit_npass[u];
+        long long combos = 0;
+        int unit_count = 0, best_len = 0, stack_n = 0, next_pass = 0, status = 0, emitted = 0;
+        const int clg = a.unit_clg ? min(a.unit_clg[u], gslot ? a.gcells_lg : a.cells_lg) : a.cells_lg;
+        const bool in_smem = clg <= a.cells_lg;
+        const int C = 1 << clg;
+        double2 *vals = in_smem ? s_vals : reinterpret_cast<double2 *>(gslot);
+        int *keys = in_smem ? s_keys : reinterpret_cast<int *>(gslot + ((size_t)16 << a.gcells_lg));
+
+        for (;;) {
+            // ---- next pass: a split half if one is pending, else the unit's next own pass (all warp-uniform) ----
+            int g0, g1;
+            if (stack_n > 0) { --stack_n; g0 = W.stack_g0[stack_n]; g1 = W.stack_g1[stack_n]; }
+            else if (next_pass < unpass) {
                 const long long w = ug1 - ug0;             // the unit's tile range cut into unpass equal passes
-                S.cur_g0 = ug0 + (int)(w * S.next_pass / unpass);
-                S.cur_g1 = ug0 + (int)(w * (S.next_pass + 1) / unpass);
-                ++S.next_pass;
-            } else S.cur_g0 = -1;
-            S.s_overflow = 0; S.s_cnt = 0; S.s_nsurv = 0;
-        }
-        for (int c = tid; c < C; c += XT) keys[c] = 0;
-        __syncthreads();
-        const int g0 = S.cur_g0, g1 = S.cur_g1;
-        if (g0 < 0) break;
-        const bool whole = g0 == 0 && g1 == G;
+                g0 = ug0 + (int)(w * next_pass / unpass);
+                g1 = ug0 + (int)(w * (next_pass + 1) / unpass);
+                ++next_pass;
+            } else break;
+            const bool whole = g0 == 0 && g1 == G;
+            for (int c = lane; c < C; c += 32) keys[c] = 0;
+            __syncwarp();
 
-        // =================== accumulate ======================================================
-        long long q0 = q_lo, cur_leg = leg_lo;
-        long long pass_combos = 0;
-        while (q0 < q_hi) {
-            const int nq = (int)min((long long)XMB, q_hi - q0);
-            const int nl = (int)min((long long)XMB, leg_hi - cur_leg);
-            if (tid < nl) {
-                const long long v = __ldg(a.lp_ptr + cur_leg + tid) - q0;
-                S.s_lp[tid] = (int)max(-(1ll << 30), min(1ll << 30, v));
-            }
-            __syncthreads();
-            if (S.s_overflow) break;                       // uniform: nobody writes the flag before the next barrier
-            int len = 0;
-            long long b = 0;
-            double Nm = 0.0, Dm = 0.0, Cm = 0.0;
-            if (tid < nq) {
-                int lo = 0, hi = nl;                       // largest leg slot with first pair <= tid
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (S.s_lp[mid] <= tid) lo = mid; else hi = mid;
+            // =================== accumulate ======================================================
+            long long q0 = q_lo, cur_leg = leg_lo, pass_combos = 0;
+            bool ovf = false;
+            int n_ins = 0;                                 // occupied cells of the table
+            while (q0 < q_hi && !ovf) {
+                const int nq = (int)min(32ll, q_hi - q0);
+                // first pair of the 32 legs from cur_leg on, relative to q0 (every leg holds >= 1 pair, so pair
+                // q0 + i belongs to one of the legs cur_leg .. cur_leg + i)
+                int lpv = 0x3FFFFFFF;
+                if (cur_leg + lane < leg_hi) {
+                    const long long v = __ldg(a.lp_ptr + cur_leg + lane) - q0;
+                    lpv = (int)max(-(1ll << 30), min((1ll << 30), v));
                 }
-                const long long L = cur_leg + lo;
-                const int pidx = tid - S.s_lp[lo];
-                const long long p = __ldg(a.leg_par_base + L) + pidx;
-                const int s = __ldg(a.par_s + p);
-                Nm = __dadd_rn(__ldg(a.leg_n + L), __ldg(a.par_e + p));      // sums in path order (extender.py:85-88)
-                Dm = __dadd_rn(__ldg(a.leg_d + L), __ldg(a.par_m + p));
-                Cm = __dmul_rn(__ldg(a.leg_c + L), __ldg(a.par_f + p));
-                const long long rb = __ldg(a.rs_ptr + s);
-                if (whole) { b = rb; len = (int)(__ldg(a.rs_ptr + s + 1) - rb); }
-                else {
-                    const int32_t *tp = a.tile_ptr + (size_t)s * G1;
-                    const int b0 = __ldg(tp + g0), b1 = __ldg(tp + g1);
-                    b = rb + b0; len = b1 - b0;
+                int cntle = 0;                             // number of legs whose first pair is <= lane
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const int v = __shfl_sync(0xffffffffu, lpv, cntle + step - 1);
+                    if (v <= lane) cntle += step;
                 }
-                if (tid == nq - 1) S.s_nextleg = (pidx + 1 == __ldg(a.leg_npar + L)) ? L + 1 : L;
-            }
-            // block scan of (non-empty flag, len)
-            const unsigned long long mine = (len > 0 ? (1ull << 40) : 0ull) | (unsigned long long)len;
-            unsigned long long incl = mine;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, off);
-                if (lane >= off) incl += t;
-            }
-            if (lane == 31) S.s_wsum[warp] = incl;
-            __syncthreads();
-            unsigned long long ws = lane < XW ? S.s_wsum[lane] : 0ull, wi = ws;
-#pragma unroll
-            for (int off = 1; off < XW; off <<= 1) {
-                const unsigned long long t = __shfl_up_sync(0xffffffffu, wi, off);
-                if (lane >= off) wi += t;
-            }
-            const unsigned long long tot = __shfl_sync(0xffffffffu, wi, XW - 1);
-            const unsigned long long woff = __shfl_sync(0xffffffffu, wi - ws, warp);
-            const unsigned long long excl = woff + incl - mine;
-            if (len > 0) {
-                const int c = (int)(excl >> 40);
-                S.d_cum[c] = (int)(excl & ((1ull << 40) - 1ull));
-                S.d_base[c] = b; S.d_N[c] = Nm; S.d_D[c] = Dm; S.d_C[c] = Cm;
-            }
-            const int nd = (int)(tot >> 40), total = (int)(tot & ((1ull << 40) - 1ull));
-            if (tid == 0) S.d_cum[nd] = total;
-            __syncthreads();
-            cur_leg = S.s_nextleg; q0 += nq;
-            pass_combos += total;
-
-            // ---- supersteps: 16 chunks of 32 products, one per warp -------------------------------
-            const int nchunk = (total + 31) >> 5;
-            Fetched nxt = fetch_chunk(a, S, warp, nd, total, lane);
-            for (int k = 0; k * XW < nchunk; ++k) {
-                const Fetched cur = nxt;
-                nxt = fetch_chunk(a, S, (k + 1) * XW + warp, nd, total, lane);
-                const int buf = ss & 1u; ++ss;
-                // produce
-                int owner = XW;
-                if (cur.valid) {
-                    const double Nn = __dadd_rn(cur.N, cur.rn);
-                    const double Dd = __dadd_rn(cur.D, cur.rd);
-                    const double cp = __dmul_rn(cur.C, cur.rc);
-                    const double sp = (Dd != 0.0) ? __ddiv_rn(Nn, Dd) : 0.0;      // extender.py:88-89
-                    S.p_num[buf][warp][lane] = __dmul_rn(sp, cp);
-                    S.p_den[buf][warp][lane] = cp;
-                    S.p_y[buf][warp][lane] = cur.y;
-                    owner = (int)(((unsigned)cur.y * XGOLD2) >> 28);
-                }
-                if (lane < XW) S.p_mask[buf][lane][warp] = 0u;
-                __syncwarp();
-                const unsigned grp = __match_any_sync(0xffffffffu, owner);
-                if (cur.valid && (__ffs(grp) - 1) == lane) S.p_mask[buf][owner][warp] = grp;
-                __syncthreads();
-                // consume: the slots addressed to owner `warp`, in (producer, lane) order
-                const unsigned pm = lane < XW ? S.p_mask[buf][warp][lane] : 0u;
-                const int cntl = __popc(pm);
-                int incl_i = cntl;
-#pragma unroll
-                for (int off = 1; off < XW; off <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl_i, off);
-                    if (lane >= off) incl_i += t;
-                }
-                const int tot_o = __shfl_sync(0xffffffffu, incl_i, XW - 1);
-                const int region = warp << RB;
-                for (int i0 = 0; i0 < tot_o; i0 += 32) {
-                    const int i = i0 + lane;
-                    const bool valid = i < tot_o;
-                    int pr = 0;                            // smallest producer with incl > i
-#pragma unroll
-                    for (int step = XW / 2; step >= 1; step >>= 1) {
-                        const int v = __shfl_sync(0xffffffffu, incl_i, pr + step - 1);
-                        if (v <= i) pr += step;
+                const int aslot = max(cntle - 1, 0);
+                const int lp_a = __shfl_sync(0xffffffffu, lpv, aslot);
+                int len = 0;
+                long long base = 0, myleg = cur_leg;
+                double dN = 0.0, dD = 0.0, dC = 0.0;
+                bool last_of_leg = false;
+                if (lane < nq) {
+                    const long long L = cur_leg + aslot;
+                    const int pidx = lane - lp_a;
+                    const long long p = __ldg(a.leg_par_base + L) + pidx;
+                    const int s = __ldg(a.par_s + p);
+                    dN = __dadd_rn(__ldg(a.leg_n + L), __ldg(a.par_e + p));      // sums in path order (extender.py:85-88)
+                    dD = __dadd_rn(__ldg(a.leg_d + L), __ldg(a.par_m + p));
+                    dC = __dmul_rn(__ldg(a.leg_c + L), __ldg(a.par_f + p));
+                    const long long rb = __ldg(a.rs_ptr + s);
+                    if (whole) { base = rb; len = (int)(__ldg(a.rs_ptr + s + 1) - rb); }
+                    else {
+                        const int32_t *tp = a.tile_ptr + (size_t)s * G1;
+                        const int b0 = __ldg(tp + g0), b1 = __ldg(tp + g1);
+                        base = rb + b0; len = b1 - b0;
                     }
-                    pr = min(pr, XW - 1);
-                    const int before = __shfl_sync(0xffffffffu, incl_i - cntl, pr);
-                    const unsigned mk = __shfl_sync(0xffffffffu, pm, pr);
-                    int y = -1 - lane;
-                    double num = 0.0, den = 0.0;
-                    if (valid) {
-                        const int src = __fns(mk, 0, i - before + 1);
-                        y = S.p_y[buf][pr][src];
-                        num = S.p_num[buf][pr][src]; den = S.p_den[buf][pr][src];
-                    }
-                    const unsigned g2 = __match_any_sync(0xffffffffu, y);
-                    const bool leader = valid && (__ffs(g2) - 1) == lane;
-                    // find-or-insert in the owner's region (write-then-verify resolves lanes racing for one empty cell)
-                    int slot = -1;
-                    bool isnew = false;
-                    {
-                        int pos = (int)((((unsigned)y * XGOLD2) << 4) >> (32 - RB));
-                        bool pending = leader;
-                        int probes = 0;
-                        while (__any_sync(0xffffffffu, pending)) {
-                            bool tried = false;
-                            if (pending) {
-                                const int kcur = keys[region + pos];
-                                if (kcur == y + 1) { slot = region + pos; pending = false; }
-                                else if (kcur == 0) { keys[region + pos] = y + 1; tried = true; }
-                                else {
-                                    pos = (pos + 1) & ((1 << RB) - 1);
-                                    if (++probes >= (1 << RB)) { pending = false; S.s_overflow = 1; }
-                                }
-                            }
-                            __syncwarp();
-                            if (tried && keys[region + pos] == y + 1) { slot = region + pos; isnew = true; pending = false; }
-                            __syncwarp();
-                        }
-                    }
-                    // terms of one end are added one by one, in lane (= path) order
-                    double an = 0.0, ad = 0.0;
-                    if (leader && slot >= 0 && !isnew) { const double2 v = vals[slot]; an = v.x; ad = v.y; }
-                    unsigned rem = leader ? g2 : 0u;
-                    while (__any_sync(0xffffffffu, rem != 0u)) {
-                        const int src = rem ? (__ffs(rem) - 1) : lane;
-                        const double n2 = __shfl_sync(0xffffffffu, num, src);
-                        const double d2 = __shfl_sync(0xffffffffu, den, src);
-                        if (rem) { an = __dadd_rn(an, n2); ad = __dadd_rn(ad, d2); rem &= rem - 1u; }
-                    }
-                    if (leader && slot >= 0) vals[slot] = make_double2(an, ad);
+                    myleg = L;
+                    last_of_leg = pidx + 1 == __ldg(a.leg_npar + L);
                 }
-            }
-        }
-        __syncthreads();
-        if (S.s_overflow) {
-            // the pass does not fit: halve its hash range and redo both halves (nothing of it was published)
-            if (tid == 0) {
-                if (g1 - g0 < 2 || S.stack_n + 2 > XSTACK) S.status = 1;
-                else {
-                    const int mid = (g0 + g1) >> 1;
-                    S.stack_g0[S.stack_n] = mid; S.stack_g1[S.stack_n] = g1; ++S.stack_n;
-                    S.stack_g0[S.stack_n] = g0; S.stack_g1[S.stack_n] = mid; ++S.stack_n;
-                }
-            }
-            __syncthreads();
-            continue;
-        }
-        combos += pass_combos;
-
-        // =================== finalize the pass ==============================================
-        unsigned *hist = reinterpret_cast<unsigned *>(&S.p_num[0][0][0]);                       // 1 KB
-        unsigned long long *sv_key = reinterpret_cast<unsigned long long *>(&S.p_den[0][0][0]); // 4 KB
-        double *sv_x = reinterpret_cast<double *>(&S.p_den[1][0][0]);                           // 4 KB
-        int *sv_end = reinterpret_cast<int *>(&S.p_num[1][0][0]);                               // 2 KB
-        for (int bq = tid; bq < XF_BINS; bq += XT) hist[bq] = 0u;
-        __syncthreads();
-        int mycnt = 0;
-        for (int c0 = warp * 32; c0 < C; c0 += XT) {
-            const int c = c0 + lane;
-            const int kk = keys[c];
-            const bool occ = kk != 0;
-            double x = 0.0;
-            if (occ) {
-                const double2 v = vals[c];
-                x = __ddiv_rn(v.x, v.y);                   // extender.py:198-201
-                vals[c].x = x;
-                atomicAdd(&hist[xsim_bin(abs_key(x))], 1u);
-                ++mycnt;
-            }
-            if (a.emit_ptr) {
-                const unsigned mo = __ballot_sync(0xffffffffu, occ);
-                int base = 0;
-                if (lane == 0 && mo) base = atomicAdd(&S.s_emit, __popc(mo));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (occ) {
-                    const long long o = a.emit_ptr[u] + base + __popc(mo & ((1u << lane) - 1u));
-                    a.emit_end[o] = kk - 1; a.emit_xsim[o] = x;
-                }
-            }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) mycnt += __shfl_xor_sync(0xffffffffu, mycnt, off);
-        if (lane == 0 && mycnt) atomicAdd(&S.s_cnt, mycnt);
-        __syncthreads();
-        const int cnt_pass = S.s_cnt;
-        unit_count += cnt_pass;
-        const int want = min(M, cnt_pass);
-        if (warp == 0) {
-            // largest bin b* such that #(bin >= b*) >= want
-            int bstar = 0, run = 0;
-            bool found = false;
-            for (int hb = XF_BINS - 32; hb >= 0 && !found && want > 0; hb -= 32) {
-                unsigned suf = hist[hb + lane];
+                // the leg that holds pair q0 + nq
+                const long long nl = __shfl_sync(0xffffffffu, myleg + (last_of_leg ? 1 : 0), nq - 1);
+                int incl = len;
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) {
-                    const unsigned t = __shfl_down_sync(0xffffffffu, suf, off);
-                    if (lane + off < 32) suf += t;
+                    const int t = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl += t;
                 }
-                const unsigned hit = __ballot_sync(0xffffffffu, run + (int)suf >= want);
-                if (hit) { bstar = hb + (31 - __clz(hit)); found = true; }
-                else run += (int)__shfl_sync(0xffffffffu, suf, 0);
-            }
-            if (lane == 0) S.s_bstar = bstar;
-        }
-        __syncthreads();
-        const int bstar = S.s_bstar;
-        // survivors: cells at or above the threshold bin, plus the running best of the earlier passes
-        for (int c = tid; c < C && want > 0; c += XT) {
-            const int kk = keys[c];
-            if (kk == 0) continue;
-            const double x = vals[c].x;
-            const unsigned long long ak = abs_key(x);
-            if (xsim_bin(ak) < bstar) continue;
-            const int pos = atomicAdd(&S.s_nsurv, 1);
-            if (pos < XSURV) { sv_key[pos] = ak; sv_x[pos] = x; sv_end[pos] = kk - 1; }
-        }
-        const int nbest = S.best_len;
-        __syncthreads();
-        int nsurv = S.s_nsurv;
-        const int newlen = min(M, cnt_pass + nbest);
-        if (nsurv + nbest <= XSURV) {
-            if (tid < nbest) { sv_key[nsurv + tid] = S.best_key[tid]; sv_x[nsurv + tid] = S.best_x[tid]; sv_end[nsurv + tid] = S.best_end[tid]; }
-            __syncthreads();
-            nsurv += nbest;
-            if (tid < nsurv) {
-                const unsigned long long mk = sv_key[tid];
-                const int me = sv_end[tid];
-                int rank = 0;
-                for (int t = 0; t < nsurv; ++t) rank += better(sv_key[t], sv_end[t], mk, me) ? 1 : 0;
-                if (rank < newlen) { S.best_key[rank] = mk; S.best_x[rank] = sv_x[tid]; S.best_end[rank] = me; }
-            }
-            if (tid == 0) S.best_len = newlen;
-        } else {
-            // one bin holds too many equal values: plain rounds over every cell and the running best
-            // (new list built in sv_*; every round picks the best candidate strictly after the last)
-            __syncthreads();
-            unsigned long long last_k = ~0ull; int last_t = -1;
-            for (int r = 0; r < newlen; ++r) {
-                unsigned long long bk = 0ull; int bt = 0x7FFFFFFF, bp = -1;
-                for (int c = tid; c < C + nbest; c += XT) {
-                    unsigned long long ak; int ee;
-                    if (c < C) { const int kk = keys[c]; if (kk == 0) continue; ak = abs_key(vals[c].x); ee = kk - 1; }
-                    else { ak = S.best_key[c - C]; ee = S.best_end[c - C]; }
-                    if (r > 0 && !better(last_k, last_t, ak, ee)) continue;
-                    if (bp < 0 || better(ak, ee, bk, bt)) { bk = ak; bt = ee; bp = c; }
-                }
-                warp_argbest(bk, bt, bp);
-                if (lane == 0) { S.r_key[warp] = bk; S.r_tie[warp] = bt; S.r_pos[warp] = bp; }
-                __syncthreads();
-                bk = lane < XW ? S.r_key[lane] : 0ull; bt = lane < XW ? S.r_tie[lane] : 0x7FFFFFFF; bp = lane < XW ? S.r_pos[lane] : -1;
-                warp_argbest(bk, bt, bp);
-                if (tid == 0 && bp >= 0) {
-                    sv_key[r] = bk; sv_end[r] = bt;
-                    sv_x[r] = bp < C ? vals[bp].x : S.best_x[bp - C];
-                }
-                last_k = bk; last_t = bt;
-                __syncthreads();
-            }
-            if (tid < newlen) { S.best_key[tid] = sv_key[tid]; S.best_x[tid] = sv_x[tid]; S.best_end[tid] = sv_end[tid]; }
-            if (tid == 0) S.best_len = newlen;
-        }
-        __syncthreads();
-    }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                cur_leg = nl; q0 += nq;
+                pass_combos += total;
 
-    // ---- publish the unit ------------------------------------------------------------------------
-    if (tid == 0) {
-        a.unit_count[u] = unit_count;
-        a.unit_combos[u] = combos;
-        a.unit_top_len[u] = S.best_len;
-        if (S.status) atomicExch(a.error_flag, 2);
-    }
-    if (tid < S.best_len) {
-        a.unit_top_end[(size_t)u * M + tid] = S.best_end[tid];
-        a.unit_top_xsim[(size_t)u * M + tid] = S.best_x[tid];
+                const int nchunk = (total + 31) >> 5;
+                Fetched nxt = fetch_chunk(a, 0, total, incl, len, base, dN, dD, dC, lane);
+                for (int c = 0; c < nchunk; ++c) {
+                    const Fetched cur = nxt;
+                    nxt = fetch_chunk(a, c + 1, total, incl, len, base, dN, dD, dC, lane);
+                    double num = 0.0, den = 0.0;
+                    if (cur.valid) {
+                        const double Nn = __dadd_rn(cur.N, cur.rn);
+                        const double Dd = __dadd_rn(cur.D, cur.rd);
+                        den = __dmul_rn(cur.C, cur.rc);
+                        const double sp = (Dd != 0.0) ? __ddiv_rn(Nn, Dd) : 0.0;      // extender.py:88-89
+                        num = __dmul_rn(sp, den);
+                    }
+                    W.u.acc.c_num[lane] = num; W.u.acc.c_den[lane] = den;
+                    const int y = cur.valid ? cur.y : (-1 - lane);
+                    const unsigned grp = __match_any_sync(0xffffffffu, y);
+                    __syncwarp();
+                    bool lane_ovf = false, inserted = false;
+                    if (cur.valid && (__ffs(grp) - 1) == lane) {
+                        // find-or-insert (only this warp touches the table; the CAS settles lanes racing for one empty cell)
+                        const int key = y + 1;
+                        int pos = (int)(((unsigned)y * XGOLD2) >> (32 - clg));
+                        int slot = -1;
+                        bool isnew = false;
+                        for (int probes = 0; probes < C; ++probes) {
+                            const int kcur = *(volatile int *)(keys + pos);
+                            if (kcur == key) { slot = pos; break; }
+                            if (kcur == 0) {
+                                const int old = atomicCAS(keys + pos, 0, key);
+                                if (old == 0) { slot = pos; isnew = true; break; }
+                                if (old == key) { slot = pos; break; }
+                            }
+                            pos = (pos + 1) & (C - 1);
+                        }
+                        inserted = isnew;
+                        if (slot < 0) lane_ovf = true;
+                        else {
+                            // the terms of this end, one by one in lane (= path) order
+                            double an = 0.0, ad = 0.0;
+                            if (!isnew) { const double2 v = vals[slot]; an = v.x; ad = v.y; }
+                            unsigned rem = grp;
+                            while (rem) {
+                                const int b = __ffs(rem) - 1;
+                                an = __dadd_rn(an, W.u.acc.c_num[b]); ad = __dadd_rn(ad, W.u.acc.c_den[b]);
+                                rem &= rem - 1u;
+                            }
+                            vals[slot] = make_double2(an, ad);
+                        }
+                    }
+                    __syncwarp();                                  // staging reads done before the next chunk's writes
+                    n_ins += __popc(__ballot_sync(0xffffffffu, inserted));
+                    ovf = __any_sync(0xffffffffu, lane_ovf) || n_ins > C - (C >> 3);   // linear probing degrades past 7/8
+                    if (ovf) break;
+                }
+            }
+            if (ovf) {
+                // the pass does not fit: halve its tile range and redo both halves (nothing of it was published)
+                if (g1 - g0 < 2 || stack_n + 2 > XSTACK) status = 1;
+                else {
+                    const int mid = (g0 + g1) >> 1;
+                    if (lane == 0) {
+                        W.stack_g0[stack_n] = mid; W.stack_g1[stack_n] = g1;
+                        W.stack_g0[stack_n + 1] = g0; W.stack_g1[stack_n + 1] = mid;
+                    }
+                    stack_n += 2;
+                }
+                __syncwarp();
+                continue;
+            }
+            combos += pass_combos;
+
+            // =================== finalize the pass ==============================================
+            // xsim of every cell (kept in vals[c].x), count, lane-local best, optional emit
+            int mycnt = 0;
+            unsigned long long lk = 0ull; int le = 0x7FFFFFFF;
+            for (int c0 = 0; c0 < C; c0 += 32) {
+                const int c = c0 + lane;
+                const int kk = keys[c];
+                const bool occ = kk != 0;
+                double x = 0.0;
+                if (occ) {
+                    const double2 v = vals[c];
+                    x = __ddiv_rn(v.x, v.y);                   // extender.py:198-201
+                    vals[c].x = x;
+                    ++mycnt;
+                    const unsigned long long ak = abs_key(x);
+                    if (mycnt == 1 || better(ak, kk - 1, lk, le)) { lk = ak; le = kk - 1; }
+                }
+                if (a.emit_ptr) {
+                    const unsigned mo = __ballot_sync(0xffffffffu, occ);
+                    if (occ) {
+                        const long long o = a.emit_ptr[u] + emitted + __popc(mo & lt_mask);
+                        a.emit_end[o] = kk - 1; a.emit_xsim[o] = x;
+                    }
+                    emitted += __popc(mo);
+                }
+            }
+            const unsigned have = __ballot_sync(0xffffffffu, mycnt > 0);
+            int cnt_pass = mycnt;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) cnt_pass += __shfl_xor_sync(0xffffffffu, cnt_pass, off);
+            unit_count += cnt_pass;
+            const int newlen = min(M, cnt_pass + best_len);
+            __syncwarp();
+            // threshold (tk, te): a candidate worse than it cannot enter the list
+            unsigned long long tk = 0ull; int te = 0x7FFFFFFF;
+            bool fast = M <= 32;
+            if (fast && cnt_pass > XSV / 2 && __popc(have) >= M) {
+                // the M-th best of the lane-local maxima bounds the M-th best cell from below
+                const int want = M;
+                int rank = 0;
+                for (int t = 0; t < 32; ++t) {
+                    const unsigned long long k2 = __shfl_sync(0xffffffffu, lk, t);
+                    const int e2 = __shfl_sync(0xffffffffu, le, t);
+                    if (((have >> t) & 1u) && better(k2, e2, lk, le)) ++rank;
+                }
+                const unsigned sel = __ballot_sync(0xffffffffu, mycnt > 0 && rank == want - 1);
+                const int sl = __ffs(sel) - 1;
+                tk = __shfl_sync(0xffffffffu, lk, sl); te = __shfl_sync(0xffffffffu, le, sl);
+            }
+            if (best_len == M) {
+                const unsigned long long bk = W.best_key[M - 1]; const int be = W.best_end[M - 1];
+                if (better(bk, be, tk, te)) { tk = bk; te = be; }
+            }
+            // survivors: cells not worse than the threshold
+            int nsurv = 0;
+            for (int c0 = 0; c0 < C && fast; c0 += 32) {
+                const int c = c0 + lane;
+                const int kk = keys[c];
+                bool take = false;
+                unsigned long long ak = 0ull; double x = 0.0;
+                if (kk != 0) { x = vals[c].x; ak = abs_key(x); take = !better(tk, te, ak, kk - 1); }
+                const unsigned mt = __ballot_sync(0xffffffffu, take);
+                if (nsurv + __popc(mt) > XSV / 2) { fast = false; break; }
+                if (take) { const int q = nsurv + __popc(mt & lt_mask); W.u.sv.key[q] = ak; W.u.sv.x[q] = x; W.u.sv.end[q] = kk - 1; }
+                nsurv += __popc(mt);
+            }
+            if (fast) {
+                // candidates = survivors + the running best; rank by counting, winners rewrite the list
+                if (lane < best_len) { W.u.sv.key[nsurv + lane] = W.best_key[lane]; W.u.sv.x[nsurv + lane] = W.best_x[lane]; W.u.sv.end[nsurv + lane] = W.best_end[lane]; }
+                __syncwarp();
+                const int ncand = nsurv + best_len;                 // <= XSV
+                for (int q = lane; q < ncand; q += 32) {
+                    const unsigned long long mk = W.u.sv.key[q]; const int me = W.u.sv.end[q];
+                    int rank = 0;
+                    for (int t = 0; t < ncand; ++t) rank += better(W.u.sv.key[t], W.u.sv.end[t], mk, me) ? 1 : 0;
+                    if (rank < newlen) { W.best_key[rank] = mk; W.best_x[rank] = W.u.sv.x[q]; W.best_end[rank] = me; }
+                }
+            } else {
+                // slow path (top_m > 32, or one value repeated very often): newlen rounds of a warp arg-best over
+                // every cell and the running best; each round takes the best candidate strictly after the last
+                __syncwarp();
+                unsigned long long last_k = ~0ull; int last_t = -1;
+                for (int r = 0; r < newlen; ++r) {
+                    unsigned long long bk = 0ull; int bt = 0x7FFFFFFF, bp = -1;
+                    for (int c = lane; c < C + best_len; c += 32) {
+                        unsigned long long ak; int ee;
+                        if (c < C) { const int kk = keys[c]; if (kk == 0) continue; ak = abs_key(vals[c].x); ee = kk - 1; }
+                        else { ak = W.best_key[c - C]; ee = W.best_end[c - C]; }
+                        if (r > 0 && !better(last_k, last_t, ak, ee)) continue;
+                        if (bp < 0 || better(ak, ee, bk, bt)) { bk = ak; bt = ee; bp = c; }
+                    }
+                    warp_argbest(bk, bt, bp);
+                    if (lane == 0 && bp >= 0) {
+                        // the new list grows in the key array of the candidates; positions < r are final
+                        W.u.sv.key[r] = bk; W.u.sv.end[r] = bt;
+                        W.u.sv.x[r] = bp < C ? vals[bp].x : W.best_x[bp - C];
+                    }
+                    last_k = bk; last_t = bt;
+                }
+                __syncwarp();
+                for (int q = lane; q < newlen; q += 32) { W.best_key[q] = W.u.sv.key[q]; W.best_x[q] = W.u.sv.x[q]; W.best_end[q] = W.u.sv.end[q]; }
+            }
+            best_len = newlen;
+            __syncwarp();
+        }
+
+        // ---- publish the unit --------------------------------------------------------------------
+        if (lane == 0) {
+            a.unit_count[u] = unit_count;
+            a.unit_combos[u] = combos;
+            a.unit_top_len[u] = best_len;
+            if (status) atomicExch(a.error_flag, 2);
+        }
+        for (int q = lane; q < best_len; q += 32) {
+            a.unit_top_end[(size_t)u * M + q] = W.best_end[q];
+            a.unit_top_xsim[(size_t)u * M + q] = W.best_x[q];
+        }
+        __syncwarp();
     }
 }
 
@@ -503,20 +425,29 @@ __global__ void __launch_bounds__(256) xsim_merge_kernel(xmap_xsim_args a) {
 
 using namespace xmap;
 
-extern "C" int64_t xmap_xsim_smem_bytes(int32_t cells_lg) {
-    return (int64_t)((sizeof(XShared) + 15) & ~(size_t)15) + ((int64_t)20 << cells_lg);
+extern "C" int64_t xmap_xsim_smem_bytes(int32_t cells_lg, int32_t warps) {
+    return (int64_t)warps * ((int64_t)sizeof(WarpScratch) + ((int64_t)20 << cells_lg));
 }
 
 extern "C" int xmap_xsim_extend(const xmap_xsim_args *args_h, void *stream_) {
     const xmap_xsim_args &a = *args_h;
     if (a.n_starts <= 0 || a.n_units <= 0) return 0;
     if (a.top_m < 1 || a.top_m > XMAP_KMAX) return fail_msg("xmap_xsim_extend: top_m out of range");
-    if (a.cells_lg < 9 || a.cells_lg > XMAP_XSIM_MAX_CELLS_LG) return fail_msg("xmap_xsim_extend: cells_lg out of range");
+    if (a.cells_lg < 6 || a.cells_lg > XMAP_XSIM_MAX_CELLS_LG) return fail_msg("xmap_xsim_extend: cells_lg out of range");
+    if (a.gws && (a.gcells_lg < a.cells_lg || a.gcells_lg > 24)) return fail_msg("xmap_xsim_extend: gcells_lg out of range");
     if (a.gb < 0 || a.gb > 16) return fail_msg("xmap_xsim_extend: gb out of range");
+    if (a.warps < 1 || a.warps * 32 > XT_MAX) return fail_msg("xmap_xsim_extend: warps per CTA out of range");
+    if (!a.unit_counter) return fail_msg("xmap_xsim_extend: unit_counter is required");
     cudaStream_t st = (cudaStream_t)stream_;
-    const size_t smem = (size_t)xmap_xsim_smem_bytes(a.cells_lg);
-    XMAP_CUDA(cudaFuncSetAttribute(xsim_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    xsim_tile_kernel<<<(unsigned)a.n_units, XT, smem, st>>>(a);
+    const size_t smem = (size_t)xmap_xsim_smem_bytes(a.cells_lg, a.warps);
+    if (smem > 227 * 1024) return fail_msg("xmap_xsim_extend: warps x table exceed shared memory");
+    XMAP_CUDA(cudaFuncSetAttribute(xsim_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    XMAP_CUDA(cudaMemsetAsync(a.unit_counter, 0, sizeof(int32_t), st));
+    int dev = 0, sms = 148;
+    XMAP_CUDA(cudaGetDevice(&dev));
+    XMAP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long ctas = min((long long)sms, ((long long)a.n_units + a.warps - 1) / a.warps);
+    xsim_warp_kernel<<<(unsigned)ctas, a.warps * 32, smem, st>>>(a);
     XMAP_LAUNCH_CHECK();
     if (a.merge) {
         xsim_merge_kernel<<<(unsigned)((a.n_starts + 7) / 8), 256, 0, st>>>(a);

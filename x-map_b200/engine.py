@@ -135,26 +135,39 @@ def _threads_for_cells(c):
     """Threads per row a table capacity gets at least: 8 cells per thread (measured best of 4 / 8 / 16 / 32)."""
     return max(32, min(512, (c // 8 + 31) // 32 * 32))
 
-REC_BYTES = 16
+REC_BYTES = 20                                              # 16-byte record + its int32 co-rating count
 SPLIT_RATERS = int(os.environ.get("XMAP_SPLIT_RATERS", "16384"))   # rows with at least this many raters are split ...
 SPLIT_SEG = 4096                                            # ... into segments of this many raters
 _PINNED = {}                                                # pinned host buffers of tables_to_host
-REC_CNT_LIMIT = 1 << 20                                     # n and mutu are 20-bit fields of a record
 
 
 _REC_POOL = {}                                              # device -> record buffers of finished engines
 
 
+def _rec_words(n_records):
+    """int64 words of the storage of n records: [n, 2] record words followed by the int32 counts."""
+    n = max(int(n_records), 1)
+    return 2 * n + (n + 1) // 2
+
+
 def _rec_buffer(n_records, device):
-    """Record-list storage [n, 2] int64.  The buffer is by far the largest allocation of the stage (12 GB
-    at cfg2); engines hand it back when they die and the next one takes it over, so a sequence of runs
-    does not depend on how the caching allocator happens to split and re-grow a block of that size."""
+    """Record-list storage (one flat int64 buffer, see _rec_views).  The buffer is by far the largest
+    allocation of the stage (15 GB at cfg2); engines hand it back when they die and the next one takes it
+    over, so a sequence of runs does not depend on how the caching allocator happens to split and re-grow
+    a block of that size."""
+    need = _rec_words(n_records)
     pool = _REC_POOL.setdefault(str(device), [])
-    fit = [q for q, t in enumerate(pool) if t.shape[0] >= max(n_records, 1)]
+    fit = [q for q, t in enumerate(pool) if t.numel() >= need]
     if fit:
-        return pool.pop(min(fit, key=lambda q: pool[q].shape[0]))      # by position: `in` / remove would compare tensors
+        return pool.pop(min(fit, key=lambda q: pool[q].numel()))      # by position: `in` / remove would compare tensors
     pool.clear()                                          # too small for this problem: let the allocator have them
-    return torch.empty((max(n_records, 1), 2), dtype=torch.int64, device=device)
+    return torch.empty(need, dtype=torch.int64, device=device)
+
+
+def _rec_views(raw, n_records):
+    """(rec [n, 2] int64 = {sim bits, other item | mutu << 32}, rec_n [n] int32) inside a raw buffer."""
+    n = max(int(n_records), 1)
+    return raw[:2 * n].view(n, 2), raw[2 * n:2 * n + (n + 1) // 2].view(torch.int32)[:n]
 
 
 def popularity_order(count):
@@ -187,9 +200,9 @@ class SimEngine:
         L = N.lib()
         # ---- triangular layout -------------------------------------------------------------------
         count = layout.item_stats[:, 3]
-        if I and float(count.max()) >= REC_CNT_LIMIT:
-            raise N.NativeError("an item has >= 2^20 ratings: neighbour records hold 20-bit co-rating counts")
         self.ord = popularity_order(count)
+        self.ord_item = torch.empty(I, dtype=torch.int32, device=dev)
+        self.ord_item[self.ord.long()] = torch.arange(I, dtype=torch.int32, device=dev)
         self.tcsr_ent = torch.empty(layout.nnz, dtype=torch.int64, device=dev)
         self.csc_aux = torch.empty((layout.nnz, 2), dtype=torch.int64, device=dev)
         self.ostat = torch.empty(max(I, 1) * 16, dtype=torch.uint8, device=dev)
@@ -216,7 +229,10 @@ class SimEngine:
             pooled = max((t.numel() * 8 for t in _REC_POOL.get(str(dev), [])), default=0)
             rec_budget = max(free // 2, pooled)
         self.exact_sizing = total * REC_BYTES > rec_budget
-        self.rec = None if self.exact_sizing else _rec_buffer(total, dev)
+        self._rec_raw = None
+        self.rec = self.rec_n = None
+        if not self.exact_sizing:
+            self._set_rec(_rec_buffer(total, dev), total)
         self.rec_cnt = torch.zeros(I, dtype=torch.int32, device=dev)
         self.bb = torch.zeros(I, dtype=torch.uint8, device=dev)
         self.row_npairs = torch.zeros(I, dtype=torch.int32, device=dev)
@@ -231,20 +247,27 @@ class SimEngine:
         self._plans = {}
         self.profile = None        # dict kind -> [(start_event, end_event)] when enabled
 
-    def __del__(self):
-        rec = getattr(self, "rec", None)
-        if rec is not None and rec.shape[0] > (1 << 20):
-            pool = _REC_POOL.setdefault(str(rec.device), [])
+    def _set_rec(self, raw, n_records):
+        self._rec_raw = raw
+        self.rec, self.rec_n = _rec_views(raw, n_records)
+
+    def _give_back(self):
+        raw = getattr(self, "_rec_raw", None)
+        self._rec_raw = self.rec = self.rec_n = None
+        if raw is not None and raw.numel() > (1 << 21) and _REC_POOL is not None:
+            pool = _REC_POOL.setdefault(str(raw.device), [])
             if len(pool) < 2:
-                pool.append(rec)
+                pool.append(raw)
+
+    def __del__(self):
+        try:
+            self._give_back()
+        except Exception:            # interpreter shutdown: module globals may be gone
+            pass
 
     def release_lists(self):
         """Drop the record storage so that the next stage sizes the lists exactly (multi-GPU: decided collectively)."""
-        rec, self.rec = self.rec, None
-        if rec is not None and rec.shape[0] > (1 << 20):
-            pool = _REC_POOL.setdefault(str(rec.device), [])
-            if len(pool) < 2:
-                pool.append(rec)
+        self._give_back()
         self.exact_sizing = True
 
     # -- argument block ----------------------------------------------------
@@ -254,10 +277,11 @@ class SimEngine:
         a.csc_ptr, a.csc_ent, a.csc_aux = N.ptr(lay.csc_ptr), N.ptr(lay.csc_ent), N.ptr(self.csc_aux)
         a.tcsr_ent = N.ptr(self.tcsr_ent)
         a.ostat, a.ord, a.tri_work = N.ptr(self.ostat), N.ptr(self.ord), N.ptr(self.tri_work)
+        a.ord_item = N.ptr(self.ord_item)
         a.dom_code, a.contains = N.ptr(m.dom_code), N.ptr(m.contains)
         a.n_items, a.method = lay.n_items, N.METHODS[self.method]
         a.num_atleast, a.k, a.r2_bits = self.num_atleast, self.k, self.r2_bits
-        a.rec_ptr, a.rec_cnt, a.rec = N.ptr(self.rec_ptr), N.ptr(self.rec_cnt), N.ptr(self.rec)
+        a.rec_ptr, a.rec_cnt, a.rec, a.rec_n = N.ptr(self.rec_ptr), N.ptr(self.rec_cnt), N.ptr(self.rec), N.ptr(self.rec_n)
         a.count_only = 1 if self.rec is None else 0
         a.bb, a.row_npairs = N.ptr(self.bb), N.ptr(self.row_npairs)
         a.tab_idx, a.tab_sim = N.ptr(self.tab_idx), N.ptr(self.tab_sim)
@@ -392,7 +416,7 @@ class SimEngine:
         with count_only = 1, the list lengths become the extents.  In a multi-GPU run the lengths are
         this rank's own records; the exchange appends the others', so the caller must add them (see
         multi.similarity_step)."""
-        self.rec = None
+        self._give_back()
         self.reset()
         self._accumulate(rows)
         self._check_error()
@@ -404,7 +428,7 @@ class SimEngine:
         self.rec_ptr[1:] = torch.cumsum(lengths, 0)
         self.rec_cap = lengths
         total = int(self.rec_ptr[-1].item()) if I else 0
-        self.rec = _rec_buffer(total, dev)
+        self._set_rec(_rec_buffer(total, dev), total)
         self._plans = {}
         self.reset()
 
@@ -526,9 +550,9 @@ class SimEngine:
         src = self.rec_ptr[:-1][i] + (torch.arange(i.numel(), device=dev) - first[i])
         r = self.rec[src]
         pack = r[:, 1]
-        j = pack & 0xFFFFFF
-        n = ((pack >> 24) & 0xFFFFF).to(torch.int32)
-        mutu = ((pack >> 44) & 0xFFFFF).to(torch.int32)
+        j = pack & 0xFFFFFFFF
+        n = self.rec_n[src]
+        mutu = ((pack >> 32) & 0xFFFFFFFF).to(torch.int32)
         sim = r[:, 0].contiguous().view(torch.float64)
         order = torch.argsort(i * I + j)
         i, j, sim, mutu, n = i[order], j[order], sim[order], mutu[order], n[order]

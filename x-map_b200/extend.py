@@ -20,6 +20,7 @@ cannot change a value and every edge is read from the row that lists it.
 All index building is torch (sort / cumsum / repeat_interleave) on whatever
 device the tables live on; the path evaluation itself is the CUDA kernel.
 """
+import os
 from dataclasses import dataclass
 
 import torch
@@ -227,12 +228,19 @@ def build_plan(tabs, item_count, has_S, has_T):
 
 
 PI_MULT = 0x9E3779B1            # pi(y) = (y * PI_MULT) mod 2^32 orders every right-segment list (csrc/xsim.cu)
-XSIM_CELLS_LG = N.XSIM_MAX_CELLS_LG     # 8192-cell shared-memory table per CTA
-XSIM_LOAD = 0.62                # target fill of the table (16 owner regions of cells / 16 each)
+XSIM_CELLS_LG = int(os.environ.get("XMAP_XSIM_CELLS_LG", "9"))    # 512-cell shared-memory table per warp ...
+XSIM_WARPS = int(os.environ.get("XMAP_XSIM_WARPS", "20"))         # ... 20 warps per CTA (limited by registers: 94 x 640)
+XSIM_LOAD = 0.62                # target fill of a table
 XSIM_RHO = 1.25                 # assumed paths per distinct end when a start's pass count is chosen
                                 # (measured at cfg2: 10 % quantile 1.30, median 1.62; a pass that turns out
                                 # too full is split on the device)
-XSIM_UNIT_WORK = 1 << 21        # paths per CTA: heavier starts are cut into several units (disjoint end ranges)
+XSIM_UNIT_WORK = 1 << int(os.environ.get("XMAP_XSIM_UNIT_LG", "17"))   # paths per unit (= per warp): heavier starts are
+                                # cut into more units (disjoint end ranges)
+XSIM_MAX_PASSES = int(os.environ.get("XMAP_XSIM_MAX_PASSES", "1000000000"))   # cap on the passes a start is cut into for
+                                # table capacity; a unit whose ends then exceed the shared-memory table keeps its table in
+                                # global memory (L2).  Measured at cfg2: 32 passes + L2 tables 968 ms, shared memory only
+                                # (no cap) 732 ms -- dependent read-modify-writes at L2 latency lose to narrow passes
+XSIM_GCELLS_LG = 16             # largest global-memory table of a unit (cells)
 
 
 @dataclass
@@ -251,18 +259,22 @@ class XsimEngine:
     """Runs the extension kernels over an XsimPlan (C ABI section 3).
 
     The accumulator of a start lives in shared memory.  The end axis is hashed (pi) and cut into 2^gb
-    tiles; a start evaluates its paths in passes over tile ranges small enough for the table, a CTA
-    ("unit") runs one or more passes of one start, heavy starts are spread over several units.  Every
-    (start, end) sum is formed in path order (leg, partner, right segment), so results are bit-identical
-    for any table size, pass split, unit split or number of GPUs."""
+    tiles; a start evaluates its paths in passes over tile ranges small enough for a warp's table, a warp
+    runs one unit = one or more passes of one start, heavy starts are spread over several units.  The
+    summation order of a (start, end) cell depends on the path structure and this plan only, so results
+    are bit-identical from run to run and for any number of GPUs."""
 
     def __init__(self, plan, top_m=10, cells_lg=XSIM_CELLS_LG, rho=XSIM_RHO, unit_work=XSIM_UNIT_WORK,
-                 load=XSIM_LOAD):
+                 load=XSIM_LOAD, warps=XSIM_WARPS, max_passes=XSIM_MAX_PASSES):
         if not (1 <= top_m <= N.KMAX):
             raise ValueError("top_m must be in [1, %d]" % N.KMAX)
-        if not (9 <= cells_lg <= N.XSIM_MAX_CELLS_LG):
-            raise ValueError("cells_lg must be in [9, %d]" % N.XSIM_MAX_CELLS_LG)
-        self.plan, self.top_m, self.cells_lg = plan, int(top_m), int(cells_lg)
+        if not (6 <= cells_lg <= N.XSIM_MAX_CELLS_LG):
+            raise ValueError("cells_lg must be in [6, %d]" % N.XSIM_MAX_CELLS_LG)
+        warps = int(warps)
+        while warps > 1 and N.lib().xmap_xsim_smem_bytes(int(cells_lg), warps) > 227 * 1024:
+            warps -= 1
+        self.plan, self.top_m, self.cells_lg, self.warps = plan, int(top_m), int(cells_lg), warps
+        self.unit_counter = torch.zeros(1, dtype=torch.int32, device=plan.start_item.device)
         p = plan
         dev = self.device = p.start_item.device
         self.launches = 0
@@ -294,8 +306,8 @@ class XsimEngine:
         r1, rm1, rf1, r2, rm2, rf2 = p.rs_vals
         rl = p.rs_ptr[1:] - p.rs_ptr[:-1]
         n_s = int(rl.numel())
-        if n_s and int(rl.max()) >= (1 << 22):
-            raise N.NativeError("a right-segment list has >= 2^22 entries: the per-batch product counter is 32-bit")
+        if n_s and int(rl.max()) >= (1 << 26):
+            raise N.NativeError("a right-segment list has >= 2^26 entries: the per-batch product counter is 32-bit")
         seg = _segment_ids(rl)
         pi = (p.rs_end.long() * PI_MULT) & 0xFFFFFFFF
         perm = torch.argsort(seg * (1 << 32) + pi, stable=True) if seg.numel() else seg
@@ -307,14 +319,17 @@ class XsimEngine:
         cap = max(16.0, load * (1 << self.cells_lg))
         ub = p.ub.double()
         e_est = torch.clamp(ub / float(rho), max=float(self.end_cap))
-        T = torch.clamp(torch.ceil(e_est / cap), min=1).long()
+        T_fit = torch.clamp(torch.ceil(e_est / cap), min=1).long()             # passes whose ends fit shared memory
         n_units_x = torch.clamp(torch.ceil(ub / float(unit_work)), min=1).long()
-        n_units_x = torch.minimum(n_units_x, torch.clamp(T * 4, min=1))         # a few passes' worth of splitting at most
-        T = torch.maximum(T, n_units_x)
+        n_units_x = torch.minimum(n_units_x, T_fit)                             # at most one unit per such pass
+        # few, wide passes keep the sub-range of a (leg, partner) pair long (full sectors, few duplicates per
+        # 32-path step, few pair look-ups); a pass whose ends exceed the shared-memory table runs with a larger
+        # table in global memory.  Heavy starts still get one pass per unit (parallelism).
+        T = torch.maximum(torch.clamp(T_fit, max=max(1, int(max_passes))), n_units_x)
         t_max = int(T.max().item()) if n else 1
-        # 2^gb tiles: at least twice the largest pass count (so pass boundaries fall close to the ideal cut)
-        # and one more level for device-side splits
-        self.gb = min(12, max(2, (2 * t_max - 1).bit_length() + 1))
+        # 2^gb tiles: at least the largest pass count (its passes are sized by the true bound end_cap and never
+        # overflow); lighter starts have many tiles per pass, so an overflowing pass can be halved on the device
+        self.gb = min(14, max(4, (t_max - 1).bit_length()))
         G = 1 << self.gb
         T = torch.clamp(T, max=G)
         n_units_x = torch.clamp(n_units_x, max=G)
@@ -338,6 +353,15 @@ class XsimEngine:
         self.unit_npass = torch.minimum(ppu[us], (self.unit_g1 - self.unit_g0).long()).to(i32).contiguous()
         self.unit_leg_lo = p.leg_ptr[:-1][us].contiguous()
         self.unit_leg_hi = p.leg_ptr[1:][us].contiguous()
+        # table a unit wants: its share of the start's estimated ends at the target load
+        e_unit = e_est[us] / T[us].double()
+        want = torch.ceil(torch.log2(torch.clamp(e_unit / float(load), min=2.0))).long()
+        self.gcells_lg = int(min(XSIM_GCELLS_LG, max(int(want.max().item()) if self.n_units else 0, self.cells_lg)))
+        self.unit_clg = torch.clamp(want, min=self.cells_lg, max=self.gcells_lg).to(i32).contiguous()
+        self.gws = None
+        if self.gcells_lg > self.cells_lg:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count if dev.type == "cuda" else 1
+            self.gws = torch.empty(sms * self.warps * (20 << self.gcells_lg), dtype=torch.uint8, device=dev)
         unit_work_est = ub[us] / nu.double()
         self.unit_order = torch.argsort(unit_work_est, descending=True, stable=True).to(i32).contiguous()
         self.T, self.n_units_x = T, n_units_x
@@ -361,7 +385,9 @@ class XsimEngine:
         a.rs_ptr, a.rs_end = P(p.rs_ptr), P(self.rs_end)
         a.rs_n, a.rs_d, a.rs_c = [P(v) for v in self.rs_ndc]
         a.tile_ptr, a.gb = P(self.tile_ptr), self.gb
-        a.cells_lg, a.top_m = self.cells_lg, self.top_m
+        a.cells_lg, a.top_m, a.warps = self.cells_lg, self.top_m, self.warps
+        a.unit_counter = N.ptr(self.unit_counter)
+        a.unit_clg, a.gws, a.gcells_lg = P(self.unit_clg), N.ptr(self.gws), self.gcells_lg
         a.error_flag = N.ptr(self.error_flag)
         return a
 

@@ -106,17 +106,18 @@ def _list_slots(base, seg):
     return base[r] + (torch.arange(tot, device=seg.device) - first[r]), tot
 
 
-def _segmented_copy(src, src_pos, dst, dst_pos, seg_len):
-    """dst[dst_pos[g] + k] = src[src_pos[g] + k] for k < seg_len[g] (16-byte records, CUDA)."""
+def _segmented_copy(src, src_pos, dst, dst_pos, seg_len, total=None):
+    """dst[dst_pos[g] + k] = src[src_pos[g] + k] for k < seg_len[g] (16-byte records or their int32 counts, CUDA)."""
     from . import _native as N
     seg_off = (torch.cumsum(seg_len, 0) - seg_len).contiguous()
-    total = int(seg_len.sum())
-    N.check(N.lib().xmap_segmented_copy16(N.ptr(src), N.ptr(src_pos.contiguous()), N.ptr(dst),
-                                          N.ptr(dst_pos.contiguous()), N.ptr(seg_off), int(seg_len.numel()), total,
-                                          torch.cuda.current_stream().cuda_stream), "xmap_segmented_copy16")
+    if total is None:
+        total = int(seg_len.sum())
+    fn = N.lib().xmap_segmented_copy4 if src.dtype == torch.int32 else N.lib().xmap_segmented_copy16
+    N.check(fn(N.ptr(src), N.ptr(src_pos.contiguous()), N.ptr(dst), N.ptr(dst_pos.contiguous()), N.ptr(seg_off),
+               int(seg_len.numel()), total, torch.cuda.current_stream().cuda_stream), "xmap_segmented_copy")
 
 
-def exchange_records_cuda(rec, rec_ptr, rec_cnt, shard, group=None):
+def exchange_records_cuda(rec, rec_ptr, rec_cnt, shard, group=None, rec_n=None):
     """exchange_records on the GPU: one packing kernel, one all-to-all of the lengths, one all-to-all
     of the records (NCCL), one appending kernel; two small device -> host reads for the split sizes."""
     world, rank, dev = shard.world, shard.rank, rec.device
@@ -137,29 +138,33 @@ def exchange_records_cuda(rec, rec_ptr, rec_cnt, shard, group=None):
     RC = torch.stack(recv_cnt)                               # [world, own]; row `rank` is zero
     sizes = torch.cat([in_split, RC.sum(1)]).tolist()         # the one host read
     in_sizes, out_sizes = sizes[:world], sizes[world:]
-    send = torch.empty((max(sum(in_sizes), 1), 2), dtype=rec.dtype, device=dev)
-    _segmented_copy(rec, rec_ptr[:-1], send, csum[:-1], out_cnt)
-    recv = torch.empty((max(sum(out_sizes), 1), 2), dtype=rec.dtype, device=dev)
-    dist.all_to_all_single(recv[:sum(out_sizes)], send[:sum(in_sizes)], out_sizes, in_sizes, group=group)
+    n_in, n_out = sum(in_sizes), sum(out_sizes)
     # append: source-major segments (s, row) land after the row's own records and the earlier sources'
     before = torch.cumsum(RC, 0) - RC + cnt[lo:hi].unsqueeze(0)
     seg_len = RC.reshape(-1)
     src_pos = torch.cumsum(seg_len, 0) - seg_len
     dst_pos = (rec_ptr[lo:hi].unsqueeze(0) + before).reshape(-1)
-    _segmented_copy(recv, src_pos, rec, dst_pos, seg_len)
+    for arr in (rec,) if rec_n is None else (rec, rec_n):          # the int32 counts travel like the records
+        tail = tuple(arr.shape[1:])
+        send = torch.empty((max(n_in, 1),) + tail, dtype=arr.dtype, device=dev)
+        _segmented_copy(arr, rec_ptr[:-1], send, csum[:-1], out_cnt, total=n_in)
+        recv = torch.empty((max(n_out, 1),) + tail, dtype=arr.dtype, device=dev)
+        dist.all_to_all_single(recv[:n_out], send[:n_in], out_sizes, in_sizes, group=group)
+        _segmented_copy(recv, src_pos, arr, dst_pos, seg_len, total=n_out)
     new_cnt = cnt[lo:hi] + RC.sum(0)
     rec_cnt.zero_()
     rec_cnt[lo:hi] = new_cnt.to(rec_cnt.dtype)
 
 
-def exchange_records(rec, rec_ptr, rec_cnt, shard, group=None):
-    """rec [total, 2] int64 records, rec_ptr [I + 1] list extents, rec_cnt [I] list lengths.
+def exchange_records(rec, rec_ptr, rec_cnt, shard, group=None, rec_n=None):
+    """rec [total, 2] int64 records (rec_n [total] int32: their co-rating counts, moved alongside),
+    rec_ptr [I + 1] list extents, rec_cnt [I] list lengths.
     On entry the lists hold the records THIS rank produced, for every row; on exit the lists of the
     rows this rank owns hold the records of every rank and the other lists are empty."""
     if shard.world == 1:
         return
     if rec.is_cuda:
-        return exchange_records_cuda(rec, rec_ptr, rec_cnt, shard, group)
+        return exchange_records_cuda(rec, rec_ptr, rec_cnt, shard, group, rec_n)
     world, rank = shard.world, shard.rank
     cnt = rec_cnt.long()
     blocks = [(shard.bounds[s], shard.bounds[s + 1]) for s in range(world)]
@@ -167,23 +172,25 @@ def exchange_records(rec, rec_ptr, rec_cnt, shard, group=None):
     own = shard.hi - shard.lo
     recv_cnt = [torch.empty(own, dtype=torch.int64, device=rec.device) for _ in range(world)]
     _all_to_all(recv_cnt, send_cnt, group)
-    send_buf = []
-    for s, (lo, hi) in enumerate(blocks):
-        if s == rank:
-            send_buf.append(rec.new_empty((0, 2)))
-            continue
-        src, _ = _list_slots(rec_ptr[lo:hi], send_cnt[s])
-        send_buf.append(rec[src])
-    recv_buf = [rec.new_empty((0 if s == rank else int(recv_cnt[s].sum()), 2)) for s in range(world)]
-    _all_to_all(recv_buf, send_buf, group)
-    cur = cnt[shard.lo:shard.hi].clone()
-    for s in range(world):
-        if s == rank:
-            continue
-        dst, tot = _list_slots(rec_ptr[shard.lo:shard.hi] + cur, recv_cnt[s])
-        if tot:
-            rec[dst] = recv_buf[s]
-        cur += recv_cnt[s]
+    for arr in (rec,) if rec_n is None else (rec, rec_n):
+        tail = tuple(arr.shape[1:])
+        send_buf = []
+        for s, (lo, hi) in enumerate(blocks):
+            if s == rank:
+                send_buf.append(arr.new_empty((0,) + tail))
+                continue
+            src, _ = _list_slots(rec_ptr[lo:hi], send_cnt[s])
+            send_buf.append(arr[src])
+        recv_buf = [arr.new_empty((0 if s == rank else int(recv_cnt[s].sum()),) + tail) for s in range(world)]
+        _all_to_all(recv_buf, send_buf, group)
+        cur = cnt[shard.lo:shard.hi].clone()
+        for s in range(world):
+            if s == rank:
+                continue
+            dst, tot = _list_slots(rec_ptr[shard.lo:shard.hi] + cur, recv_cnt[s])
+            if tot:
+                arr[dst] = recv_buf[s]
+            cur += recv_cnt[s]
     rec_cnt.zero_()
     rec_cnt[shard.lo:shard.hi] = cur.to(rec_cnt.dtype)
 
@@ -216,7 +223,8 @@ def similarity_step(engine, shard, group=None):
     engine.reset()
     stats = engine.accumulate(rows)
     if shard.world > 1:
-        engine._timed("exchange", lambda: exchange_records(engine.rec, engine.rec_ptr, engine.rec_cnt, shard, group))
+        engine._timed("exchange", lambda: exchange_records(engine.rec, engine.rec_ptr, engine.rec_cnt, shard, group,
+                                                                   rec_n=engine.rec_n))
         dist.all_reduce(engine.bb, op=dist.ReduceOp.MAX, group=group)
     engine.select(rows)
     nkept = None
