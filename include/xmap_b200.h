@@ -268,6 +268,12 @@ typedef struct xmap_xsim_args {
 
 int64_t xmap_xsim_smem_bytes(int32_t cells_lg, int32_t warps);
 int xmap_xsim_extend(const xmap_xsim_args *args_h, void *stream);
+/* CTA-cooperative variant: one CTA of 8 warps per unit (blockIdx b runs unit_order[b]) with ONE table of
+ * 2^cells_lg cells (two CTAs per SM); products are routed through shared memory to the warp that owns the
+ * end's table region.  Same unit arrays, outputs and determinism contract; unit_counter / warps / unit_clg /
+ * gws are not used. */
+int64_t xmap_xsim_cta_smem_bytes(int32_t cells_lg);
+int xmap_xsim_extend_cta(const xmap_xsim_args *args_h, void *stream);
 /* only the per-start merge (multi-GPU: after the unit results of all ranks have been summed) */
 int xmap_xsim_merge(const xmap_xsim_args *args_h, void *stream);
 
@@ -302,6 +308,30 @@ int xmap_build_alterego(const int32_t *csr_ptr, const uint64_t *csr_ent, const i
                         const int64_t *ts, int32_t n_users, int64_t nnz, const int32_t *map,
                         int32_t *out_user, int32_t *out_item, double *out_rating, int64_t *out_ts,
                         int64_t *n_out_h, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * (5) RecommenderSim on the AlterEgo profile: item-item cosine with significance
+ * weighting + per-pair local sensitivity.
+ * Replaces: RecommenderSim.get_info / produce_pairwise / cosine_sim / calculate_sim with method
+ * "cosine_item" (recommenderSim.py:29-62, 64-75, 90-132, 186-195; assist.py:153-175).
+ * The profile is a flat record list (a (user, item) pair may occur twice; nothing is deduplicated or
+ * filtered; self pairs (i, i) exist).
+ *   xmap_recsim_item_info : info[3*i..] = (average, norm2, count) over the records of item i, the records
+ *                           grouped by item (item_ptr [n_items + 1], rating_by_item).
+ *   xmap_recsim_fill_entries: records grouped by user in list order (user_ptr [n_users + 1]); user u owns
+ *                           entries [ent_off[u], ent_off[u+1]) with ent_off = exclusive scan of d(d-1).
+ *                           key[t] = item_a * n_items + item_b, src[t] = pos_a << 32 | pos_b, t in the
+ *                           reference's emission order, so a STABLE sort by key keeps arrival order.
+ *   xmap_recsim_pairs     : per run of equal keys [seg_ptr[g], seg_ptr[g+1]) of the sorted entries:
+ *                           (i, j, n, sim, local sensitivity); NaN rule of Python's max() reproduced.
+ * ------------------------------------------------------------------------- */
+int xmap_recsim_item_info(const int64_t *item_ptr, const double *rating_by_item, int32_t n_items, double *info,
+                          void *stream);
+int xmap_recsim_fill_entries(const int64_t *user_ptr, const int64_t *ent_off, int32_t n_users, const int32_t *item,
+                             int64_t n_items, int64_t total, int64_t *key, int64_t *src, void *stream);
+int xmap_recsim_pairs(const int64_t *seg_ptr, const int64_t *seg_key, const int64_t *src, const double *rating,
+                      const double *info, int64_t n_items, int64_t n_pairs, int32_t num_atleast,
+                      int32_t *out_i, int32_t *out_j, int64_t *out_n, double *out_sim, double *out_ls, void *stream);
 
 #ifdef __cplusplus
 }

@@ -106,44 +106,59 @@ def sim_pairs(user, item, rating, n_users, n_items, prefix_code,
 
 def sim_rows(user, item, rating, n_users, n_items, prefix_code, rows,
              method="adjust_cosine", num_atleast=50):
-    """sim_pairs restricted to the directed pairs (i, j) with i in `rows` (a 1-D array of item indices):
-    the same arithmetic on R^T R[rows, :], so that a full-size input (BASELINE.json configs[1]) can be
-    checked on a sample of item rows within host memory.  Returns the kept pairs sorted by (i, j) and,
-    per sampled row, the number of co-rated columns (pre-filter)."""
+    """sim_pairs restricted to the directed pairs (i, j) with i in `rows` (a 1-D array of item indices), so
+    that a full-size input (BASELINE.json configs[1]) can be checked on a sample of item rows.  One row at a
+    time: the ratings of the row's raters are gathered (ascending user, like the reference's arrival order
+    under the canonical rules) and reduced per column with np.bincount, which adds in array order.  Returns
+    the kept pairs sorted by (i, j) and, per sampled row, the number of co-rated columns (pre-filter)."""
     rows = np.unique(np.asarray(rows, dtype=np.int64))
     order = np.lexsort((item, user))
     user, item, rating = user[order], item[order], rating[order]
     st = user_item_stats(user, item, rating, n_users, n_items)
     r = rating.astype(np.float64)
-    shape = (n_users, n_items)
     if method == "adjust_cosine":
         val, den = r - st["mu"][user], st["adj_norm2"]
     elif method == "cosine":
         val, den = r, st["norm2"]
     else:
         raise ValueError(method)
-    a = (r >= st["avg"][item]).astype(np.float64)
-    mk = lambda v: sp.csr_matrix((v, (user, item)), shape=shape)
-    M, C, A, B = mk(np.ones(len(user))), mk(val), mk(a), mk(1.0 - a)
-    sub = lambda X: X.tocsc()[:, rows].T.tocsr()                     # [len(rows), n_users]
-    N = (sub(M) @ M).tocoo()
-    ri, j = N.row.astype(np.int64), N.col.astype(np.int64)
-    i = rows[ri]
-    keep = i != j
-    ri, i, j, n = ri[keep], i[keep], j[keep], np.rint(N.data[keep])
-    o = np.lexsort((j, i))
-    ri, i, j, n = ri[o], i[o], j[o], n[o]
-    inner = np.asarray((sub(C) @ C).tocsr()[ri, j]).ravel()
-    mutu = np.rint(np.asarray((sub(A) @ A + sub(B) @ B).tocsr()[ri, j]).ravel())
-    dd = den[i] * den[j]
-    with np.errstate(invalid="ignore", divide="ignore"):
-        cosv = np.where(dd != 0, 1.0 * inner / dd, 0.0)
-    sim = 1.0 * cosv * np.minimum(n, num_atleast) / num_atleast
-    frac = 1.0 * mutu / (st["count"][i] + st["count"][j] - n)
-    kept = (sim != 0.0) & (mutu != 0.0) & (frac != 0.0)
-    label = (prefix_code[i] != prefix_code[j]).astype(np.int32)
-    return dict(rows=rows, i=i[kept], j=j[kept], sim=sim[kept], mutu=mutu[kept], n=n[kept], frac=frac[kept],
-                label=label[kept], n_cols=np.bincount(ri, minlength=len(rows)), stats=st)
+    ge = (r >= st["avg"][item])                                   # baselinerSim.py:106-107
+    uptr = np.zeros(n_users + 1, dtype=np.int64); uptr[1:] = np.cumsum(np.bincount(user, minlength=n_users))
+    o2 = np.argsort(item, kind="stable")                          # CSC: ascending user inside a column
+    iptr = np.zeros(n_items + 1, dtype=np.int64); iptr[1:] = np.cumsum(np.bincount(item, minlength=n_items))
+    c_user, c_val, c_ge = user[o2], val[o2], ge[o2]
+    out = {k: [] for k in ("i", "j", "sim", "mutu", "n", "frac", "label")}
+    n_cols = np.zeros(len(rows), dtype=np.int64)
+    for q, i in enumerate(rows):
+        ru = c_user[iptr[i]:iptr[i + 1]]
+        lens = uptr[ru + 1] - uptr[ru]
+        tot = int(lens.sum())
+        if tot == 0:
+            continue
+        rep = np.repeat(np.arange(len(ru)), lens)
+        pos = uptr[ru][rep] + (np.arange(tot) - (np.cumsum(lens) - lens)[rep])
+        cols = item[pos]
+        keep = cols != i
+        cols, rep, pos = cols[keep], rep[keep], pos[keep]
+        n = np.bincount(cols, minlength=n_items)
+        inner = np.bincount(cols, weights=c_val[iptr[i]:iptr[i + 1]][rep] * val[pos], minlength=n_items)
+        mutu = np.bincount(cols, weights=(c_ge[iptr[i]:iptr[i + 1]][rep] == ge[pos]).astype(np.float64), minlength=n_items)
+        j = np.flatnonzero(n)
+        n_cols[q] = len(j)
+        nj, inj, mj = n[j].astype(np.float64), inner[j], np.rint(mutu[j])
+        dd = den[i] * den[j]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            cosv = np.where(dd != 0, 1.0 * inj / dd, 0.0)
+        sim = 1.0 * cosv * np.minimum(nj, num_atleast) / num_atleast
+        frac = 1.0 * mj / (st["count"][i] + st["count"][j] - nj)
+        kept = (sim != 0.0) & (mj != 0.0) & (frac != 0.0)
+        out["i"].append(np.full(int(kept.sum()), i, dtype=np.int64)); out["j"].append(j[kept])
+        out["sim"].append(sim[kept]); out["mutu"].append(mj[kept]); out["n"].append(nj[kept]); out["frac"].append(frac[kept])
+        out["label"].append((prefix_code[i] != prefix_code[j[kept]]).astype(np.int32))
+    cat = lambda k, dt: np.concatenate(out[k]) if out[k] else np.zeros(0, dtype=dt)
+    return dict(rows=rows, i=cat("i", np.int64), j=cat("j", np.int64), sim=cat("sim", np.float64),
+                mutu=cat("mutu", np.float64), n=cat("n", np.float64), frac=cat("frac", np.float64),
+                label=cat("label", np.int32), n_cols=n_cols, stats=st)
 
 
 def _matmul_keep_zeros(At, B):

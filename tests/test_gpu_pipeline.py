@@ -92,3 +92,66 @@ def test_generator_accepts_foreign_xsim_rows_and_mapping_dict():
     mapped = gen.cross_private_mapping(xs, session=trainRDD._xmap_session)
     alter2 = gen.build_alterEgo(trainRDD, map_to_dict(mapped)).collect()
     assert sorted(map(str, alter)) == sorted(map(str, alter2))
+
+
+def test_facade_methods_match_reference_golden():
+    """The reference-named stage methods a caller can use directly (baselinerSim.py:17-82, 218-244;
+    extender.py:16-44; assist.py:105-133) against the golden vectors of the unmodified reference."""
+    from xmap_b200.rdd import LocalRDD
+    from xmap_b200.core import BaselinerSim, ExtendSim, baseliner_calculate_sim_pipeline
+    from xmap_b200.utils.assist import extract_siminfo
+    g = PT.load_golden("adj_low_overlap")
+    iids = [str(s) for s in g["iids"]]
+    uids = [str(s) for s in g["uids"]]
+    ipos = {s: n for n, s in enumerate(iids)}
+    trainRDD = LocalRDD(_train_records(g))
+    tool = BaselinerSim(str(g["method"]), int(g["num_atleast"]))
+    # get_universal_user_info / get_universal_item_info
+    ui = dict(tool.get_universal_user_info(trainRDD).collect())
+    assert np.array_equal(np.array([ui[u][0] for u in uids]), g["user_avg"])
+    ii = dict(tool.get_universal_item_info(trainRDD).collect())
+    info = np.array([ii[i] for i in iids])
+    assert np.array_equal(info[:, 0], g["item_info"][:, 0]) and np.array_equal(info[:, 3], g["item_info"][:, 3])
+    np.testing.assert_allclose(info[:, 1:3], g["item_info"][:, 1:3], rtol=1e-13)
+    simRDD = baseliner_calculate_sim_pipeline(None, tool, trainRDD)
+    # get_item_sim: adjacency rows (iid1, [(iid2, sim, mutu, frac)*])
+    adj = dict(tool.get_item_sim(simRDD).collect())
+    want_rows = {}
+    for a, b, v, m, f in zip(g["sim_i"], g["sim_j"], g["sim_val"], g["sim_mutu"], g["sim_frac"]):
+        want_rows.setdefault(iids[a], []).append((iids[b], v, float(m), f))
+    assert set(adj) == set(want_rows)
+    for a, lst in want_rows.items():
+        got = sorted(adj[a])
+        assert [(x[0], x[2], x[3]) for x in got] == [(x[0], x[2], x[3]) for x in sorted(lst)]
+        np.testing.assert_allclose([x[1] for x in got], [x[1] for x in sorted(lst)], rtol=PT.SIM_RTOL)
+    # build_sim_DF: the BB set is DISTINCT id1 WHERE label = 1 (assist.py:82-87)
+    df = tool.build_sim_DF(simRDD)
+    assert len(df) == len(g["sim_i"]) and set(df[0]) == {"id1", "id2", "sim", "mutu", "frac_mutu", "label"}
+    bb = sorted({r["id1"] for r in df if r["label"] == 1})
+    assert bb == [iids[q] for q in np.flatnonzero(g["bb"])]
+    # find_knn_items + extract_siminfo: the four neighbour tables and the two dictionaries
+    ext = ExtendSim(int(g["k"]))
+    classified = ext.find_knn_items(simRDD)
+    lists = {n: {} for n in ("BB_BB", "BB_NB", "NB_BB", "NB_NN")}
+    for iid, B, N in classified.collect():
+        if B is not None:
+            lists["BB_BB"][iid], lists["BB_NB"][iid] = [x[0] for x in B[0]], [x[0] for x in B[1]]
+        else:
+            lists["NB_BB"][iid], lists["NB_NN"][iid] = [x[0] for x in N[0]], [x[0] for x in N[1]]
+    for nm in lists:
+        ptr, nbr = g[nm + "_ptr"], g[nm + "_nbr"]
+        for it, iid in enumerate(iids):
+            want = [iids[q] for q in nbr[ptr[it]:ptr[it + 1]]]
+            assert lists[nm].get(iid, []) == want, (nm, iid)
+    BB_info, NB_info, knn_BB, knn_NB = extract_siminfo(None, classified)
+    assert sorted(knn_BB.value) == bb
+    assert sorted(knn_NB.value) == [iids[q] for q in np.flatnonzero(g["valid_nb"])]
+    some = bb[0]
+    nb = set(lists["BB_BB"][some]) | set(lists["BB_NB"][some])
+    assert set(knn_BB.value[some]) == nb and all(len(v) == 3 for v in knn_BB.value[some].values())
+    # a neighbour's value tuple is (sim, mutu, frac) of the reference pair
+    key = {(iids[a], iids[b]): (v, float(m), f) for a, b, v, m, f in
+           zip(g["sim_i"], g["sim_j"], g["sim_val"], g["sim_mutu"], g["sim_frac"])}
+    for nbr_id, (s_, m_, f_) in knn_BB.value[some].items():
+        w = key[(some, nbr_id)]
+        assert m_ == w[1] and f_ == w[2] and abs(s_ - w[0]) <= PT.SIM_RTOL * abs(w[0])

@@ -1,0 +1,62 @@
+"""GPU parity: RecommenderSim `cosine_item` + local sensitivity on the AlterEgo profile,
+through the C ABI, against what the UNMODIFIED reference produced (tests/golden/*_recsim.npz, minted by
+oracle/make_golden_recsim.py) and against the numpy restatement on a larger profile."""
+import numpy as np
+import pytest
+
+from tests import parity as PT
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5            # BASELINE.json north_star: similarity values within 1e-5 relative
+
+
+def _compare(R, ref_i, ref_j, ref_sim, ref_ls, ref_n=None):
+    i, j = R.i.cpu().numpy(), R.j.cpu().numpy()
+    assert np.array_equal(i, ref_i) and np.array_equal(j, ref_j), "pair sets differ"
+    if ref_n is not None:
+        assert np.array_equal(R.n.cpu().numpy(), ref_n)
+    np.testing.assert_allclose(R.sim.cpu().numpy(), ref_sim, rtol=RTOL, atol=0)
+    ls = R.ls.cpu().numpy()
+    assert np.array_equal(np.isnan(ls), np.isnan(ref_ls)), "NaN pattern of the local sensitivity differs"
+    ok = ~np.isnan(ref_ls)
+    # a sensitivity is a difference of similarities: 1e-5 relative to the similarity scale
+    np.testing.assert_allclose(ls[ok], ref_ls[ok], rtol=RTOL, atol=1e-12)
+    return float(np.max(np.abs(R.sim.cpu().numpy() - ref_sim) / np.maximum(np.abs(ref_sim), 1e-300))) if len(ref_sim) else 0.0
+
+
+@pytest.mark.parametrize("name", PT.GOLDEN_CASES)
+def test_recsim_matches_reference_golden(name):
+    from xmap_b200 import recsim
+    g = PT.load_golden(name + "_recsim")
+    nI = int(max(g["ae_item"].max(), g["rs_i"].max(), g["rs_j"].max())) + 1
+    R = recsim.cosine_item(g["ae_user"], g["ae_item"], g["ae_rating"], nI, int(g["num_atleast"]))
+    rel = _compare(R, g["rs_i"], g["rs_j"], g["rs_sim"], g["rs_ls"])
+    assert int((R.i == R.j).sum()) > 0                             # self pairs: a real next to a synthetic rating
+    info = R.info.cpu().numpy()
+    np.testing.assert_allclose(info[g["info_item"], 0], g["info_avg"], rtol=1e-13)
+    np.testing.assert_allclose(info[g["info_item"], 1], g["info_norm2"], rtol=1e-13)
+    assert np.array_equal(info[g["info_item"], 2], g["info_count"].astype(np.float64))
+    assert R.n_entries == int(R.n.sum())
+    print(name, "recsim pairs", len(g["rs_i"]), "sim max rel", rel)
+
+
+def test_recsim_vs_restatement_with_duplicates():
+    """A larger profile with duplicate (user, item) records, long pair lists (popular items) and half-star means."""
+    from oracle import restate as RS
+    from xmap_b200 import recsim
+    rng = np.random.default_rng(17)
+    nU, nI, n = 3000, 500, 60000
+    p_item = 1.0 / np.arange(1, nI + 1); p_item /= p_item.sum()
+    user = rng.integers(0, nU, n); item = rng.choice(nI, n, p=p_item)
+    rating = rng.integers(1, 11, n) * 0.5
+    # synthetic records next to real ones: repeat 5 % of the records with another rating (generator.py:156-157)
+    dup = rng.choice(n, n // 20, replace=False)
+    user = np.concatenate([user, user[dup]]); item = np.concatenate([item, item[dup]])
+    rating = np.concatenate([rating, rng.integers(1, 11, len(dup)) * 0.5 + 0.25])
+    o = np.argsort(user, kind="stable")
+    user, item, rating = user[o], item[o], rating[o]
+    P = RS.recommender_cosine_item(user, item, rating, nI, 50)
+    R = recsim.cosine_item(user, item, rating, nI, 50)
+    _compare(R, P["i"], P["j"], P["sim"], P["ls"], P["n"])
+    assert int((P["i"] == P["j"]).sum()) > 100 and int(P["n"].max()) > 200
+    np.testing.assert_allclose(R.info.cpu().numpy()[:, 1], P["norm2"], rtol=1e-13)

@@ -29,6 +29,35 @@ def test_sim_matches_reference_golden(name):
     PT.compare_knn(tabs, g["bb"], g["valid_nb"], lists)
 
 
+def test_sim_matches_reference_mid_size_golden():
+    """The CTA launch shapes and the histogram path of the selection against the UNMODIFIED reference: the
+    mid-size golden (90 K ratings, 366 K kept pairs, rows of up to 3 900 co-rating products, lists of ~1e3 neighbours)."""
+    g = PT.load_golden("adj_mid")
+    meta = PT.golden_meta(g)
+    nU, nI = len(g["uids"]), len(g["iids"])
+    lay, eng, tabs, pairs = PT.run_gpu_sim(g["user"], g["item"], g["rating"], nU, nI, meta,
+                                           str(g["method"]), int(g["num_atleast"]), int(g["k"]))
+    kinds = _kinds(dict(tabs=tabs))
+    assert any(k.endswith("_t32") for k in kinds) and sum(1 for k in kinds if not k.endswith("_t32")) >= 3, kinds
+    assert np.array_equal(lay.user_mu.cpu().numpy(), g["user_avg"])
+    its = lay.item_stats.cpu().numpy()
+    assert np.array_equal(its[:, 0], g["item_info"][:, 0]) and np.array_equal(its[:, 3], g["item_info"][:, 3])
+    gi, gj = pairs["i"].cpu().numpy(), pairs["j"].cpu().numpy()
+    assert np.array_equal(gi, g["sim_i"]) and np.array_equal(gj, g["sim_j"]), "kept-pair sets differ"
+    assert np.array_equal(pairs["mutu"].cpu().numpy(), g["sim_mutu"]) and np.array_equal(pairs["label"].cpu().numpy(), g["sim_label"])
+    assert np.array_equal(pairs["frac"].cpu().numpy().astype(np.float32), g["sim_frac"])
+    rel = np.abs(pairs["sim"].cpu().numpy() - g["sim_val"]) / np.abs(g["sim_val"])
+    assert rel.max() <= PT.SIM_RTOL, rel.max()
+    lists = {n: (g[n + "_ptr"], g[n + "_nbr"]) for n in ("BB_BB", "BB_NB", "NB_BB", "NB_NN")}
+    key = g["sim_i"].astype(np.int64) * nI + g["sim_j"]
+
+    def ref_sim(it, j):
+        q = np.searchsorted(key, it * nI + j)
+        return g["sim_val"][q] if q < len(key) and key[q] == it * nI + j else 0.0
+    near = PT.compare_knn(tabs, g["bb"], g["valid_nb"], lists, ref_sim=ref_sim)
+    assert near <= 2, "%d lists differ from the reference by near-ties (regression ceiling)" % near
+
+
 def _kinds(out):
     return [k for k, _ in out["tabs"].stats["accumulate"]]
 

@@ -102,3 +102,24 @@ def test_sim_rows_restriction_equals_sim_pairs():
         assert m.sum() > 100
         for key in ("i", "j", "sim", "mutu", "n", "frac", "label"):
             assert np.array_equal(P[key][m], Q[key]), key
+
+
+def test_restatement_vs_reference_mid_size():
+    """The mid-size golden (90 K ratings, 366 K kept pairs; the reference took 17 s for the similarity stage):
+    similarity, mutuality, labels, BB set and all four neighbour tables of the restatement against the
+    unmodified reference.  Lists of ~1e3 neighbours and rows with thousands of co-rating products."""
+    g, meta, nU, nI, P = _case("adj_mid")
+    assert len(g["user"]) > 85000 and len(g["sim_i"]) > 300000
+    assert np.array_equal(P["i"], g["sim_i"]) and np.array_equal(P["j"], g["sim_j"])
+    assert np.array_equal(P["mutu"], g["sim_mutu"]) and np.array_equal(P["label"], g["sim_label"])
+    assert np.array_equal(P["frac"].astype(np.float32), g["sim_frac"])      # stored as its float32 image
+    np.testing.assert_allclose(P["sim"], g["sim_val"], rtol=1e-10)
+    assert np.array_equal(P["stats"]["mu"], g["user_avg"])
+    knn = RS.select_knn(P, nI, int(g["k"]), meta["dom_code"], meta["contains"])
+    assert np.array_equal(knn["bb"], g["bb"]) and np.array_equal(knn["valid_nb"], g["valid_nb"])
+    lists = PT.restate_lists(knn, P)
+    n_diff = 0
+    for nm in ("BB_BB", "BB_NB", "NB_BB", "NB_NN"):
+        assert np.array_equal(lists[nm][0], g[nm + "_ptr"])
+        n_diff += int((lists[nm][1] != g[nm + "_nbr"]).sum())
+    assert n_diff == 0, "%d neighbour entries differ from the reference" % n_diff

@@ -1,0 +1,157 @@
+// RecommenderSim on the AlterEgo profile: item-item cosine similarity with significance weighting and the
+// per-pair local sensitivity (recommenderSim.py:64-75 produce_pairwise, :90-132 cosine_sim, :186-195
+// calculate_sim with method "cosine_item"; assist.py:153-175).
+//
+// What the reference computes (pinned by oracle/harness.run_recommender_sim, tests/golden/*_recsim.npz):
+//   * the profile is a flat list of (user, item, rating) records; a (user, item) pair may occur twice (a real
+//     target rating next to a synthetic one, generator.py:156-157), which yields self pairs (i, i) and double
+//     co-rating entries -- nothing is deduplicated and nothing is filtered;
+//   * every user with d >= 2 records emits, for every 2-combination (p < q) of its records in list order, the
+//     entry (item_p, item_q) <- (r_p, r_q) and then (item_q, item_p) <- (r_q, r_p)        (:64-75);
+//   * per directed pair, over its entries in arrival order: n = #entries, inner = sum r_a r_b,
+//     sim = cosine(inner, norm_i norm_j) * min(n, N) / N with the norms over ALL records of the item (:118-122),
+//     and the local sensitivity max |v - sim| over the 2 n leave-one-out similarities (:98-116), where
+//     Python's max() lets a NaN win only if it is the first element.
+//
+// Device design: HBM-bound streaming in three steps.  (1) fill: one thread per co-rating entry computes its
+// directed pair key and the positions of its two records (the entry index follows the reference's emission
+// order, so a STABLE sort by key leaves every pair's entries in arrival order); (2) the caller sorts the keys
+// (CUB radix sort through torch: library plumbing); (3) pairs: one warp per pair walks its entries twice --
+// the inner product, then the 2 n leave-one-out deviations, which need the finished inner product.
+#include "common.cuh"
+
+namespace xmap {
+
+// (count, sum r, sum r^2) per item over records grouped by item: one warp per item, fixed fold order
+__global__ void __launch_bounds__(256) recsim_item_info_kernel(const int64_t *__restrict__ item_ptr,
+                                                               const double *__restrict__ rating_by_item, int32_t n_items,
+                                                               double *__restrict__ info) {
+    const int i = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n_items) return;
+    const int64_t lo = item_ptr[i], hi = item_ptr[i + 1];
+    double s = 0.0, s2 = 0.0;
+    for (int64_t e = lo + lane; e < hi; e += 32) { const double r = rating_by_item[e]; s += r; s2 = __dadd_rn(s2, __dmul_rn(r, r)); }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, off);
+        s2 += __shfl_down_sync(0xffffffffu, s2, off);
+    }
+    if (lane == 0) {
+        const double c = (double)(hi - lo);
+        info[3 * (size_t)i + 0] = c > 0 ? s / c : 0.0;      // average          (recommenderSim.py:51-58)
+        info[3 * (size_t)i + 1] = sqrt(s2);                 // norm2            (:41-49)
+        info[3 * (size_t)i + 2] = c;                        // count
+    }
+}
+
+// entry t of user u (records [lo, lo + d)): combination c = t / 2 in lexicographic (p < q) order, direction t % 2
+__global__ void __launch_bounds__(256) recsim_fill_kernel(const int64_t *__restrict__ user_ptr, const int64_t *__restrict__ ent_off,
+                                                          int32_t n_users, const int32_t *__restrict__ item, int64_t n_items,
+                                                          int64_t total, int64_t *__restrict__ key, int64_t *__restrict__ src) {
+    const int64_t t = blockIdx.x * (int64_t)256 + threadIdx.x;
+    if (t >= total) return;
+    int32_t a = 0, b = n_users;                          // largest u with ent_off[u] <= t (users without entries are skipped)
+    while (b - a > 1) {
+        const int32_t mid = (a + b) >> 1;
+        if (__ldg(ent_off + mid) <= t) a = mid; else b = mid;
+    }
+    const int64_t lo = user_ptr[a], d = user_ptr[a + 1] - lo;
+    const int64_t e = t - ent_off[a], c = e >> 1;
+    // p = the row of combination c: c >= p (2 d - p - 1) / 2
+    int64_t p = (int64_t)floor(((double)(2 * d - 1) - sqrt((double)(2 * d - 1) * (double)(2 * d - 1) - 8.0 * (double)c)) * 0.5);
+    p = max((int64_t)0, min(p, d - 2));
+    while (p > 0 && p * (2 * d - p - 1) / 2 > c) --p;
+    while ((p + 1) * (2 * d - p - 2) / 2 <= c) ++p;
+    const int64_t q = p + 1 + (c - p * (2 * d - p - 1) / 2);
+    const int64_t pa = (e & 1) ? lo + q : lo + p, pb = (e & 1) ? lo + p : lo + q;
+    key[t] = (int64_t)item[pa] * n_items + (int64_t)item[pb];
+    src[t] = (pa << 32) | pb;
+}
+
+__device__ __forceinline__ double rs_cosine(double dot, double nn) {           // recommenderSim.py:84-88
+    return nn != 0.0 ? dot / nn : 0.0;                                        // a NaN product is truthy in Python
+}
+
+// one warp per directed pair: entries [seg_ptr[g], seg_ptr[g + 1]) of the sorted arrays
+__global__ void __launch_bounds__(256) recsim_pair_kernel(const int64_t *__restrict__ seg_ptr, const int64_t *__restrict__ seg_key,
+                                                          const int64_t *__restrict__ src, const double *__restrict__ rating,
+                                                          const double *__restrict__ info, int64_t n_items, int64_t n_pairs,
+                                                          int32_t num_atleast, int32_t *__restrict__ out_i, int32_t *__restrict__ out_j,
+                                                          int64_t *__restrict__ out_n, double *__restrict__ out_sim,
+                                                          double *__restrict__ out_ls) {
+    const int64_t g = (blockIdx.x * (int64_t)256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= n_pairs) return;
+    const int64_t lo = seg_ptr[g], hi = seg_ptr[g + 1], n = hi - lo;
+    const int64_t k = seg_key[g];
+    const int i = (int)(k / n_items), j = (int)(k % n_items);
+    const double nx = info[3 * (size_t)i + 1], ny = info[3 * (size_t)j + 1];
+    const double N = (double)num_atleast;
+    double inner = 0.0;
+    for (int64_t e = lo + lane; e < hi; e += 32) {
+        const int64_t s = src[e];
+        inner = __dadd_rn(inner, __dmul_rn(rating[s >> 32], rating[s & 0xFFFFFFFFll]));      // products rounded like the reference's
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) inner += __shfl_xor_sync(0xffffffffu, inner, off);
+    const double sim = 1.0 * rs_cosine(inner, nx * ny) * (double)min(n, (int64_t)num_atleast) / N;      // :77-82, :121-122
+    // local sensitivity (:98-116): per entry the two leave-one-out similarities, v1 then v2
+    const double w = (double)min(n - 1, (int64_t)num_atleast);
+    double best = -1.0;                                   // max over the non-NaN deviations (all are >= 0)
+    bool first_nan = false;
+    for (int64_t e = lo + lane; e < hi; e += 32) {
+        const int64_t s = src[e];
+        const double ra = rating[s >> 32], rb = rating[s & 0xFFFFFFFFll];
+        const double mi = __dsub_rn(inner, __dmul_rn(ra, rb));                 // no fused multiply-add: a single-entry pair must give 0
+        const double nx2 = __dmul_rn(nx, nx), ny2 = __dmul_rn(ny, ny);
+        const double m1 = sqrt(__dmul_rn(__dsub_rn(nx2, __dmul_rn(ra, ra)), ny2));
+        const double m2 = sqrt(__dmul_rn(nx2, __dsub_rn(ny2, __dmul_rn(rb, rb))));
+        const double d1 = fabs(1.0 * rs_cosine(mi, m1) * w / N - sim);
+        const double d2 = fabs(1.0 * rs_cosine(mi, m2) * w / N - sim);
+        if (e == lo && d1 != d1) first_nan = true;        // Python's max(): a NaN only wins when it comes first
+        if (d1 == d1 && d1 > best) best = d1;
+        if (d2 == d2 && d2 > best) best = d2;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, off));
+    first_nan = __shfl_sync(0xffffffffu, first_nan ? 1 : 0, 0) != 0;
+    if (lane == 0) {
+        out_i[g] = i; out_j[g] = j; out_n[g] = n; out_sim[g] = sim;
+        // every deviation NaN except possibly none: with a non-NaN first element the result is the max of the
+        // non-NaN ones (best >= 0 always holds then, the first element itself being one of them)
+        out_ls[g] = first_nan ? __longlong_as_double(0x7FF8000000000000ll) : best;
+    }
+}
+
+}  // namespace xmap
+
+using namespace xmap;
+
+extern "C" int xmap_recsim_item_info(const int64_t *item_ptr, const double *rating_by_item, int32_t n_items, double *info,
+                                     void *stream_) {
+    if (n_items <= 0) return 0;
+    recsim_item_info_kernel<<<(unsigned)((n_items + 7) / 8), 256, 0, (cudaStream_t)stream_>>>(item_ptr, rating_by_item, n_items, info);
+    XMAP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xmap_recsim_fill_entries(const int64_t *user_ptr, const int64_t *ent_off, int32_t n_users, const int32_t *item,
+                                        int64_t n_items, int64_t total, int64_t *key, int64_t *src, void *stream_) {
+    if (total <= 0) return 0;
+    recsim_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(user_ptr, ent_off, n_users, item, n_items,
+                                                                                          total, key, src);
+    XMAP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xmap_recsim_pairs(const int64_t *seg_ptr, const int64_t *seg_key, const int64_t *src, const double *rating,
+                                 const double *info, int64_t n_items, int64_t n_pairs, int32_t num_atleast,
+                                 int32_t *out_i, int32_t *out_j, int64_t *out_n, double *out_sim, double *out_ls, void *stream_) {
+    if (n_pairs <= 0) return 0;
+    if (num_atleast < 1) return fail_msg("xmap_recsim_pairs: num_atleast must be >= 1");
+    recsim_pair_kernel<<<(unsigned)((n_pairs + 7) / 8), 256, 0, (cudaStream_t)stream_>>>(seg_ptr, seg_key, src, rating, info, n_items,
+                                                                                        n_pairs, num_atleast, out_i, out_j, out_n,
+                                                                                        out_sim, out_ls);
+    XMAP_LAUNCH_CHECK();
+    return 0;
+}

@@ -241,6 +241,10 @@ XSIM_MAX_PASSES = int(os.environ.get("XMAP_XSIM_MAX_PASSES", "1000000000"))   # 
                                 # global memory (L2).  Measured at cfg2: 32 passes + L2 tables 968 ms, shared memory only
                                 # (no cap) 732 ms -- dependent read-modify-writes at L2 latency lose to narrow passes
 XSIM_GCELLS_LG = 16             # largest global-memory table of a unit (cells)
+XSIM_MODE = os.environ.get("XMAP_XSIM_MODE", "warp")               # "warp": one warp per unit (xsim.cu); "cta": one CTA per
+                                                                   # unit with one 8x larger table (xsim_cta.cu)
+XSIM_CTA_CELLS_LG = int(os.environ.get("XMAP_XSIM_CTA_CELLS_LG", "12"))
+XSIM_CTA_UNIT_LG = int(os.environ.get("XMAP_XSIM_CTA_UNIT_LG", "20"))
 
 
 @dataclass
@@ -264,8 +268,19 @@ class XsimEngine:
     summation order of a (start, end) cell depends on the path structure and this plan only, so results
     are bit-identical from run to run and for any number of GPUs."""
 
-    def __init__(self, plan, top_m=10, cells_lg=XSIM_CELLS_LG, rho=XSIM_RHO, unit_work=XSIM_UNIT_WORK,
-                 load=XSIM_LOAD, warps=XSIM_WARPS, max_passes=XSIM_MAX_PASSES):
+    def __init__(self, plan, top_m=10, cells_lg=None, rho=XSIM_RHO, unit_work=None,
+                 load=XSIM_LOAD, warps=XSIM_WARPS, max_passes=XSIM_MAX_PASSES, mode=XSIM_MODE):
+        if mode not in ("warp", "cta"):
+            raise ValueError("mode must be 'warp' or 'cta'")
+        self.mode = mode
+        if cells_lg is None:
+            cells_lg = XSIM_CTA_CELLS_LG if mode == "cta" else XSIM_CELLS_LG
+        if unit_work is None:
+            unit_work = (1 << XSIM_CTA_UNIT_LG) if mode == "cta" else XSIM_UNIT_WORK
+        if mode == "cta":
+            max_passes = 10 ** 9                 # shared memory only
+            if cells_lg < 9:
+                raise ValueError("cta mode needs cells_lg >= 9")
         if not (1 <= top_m <= N.KMAX):
             raise ValueError("top_m must be in [1, %d]" % N.KMAX)
         if not (6 <= cells_lg <= N.XSIM_MAX_CELLS_LG):
@@ -419,8 +434,9 @@ class XsimEngine:
         a.unit_order, a.n_units = N.ptr(order), int(order.numel())
         a.merge = 1 if world == 1 else 0
         st = torch.cuda.current_stream().cuda_stream
+        run_units = L.xmap_xsim_extend_cta if self.mode == "cta" else L.xmap_xsim_extend
         if n and nu:
-            N.check(L.xmap_xsim_extend(a, st), "xmap_xsim_extend")
+            N.check(run_units(a, st), "xmap_xsim_extend")
             self.launches += 1 + a.merge
             if world > 1:
                 from .multi import sum_unit_results
@@ -450,7 +466,8 @@ class XsimEngine:
             a.unit_count, a.unit_combos, a.unit_top_end, a.unit_top_xsim, a.unit_top_len = [N.ptr(t) for t in scratch]
             a.unit_order, a.n_units, a.merge = N.ptr(self.unit_order), nu, 0
             a.emit_ptr, a.emit_end, a.emit_xsim = N.ptr(ptr), N.ptr(e_end), N.ptr(e_x)
-            N.check(L.xmap_xsim_extend(a, torch.cuda.current_stream().cuda_stream), "xmap_xsim_extend(emit)")
+            run_units = L.xmap_xsim_extend_cta if self.mode == "cta" else L.xmap_xsim_extend
+            N.check(run_units(a, torch.cuda.current_stream().cuda_stream), "xmap_xsim_extend(emit)")
             self.launches += 1
             self._check()
             if not torch.equal(scratch[0], res.unit_count):

@@ -1,0 +1,75 @@
+"""RecommenderSim on the AlterEgo profile (C ABI section 5).
+
+Reference: RecommenderSim.get_info / produce_pairwise / cosine_sim / calculate_sim with method
+"cosine_item" (recommenderSim.py:29-62, 64-75, 90-132, 186-195), driven by
+assist.recommender_calculate_sim_pipeline (assist.py:153-175).
+"""
+from dataclasses import dataclass
+
+import torch
+
+from . import _native as N
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@dataclass
+class RecSim:
+    """Every directed item pair with at least one co-rating entry, sorted by (i, j) (self pairs included)."""
+    i: torch.Tensor          # int32
+    j: torch.Tensor          # int32
+    n: torch.Tensor          # int64  co-rating entries
+    sim: torch.Tensor        # f64    cosine * min(n, N) / N          (recommenderSim.py:121-122)
+    ls: torch.Tensor         # f64    local sensitivity              (:98-116)
+    info: torch.Tensor       # f64 [n_items, 3] = (average, norm2, count) over the records of the item (:29-62)
+    n_entries: int
+
+
+def cosine_item(user, item, rating, n_items, num_atleast=50, device="cuda"):
+    """user / item / rating: the flat profile records in the order the reference receives them
+    (only the order of a user's records matters: it fixes the arrival order of a pair's entries)."""
+    L = N.lib()
+    dev = torch.device(device)
+    user = torch.as_tensor(user, dtype=torch.int64).to(dev)
+    item = torch.as_tensor(item, dtype=torch.int32).to(dev).contiguous()
+    rating = torch.as_tensor(rating, dtype=torch.float64).to(dev).contiguous()
+    n_rec = int(user.numel())
+    i64 = dict(dtype=torch.int64, device=dev)
+    # ---- item info: records grouped by item ---------------------------------------------------------
+    oi = torch.argsort(item.long(), stable=True)
+    item_ptr = torch.zeros(n_items + 1, **i64)
+    item_ptr[1:] = torch.cumsum(torch.bincount(item.long(), minlength=n_items), 0)
+    info = torch.zeros((n_items, 3), dtype=torch.float64, device=dev)
+    N.check(L.xmap_recsim_item_info(N.ptr(item_ptr), N.ptr(rating[oi].contiguous()), n_items, N.ptr(info), _st()),
+            "xmap_recsim_item_info")
+    # ---- co-rating entries: records grouped by user, list order kept ---------------------------------
+    ou = torch.argsort(user, stable=True)
+    u_s, it_s, r_s = user[ou], item[ou].contiguous(), rating[ou].contiguous()
+    uniq, d = torch.unique_consecutive(u_s, return_counts=True)
+    n_users = int(uniq.numel())
+    user_ptr = torch.zeros(n_users + 1, **i64)
+    user_ptr[1:] = torch.cumsum(d, 0)
+    ent_off = torch.zeros(n_users + 1, **i64)
+    ent_off[1:] = torch.cumsum(d * (d - 1), 0)
+    total = int(ent_off[-1].item()) if n_users else 0
+    key = torch.empty(total, **i64)
+    src = torch.empty(total, **i64)
+    N.check(L.xmap_recsim_fill_entries(N.ptr(user_ptr), N.ptr(ent_off), n_users, N.ptr(it_s), n_items, total,
+                                       N.ptr(key), N.ptr(src), _st()), "xmap_recsim_fill_entries")
+    key_s, perm = torch.sort(key, stable=True)          # CUB radix sort (library plumbing); stable: arrival order kept
+    src_s = src[perm].contiguous()
+    seg_key, cnt = torch.unique_consecutive(key_s, return_counts=True)
+    n_pairs = int(seg_key.numel())
+    seg_ptr = torch.zeros(n_pairs + 1, **i64)
+    seg_ptr[1:] = torch.cumsum(cnt, 0)
+    out_i = torch.empty(n_pairs, dtype=torch.int32, device=dev)
+    out_j = torch.empty(n_pairs, dtype=torch.int32, device=dev)
+    out_n = torch.empty(n_pairs, **i64)
+    out_sim = torch.empty(n_pairs, dtype=torch.float64, device=dev)
+    out_ls = torch.empty(n_pairs, dtype=torch.float64, device=dev)
+    N.check(L.xmap_recsim_pairs(N.ptr(seg_ptr), N.ptr(seg_key.contiguous()), N.ptr(src_s), N.ptr(r_s), N.ptr(info),
+                                n_items, n_pairs, int(num_atleast), N.ptr(out_i), N.ptr(out_j), N.ptr(out_n),
+                                N.ptr(out_sim), N.ptr(out_ls), _st()), "xmap_recsim_pairs")
+    return RecSim(out_i, out_j, out_n, out_sim, out_ls, info, total)
