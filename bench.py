@@ -68,10 +68,7 @@ def _compact(name, sr, keep, k, tag):
                 nnz=int(len(user)), W=int((du * (du - 1)).sum()))
 
 
-def make_pipelines(name):
-    """The two-domain problems of a workload: one for a two-domain shape; for a multi-domain shape one
-    source -> target problem per source domain, cut from ONE rating set, exactly as multidomain_demo.py:101-128
-    runs them (independent pipelines whose AlterEgo records are unioned)."""
+def _generate_pipelines(name):
     from xmap_b200 import synth
     nu, ni, nd, ndom, ov, k = WORKLOADS[name]
     sr = synth.make_ratings(nu, ni, nd, n_domains=ndom, overlap=ov)
@@ -79,6 +76,34 @@ def make_pipelines(name):
         return [_compact(name, sr, None, k, "")]
     tgt = ndom - 1
     return [_compact(name, sr, (sr.domain == d) | (sr.domain == tgt), k, "[%s->T:]" % sr.labels[d]) for d in range(tgt)]
+
+
+def make_pipelines(name):
+    """The two-domain problems of a workload: one for a two-domain shape; for a multi-domain shape one
+    source -> target problem per source domain, cut from ONE rating set, exactly as multidomain_demo.py:101-128
+    runs them (independent pipelines whose AlterEgo records are unioned).
+    Under torchrun the ranks of a node share one generation: local rank 0 writes the arrays to /dev/shm, the others
+    read them (the generator is deterministic; this only avoids N processes competing for the host cores)."""
+    world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world <= 1 or not os.path.isdir("/dev/shm"):
+        return _generate_pipelines(name)
+    import pickle
+    tag = "%s_%s_%s" % (name, "_".join(str(x) for x in WORKLOADS[name]), os.environ.get("MASTER_PORT", "0"))
+    path = "/dev/shm/xmap_b200_%s.pkl" % tag
+    if local == 0:
+        pipes = _generate_pipelines(name)
+        with open(path + ".tmp", "wb") as f:
+            pickle.dump(pipes, f, protocol=4)
+        os.replace(path + ".tmp", path)
+        return pipes
+    t0 = time.time()
+    while not os.path.exists(path):
+        if time.time() - t0 > 1800:
+            raise RuntimeError("timed out waiting for %s" % path)
+        time.sleep(0.5)
+    with open(path, "rb") as f:
+        return pickle.load(f)
 
 
 def make_workload(name):
@@ -501,8 +526,8 @@ def main():
             # figure is an equivalent-traffic rate, next to the 28 B right-segment read each path really makes
             xk = pipe["xsim_kernels_ms"] * 1e-3
             gb16, gb28 = 16.0 * pipe["xsim_paths"] / xk / 1e9, 28.0 * pipe["xsim_paths"] / xk / 1e9
-            line["pipeline_roofline"] = {"kernel": "xsim_warp_kernel", "bound": "hbm", "achieved": gb16, "peak": peaks["hbm_gbs"],
-                                         "unit": "GB/s", "frac": gb16 / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC.get("xsim_warp_kernel"),
+            line["pipeline_roofline"] = {"kernel": "xsim_%s_kernel" % X.XSIM_MODE, "bound": "hbm", "achieved": gb16, "peak": peaks["hbm_gbs"],
+                                         "unit": "GB/s", "frac": gb16 / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC.get("xsim_%s_kernel" % X.XSIM_MODE),
                                          "algorithmic_bytes_per_path": 16, "paths": pipe["xsim_paths"],
                                          "kernel_ms": pipe["xsim_kernels_ms"], "right_segment_read_gbs": gb28,
                                          "note": "host wall-clock around the kernel launches + merge (max over ranks via the barrier)"}

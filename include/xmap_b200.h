@@ -333,6 +333,21 @@ int xmap_recsim_pairs(const int64_t *seg_ptr, const int64_t *seg_key, const int6
                       const double *info, int64_t n_items, int64_t n_pairs, int32_t num_atleast,
                       int32_t *out_i, int32_t *out_j, int64_t *out_n, double *out_sim, double *out_ls, void *stream);
 
+/* (5b) Non-private neighbour selection on the RecommenderSim output (SURVEY.md 8(f) #2;
+ * RecommenderPrivacy.nonprivate_neighbor_selection + nonnoise_perturbation, recommenderPrivacy.py:141-189):
+ * per item the first k neighbours by |sim| descending, ties to the smaller index; row_ptr [n_items + 1]
+ * indexes the (i, j)-sorted pair arrays.  Tables [n_items][k]. */
+int xmap_recsim_neighbors(const int64_t *row_ptr, const int32_t *pair_j, const double *pair_sim, int32_t n_items,
+                          int32_t k, int32_t *nb_idx, double *nb_sim, int32_t *nb_len, void *stream);
+/* (5c) Item-based prediction of test (user, item) pairs on the AlterEgo profile (SURVEY.md 8(f) #3;
+ * RecommenderPrediction.item_based_prediction, recommenderPrediction.py:26-103): profile records grouped by user
+ * in list order (prof_ptr [n_users + 1]); pred_* = bounded rating without / with temporal decay, -1 where the
+ * item has no neighbour list.  error_flag 4: more than 128 matching profile records for one prediction. */
+int xmap_recsim_predict(const int64_t *prof_ptr, const int32_t *prof_item, const double *prof_rating,
+                        const int64_t *prof_ts, const double *info, const int32_t *nb_idx, const double *nb_sim,
+                        const int32_t *nb_len, int32_t k, const int32_t *t_user, const int32_t *t_item, int64_t n_test,
+                        double alpha, double *pred_nodecay, double *pred_decay, int32_t *error_flag, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

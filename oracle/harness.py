@@ -74,6 +74,8 @@ def load_reference():
             from xmap.core.baselinerClean import BaselinerClean
             from xmap.core.baselinerSplit import BaselinerSplit
             from xmap.core.recommenderSim import RecommenderSim
+            from xmap.core.recommenderPrivacy import RecommenderPrivacy
+            from xmap.core.recommenderPrediction import RecommenderPrediction
             from xmap.utils import assist
     finally:
         sys.path.remove(REFERENCE_CODE)
@@ -82,7 +84,8 @@ def load_reference():
     _ref = dict(pyspark=pyspark, sc=sc, sqlContext=SQLContext(sc),
                 BaselinerSim=BaselinerSim, ExtendSim=ExtendSim,
                 Generator=Generator, BaselinerClean=BaselinerClean,
-                BaselinerSplit=BaselinerSplit, RecommenderSim=RecommenderSim, assist=assist)
+                BaselinerSplit=BaselinerSplit, RecommenderSim=RecommenderSim,
+                RecommenderPrivacy=RecommenderPrivacy, RecommenderPrediction=RecommenderPrediction, assist=assist)
     return _ref
 
 
@@ -179,3 +182,35 @@ def run_recommender_sim(alter_records, method="cosine_item", num_atleast=50):
     item_info = dict(out[5].value)
     sims = sorted(((k, [float(v[0]), float(v[1])]) for k, v in sims), key=lambda x: x[0])
     return sims, item_info, dt
+
+
+def run_recommender_predict(alter_records, test_records, mapping_range=10, alpha=0.03,
+                            method="cosine_item", num_atleast=50, epsilon=0.6, rpo=0.1):
+    """The rest of the demo after AlterEgo generation (twodomain_demo.py:119-134):
+    recommender_calculate_sim_pipeline -> recommender_privacy_pipeline (non-private: top-`mapping_range`
+    neighbours by |sim|, recommenderPrivacy.py:141-178) -> item-based prediction + MAE
+    (recommenderPrediction.py:26-139), all by the unmodified reference.
+
+    Canonical order (SURVEY.md App. A.6 rule 3): the similarity records enter the neighbour selection sorted
+    by (id1, id2), so ties in |sim| resolve to the smaller neighbour id.
+
+    Returns (neighbours {iid: [(nid, sim)*]}, predictions [(uid, [(iid, real, no_decay, decay) | ()]*)], mae string)."""
+    R = load_reference()
+    sc, assist = R["sc"], R["assist"]
+    sim_tool = R["RecommenderSim"](method, num_atleast)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = assist.recommender_calculate_sim_pipeline(sc, sim_tool, sc.parallelize(list(alter_records)))
+        sims = sorted(out[6].collect(), key=lambda x: x[0])
+    user_dict_bd, item_dict_bd, user_info_bd, item_info_bd = out[2], out[3], out[4], out[5]
+    priv_tool = R["RecommenderPrivacy"](mapping_range, epsilon, rpo)
+    simpair = assist.recommender_privacy_pipeline(priv_tool, sc.parallelize(sims), False)
+    neigh = simpair.collectAsMap()
+    pred_tool = R["RecommenderPrediction"](alpha, method)
+    import io, contextlib
+    with contextlib.redirect_stdout(io.StringIO()):          # calculate_mae prints rdd.take(1)
+        testRDD = sc.parallelize(list(test_records))
+        predicted = pred_tool.item_based_recommendation(testRDD, item_dict_bd, sc.broadcast(neigh), item_info_bd)
+        preds = predicted.collect()
+        mae = pred_tool.calculate_mae(sc.parallelize(preds))
+    return neigh, preds, mae

@@ -452,3 +452,64 @@ def recommender_cosine_item(user, item, rating, n_items, num_atleast=50):
                 res = x
         ls[g] = res
     return dict(i=pi, j=pj, n=n, sim=sim, ls=ls, norm2=norm2)
+
+
+# --------------------------------------------------------------------------
+# non-private neighbour selection (recommenderPrivacy.py:141-178) and item-based
+# prediction + MAE (recommenderPrediction.py:26-139) on the AlterEgo profile.
+# --------------------------------------------------------------------------
+def recommender_neighbors(pairs, n_items, mapping_range=10):
+    """pairs: output of recommender_cosine_item (sorted by (i, j)).  Per item the first `mapping_range`
+    neighbours by |sim| descending, ties to the smaller neighbour index (stable sort of the canonical order);
+    the self pair (i, i) is a neighbour like any other.  Returns (ptr [n_items + 1], idx, sim)."""
+    i, j, sim = pairs["i"], pairs["j"], pairs["sim"]
+    o = np.lexsort((j, -np.abs(sim), i))
+    ptr_all = np.searchsorted(i[o], np.arange(n_items + 1))
+    idx, val, ptr = [], [], np.zeros(n_items + 1, dtype=np.int64)
+    for it in range(n_items):
+        sel = o[ptr_all[it]:ptr_all[it + 1]][:mapping_range]
+        idx.append(j[sel]); val.append(sim[sel])
+        ptr[it + 1] = ptr[it] + len(sel)
+    return ptr, (np.concatenate(idx) if idx else np.zeros(0, np.int64)), (np.concatenate(val) if val else np.zeros(0))
+
+
+def bound_rating(x):
+    """recommenderPrediction.py:19-24: int() truncates towards zero."""
+    return 1.0 * max(0, min(int(x + 0.5), 5))
+
+
+def recommender_predict(p_user, p_item, p_rating, p_ts, nb_ptr, nb_idx, nb_sim, item_avg,
+                        t_user, t_item, t_rating, alpha=0.03):
+    """Item-based prediction of every test (user, item) pair: (no-decay, decay) predictions (-1 where the item
+    has no neighbour list) and the two MAEs (recommenderPrediction.py:26-139).  Profile records in list order."""
+    by_ui = {}
+    for q, (u, i) in enumerate(zip(p_user, p_item)):
+        by_ui.setdefault((int(u), int(i)), []).append(q)          # profile order within (user, item)
+    out0, out1 = np.full(len(t_user), -1.0), np.full(len(t_user), -1.0)
+    for q, (u, it) in enumerate(zip(t_user, t_item)):
+        a, b = nb_ptr[it], nb_ptr[it + 1]
+        if b == a:
+            continue                                              # `iid not in sim_bd.value.keys()` -> ()
+        ent = []                                                  # (sim * (r - avg_n), |sim|, time)
+        for nid, ns in zip(nb_idx[a:b], nb_sim[a:b]):
+            for r in by_ui.get((int(u), int(nid)), ()):
+                ent.append((ns * (p_rating[r] - item_avg[nid]), abs(ns), p_ts[r]))
+        avg = item_avg[it]
+        if ent:
+            nd = avg + sum(e[0] for e in ent) / sum(e[1] for e in ent)
+            srt = sorted(ent, key=lambda e: e[2])                 # sort_by_time: equal times share a rank
+            order, ranks = 0, []
+            for k, e in enumerate(srt):
+                if not (k != 0 and e[2] == srt[k - 1][2]):
+                    order += 1
+                ranks.append(order)
+            cur = max(ranks) + 1
+            f = [np.exp(-alpha * (cur - t)) for t in ranks]
+            dc = avg + sum(e[0] * w for e, w in zip(srt, f)) / sum(e[1] * w for e, w in zip(srt, f))
+        else:
+            nd = dc = avg
+        out0[q], out1[q] = bound_rating(nd), bound_rating(dc)
+    ok = out0 >= 0
+    mae0 = float(np.abs(t_rating[ok] - out0[ok]).sum() / ok.sum()) if ok.any() else float("nan")
+    mae1 = float(np.abs(t_rating[ok] - out1[ok]).sum() / ok.sum()) if ok.any() else float("nan")
+    return out0, out1, mae0, mae1

@@ -60,3 +60,35 @@ def test_recsim_vs_restatement_with_duplicates():
     _compare(R, P["i"], P["j"], P["sim"], P["ls"], P["n"])
     assert int((P["i"] == P["j"]).sum()) > 100 and int(P["n"].max()) > 200
     np.testing.assert_allclose(R.info.cpu().numpy()[:, 1], P["norm2"], rtol=1e-13)
+
+
+@pytest.mark.parametrize("name", PT.GOLDEN_CASES)
+def test_neighbors_and_prediction_match_reference_golden(name):
+    """SURVEY.md 8(f) #2-#3 through the C ABI against the UNMODIFIED reference (tests/golden/*_recpred.npz):
+    non-private neighbour tables (indices exact, order included), bounded predictions with and without temporal
+    decay (exact: they are integers), both MAEs."""
+    from xmap_b200 import recsim
+    g = PT.load_golden(name + "_recpred")
+    nI = int(max(g["ae_item"].max(), g["test_item"].max(), g["nb_idx"].max())) + 1
+    nU = int(max(g["ae_user"].max(), g["test_user"].max())) + 1
+    K = int(g["mapping_range"])
+    R = recsim.cosine_item(g["ae_user"], g["ae_item"], g["ae_rating"], nI, int(g["num_atleast"]))
+    nb = recsim.neighbors(R, nI, K)
+    ln, idx, sim = nb.len.cpu().numpy(), nb.idx.cpu().numpy(), nb.sim.cpu().numpy()
+    has = np.flatnonzero(ln)
+    assert np.array_equal(has, g["nb_item"]) and np.array_equal(ln[has], np.diff(g["nb_ptr"]))
+    near = 0
+    for q, it in enumerate(g["nb_item"]):
+        a, b = g["nb_ptr"][q], g["nb_ptr"][q + 1]
+        if not np.array_equal(idx[it, :ln[it]], g["nb_idx"][a:b]):
+            assert np.allclose(np.abs(sim[it, :ln[it]]), np.abs(g["nb_sim"][a:b]), rtol=1e-9, atol=0), "neighbours of item %d differ" % it
+            near += 1
+        else:
+            np.testing.assert_allclose(sim[it, :ln[it]], g["nb_sim"][a:b], rtol=RTOL)
+    assert near <= 1
+    p0, p1, m0, m1 = recsim.predict(g["ae_user"], g["ae_item"], g["ae_rating"], g["ae_ts"], nU, R, nb,
+                                    g["test_user"], g["test_item"], g["test_rating"], float(g["alpha"]))
+    p0, p1 = p0.cpu().numpy(), p1.cpu().numpy()
+    # a bounded prediction is int(x + 0.5): it can differ from the reference only if x + 0.5 is an integer to ~1e-12
+    assert int((p0 != g["pred_nodecay"]).sum()) <= (1 if near else 0) and int((p1 != g["pred_decay"]).sum()) <= (1 if near else 0)
+    assert abs(m0 - float(g["mae_nodecay"])) <= 1e-2 * near + 1e-12 and abs(m1 - float(g["mae_decay"])) <= 1e-2 * near + 1e-12

@@ -47,7 +47,22 @@ def test_sim_matches_reference_mid_size_golden():
     assert np.array_equal(pairs["mutu"].cpu().numpy(), g["sim_mutu"]) and np.array_equal(pairs["label"].cpu().numpy(), g["sim_label"])
     assert np.array_equal(pairs["frac"].cpu().numpy().astype(np.float32), g["sim_frac"])
     rel = np.abs(pairs["sim"].cpu().numpy() - g["sim_val"]) / np.abs(g["sim_val"])
-    assert rel.max() <= PT.SIM_RTOL, rel.max()
+    # |sim| < 1e-13 is the rounding residue of an inner product that cancels exactly (here one pair of two co-raters,
+    # 1.1e-19 in the reference, 1.5e-19 here): not comparable digit by digit, see DESIGN.md 6.1
+    rel[np.abs(g["sim_val"]) < PT.FRAGILE_SIM] = 0.0
+    assert int((np.abs(g["sim_val"]) < PT.FRAGILE_SIM).sum()) <= 2
+    if rel.max() > PT.SIM_RTOL:
+        bad = np.flatnonzero(rel > PT.SIM_RTOL)
+        cnt = its[:, 3]
+        od = eng.ord.cpu().numpy(); tw = eng.tri_work.cpu().numpy()
+        msg = ["%d of %d pairs off" % (len(bad), len(rel))]
+        for q in bad[:12]:
+            a, b = int(gi[q]), int(gj[q])
+            lo = a if od[a] < od[b] else b
+            msg.append("(%d,%d) n=%d gpu=%.6g ref=%.6g ratio=%.6f cnt=(%d,%d) row=%d ord=%d work=%d rtop=%d" % (
+                a, b, int(pairs["n"][q]), float(pairs["sim"][q]), g["sim_val"][q], float(pairs["sim"][q]) / g["sim_val"][q],
+                cnt[a], cnt[b], lo, od[lo], tw[lo], nI - 1 - od[lo]))
+        raise AssertionError("; ".join(msg))
     lists = {n: (g[n + "_ptr"], g[n + "_nbr"]) for n in ("BB_BB", "BB_NB", "NB_BB", "NB_NN")}
     key = g["sim_i"].astype(np.int64) * nI + g["sim_j"]
 

@@ -123,3 +123,24 @@ def test_restatement_vs_reference_mid_size():
         assert np.array_equal(lists[nm][0], g[nm + "_ptr"])
         n_diff += int((lists[nm][1] != g[nm + "_nbr"]).sum())
     assert n_diff == 0, "%d neighbour entries differ from the reference" % n_diff
+
+
+@pytest.mark.parametrize("name", PT.GOLDEN_CASES)
+def test_restatement_neighbors_and_prediction_vs_reference(name):
+    """non-private neighbour selection and item-based prediction + MAE on the AlterEgo
+    profile -- the restatement against the unmodified reference (oracle/make_golden_recpred.py)."""
+    g = PT.load_golden(name + "_recpred")
+    nI = int(max(g["ae_item"].max(), g["test_item"].max(), g["nb_idx"].max())) + 1
+    P = RS.recommender_cosine_item(g["ae_user"], g["ae_item"], g["ae_rating"], nI, int(g["num_atleast"]))
+    ptr, idx, val = RS.recommender_neighbors(P, nI, int(g["mapping_range"]))
+    has = np.flatnonzero(np.diff(ptr))
+    assert np.array_equal(has, g["nb_item"])
+    assert np.array_equal(np.diff(ptr)[has], np.diff(g["nb_ptr"]))
+    assert np.array_equal(idx, g["nb_idx"])
+    np.testing.assert_allclose(val, g["nb_sim"], rtol=1e-12)
+    cnt = np.bincount(g["ae_item"], minlength=nI)
+    avg = np.bincount(g["ae_item"], weights=g["ae_rating"], minlength=nI) / np.maximum(cnt, 1)
+    p0, p1, m0, m1 = RS.recommender_predict(g["ae_user"], g["ae_item"], g["ae_rating"], g["ae_ts"], ptr, idx, val, avg,
+                                            g["test_user"], g["test_item"], g["test_rating"], float(g["alpha"]))
+    assert np.array_equal(p0, g["pred_nodecay"]) and np.array_equal(p1, g["pred_decay"])
+    assert abs(m0 - float(g["mae_nodecay"])) < 1e-12 and abs(m1 - float(g["mae_decay"])) < 1e-12

@@ -123,6 +123,101 @@ __global__ void __launch_bounds__(256) recsim_pair_kernel(const int64_t *__restr
     }
 }
 
+// ---- non-private neighbour selection (recommenderPrivacy.py:141-178): per item the first K neighbours by |sim|
+// descending, ties to the smaller neighbour index; the self pair is a neighbour like any other.  One warp per
+// item over its run of the (i, j)-sorted pair list: K rounds of a warp arg-best, each taking the best
+// candidate strictly after the previous winner.
+__global__ void __launch_bounds__(256) recsim_neighbors_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ pj,
+                                                               const double *__restrict__ psim, int32_t n_items, int32_t K,
+                                                               int32_t *__restrict__ nb_idx, double *__restrict__ nb_sim,
+                                                               int32_t *__restrict__ nb_len) {
+    const int i = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n_items) return;
+    const int64_t lo = row_ptr[i], hi = row_ptr[i + 1];
+    unsigned long long last_k = ~0ull;
+    int last_t = -1, got = 0;
+    for (int r = 0; r < K; ++r) {
+        unsigned long long bk = 0ull; int bt = 0x7FFFFFFF, bp = -1;
+        for (int64_t e = lo + lane; e < hi; e += 32) {
+            const unsigned long long ak = abs_key(psim[e]);
+            const int jj = pj[e];
+            if (r > 0 && !better(last_k, last_t, ak, jj)) continue;
+            if (bp < 0 || better(ak, jj, bk, bt)) { bk = ak; bt = jj; bp = (int)(e - lo); }
+        }
+        warp_argbest(bk, bt, bp);
+        if (bp < 0) break;
+        if (lane == 0) { nb_idx[(size_t)i * K + r] = bt; nb_sim[(size_t)i * K + r] = psim[lo + bp]; }
+        last_k = bk; last_t = bt;
+        got = r + 1;
+    }
+    if (lane == 0) nb_len[i] = got;
+}
+
+// ---- item-based prediction (recommenderPrediction.py:26-103): one thread per test (user, item) pair.
+// Entries = (sim * (r - avg_n), |sim|, time) for every profile record of the user on a neighbour n of the item, in
+// (neighbour, profile list) order; no-decay = avg + sum a / sum b; decay = the same with weights
+// exp(-alpha (cur - rank)) after a stable sort by time (equal times share a rank, :36-49).
+constexpr int PRED_CAP = 128;
+
+__device__ __forceinline__ double rs_bound_rating(double x) {      // :19-24, int() truncates towards zero
+    const int v = (int)(x + 0.5);
+    return 1.0 * (double)max(0, min(v, 5));
+}
+
+__global__ void __launch_bounds__(128) recsim_predict_kernel(const int64_t *__restrict__ prof_ptr, const int32_t *__restrict__ prof_item,
+                                                             const double *__restrict__ prof_rating, const int64_t *__restrict__ prof_ts,
+                                                             const double *__restrict__ info, const int32_t *__restrict__ nb_idx,
+                                                             const double *__restrict__ nb_sim, const int32_t *__restrict__ nb_len, int32_t K,
+                                                             const int32_t *__restrict__ t_user, const int32_t *__restrict__ t_item,
+                                                             int64_t n_test, double alpha, double *__restrict__ pred0,
+                                                             double *__restrict__ pred1, int32_t *__restrict__ error_flag) {
+    const int64_t q = blockIdx.x * (int64_t)128 + threadIdx.x;
+    if (q >= n_test) return;
+    const int u = t_user[q], it = t_item[q];
+    const int L = nb_len[it];
+    if (L == 0) { pred0[q] = -1.0; pred1[q] = -1.0; return; }        // `iid not in sim_bd.value.keys()` -> ()
+    double ea[PRED_CAP], eb[PRED_CAP];
+    long long et[PRED_CAP];
+    int n = 0;
+    const int64_t lo = prof_ptr[u], hi = prof_ptr[u + 1];
+    for (int r = 0; r < L; ++r) {
+        const int nid = nb_idx[(size_t)it * K + r];
+        const double ns = nb_sim[(size_t)it * K + r];
+        const double avg_n = info[3 * (size_t)nid];
+        for (int64_t e = lo; e < hi; ++e) {
+            if (prof_item[e] != nid) continue;
+            if (n == PRED_CAP) { atomicExch(error_flag, 4); break; }
+            ea[n] = __dmul_rn(ns, __dsub_rn(prof_rating[e], avg_n)); eb[n] = fabs(ns); et[n] = prof_ts[e];
+            ++n;
+        }
+    }
+    const double avg = info[3 * (size_t)it];
+    double p0 = avg, p1 = avg;
+    if (n > 0) {
+        double sa = 0.0, sb = 0.0;
+        for (int k = 0; k < n; ++k) { sa = __dadd_rn(sa, ea[k]); sb = __dadd_rn(sb, eb[k]); }
+        p0 = __dadd_rn(avg, __ddiv_rn(sa, sb));
+        for (int k = 1; k < n; ++k) {                              // stable insertion sort by time
+            const double a0 = ea[k], b0 = eb[k];
+            const long long t0 = et[k];
+            int m = k - 1;
+            while (m >= 0 && et[m] > t0) { ea[m + 1] = ea[m]; eb[m + 1] = eb[m]; et[m + 1] = et[m]; --m; }
+            ea[m + 1] = a0; eb[m + 1] = b0; et[m + 1] = t0;
+        }
+        int order = 0, top = 0;
+        for (int k = 0; k < n; ++k) if (k == 0 || et[k] != et[k - 1]) ++top;
+        const double cur = (double)(top + 1);
+        sa = 0.0; sb = 0.0;
+        for (int k = 0; k < n; ++k) {
+            if (k == 0 || et[k] != et[k - 1]) ++order;
+            const double f = exp(-alpha * (cur - (double)order));
+            sa = __dadd_rn(sa, __dmul_rn(ea[k], f)); sb = __dadd_rn(sb, __dmul_rn(eb[k], f));
+        }
+        p1 = __dadd_rn(avg, __ddiv_rn(sa, sb));
+    }
+    pred0[q] = rs_bound_rating(p0); pred1[q] = rs_bound_rating(p1);
+}
+
 }  // namespace xmap
 
 using namespace xmap;
@@ -152,6 +247,28 @@ extern "C" int xmap_recsim_pairs(const int64_t *seg_ptr, const int64_t *seg_key,
     recsim_pair_kernel<<<(unsigned)((n_pairs + 7) / 8), 256, 0, (cudaStream_t)stream_>>>(seg_ptr, seg_key, src, rating, info, n_items,
                                                                                         n_pairs, num_atleast, out_i, out_j, out_n,
                                                                                         out_sim, out_ls);
+    XMAP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xmap_recsim_neighbors(const int64_t *row_ptr, const int32_t *pair_j, const double *pair_sim, int32_t n_items,
+                                     int32_t k, int32_t *nb_idx, double *nb_sim, int32_t *nb_len, void *stream_) {
+    if (n_items <= 0) return 0;
+    if (k < 1 || k > XMAP_KMAX) return fail_msg("xmap_recsim_neighbors: k out of range");
+    recsim_neighbors_kernel<<<(unsigned)((n_items + 7) / 8), 256, 0, (cudaStream_t)stream_>>>(row_ptr, pair_j, pair_sim, n_items, k,
+                                                                                          nb_idx, nb_sim, nb_len);
+    XMAP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xmap_recsim_predict(const int64_t *prof_ptr, const int32_t *prof_item, const double *prof_rating,
+                                   const int64_t *prof_ts, const double *info, const int32_t *nb_idx, const double *nb_sim,
+                                   const int32_t *nb_len, int32_t k, const int32_t *t_user, const int32_t *t_item, int64_t n_test,
+                                   double alpha, double *pred_nodecay, double *pred_decay, int32_t *error_flag, void *stream_) {
+    if (n_test <= 0) return 0;
+    recsim_predict_kernel<<<(unsigned)((n_test + 127) / 128), 128, 0, (cudaStream_t)stream_>>>(
+        prof_ptr, prof_item, prof_rating, prof_ts, info, nb_idx, nb_sim, nb_len, k, t_user, t_item, n_test, alpha,
+        pred_nodecay, pred_decay, error_flag);
     XMAP_LAUNCH_CHECK();
     return 0;
 }

@@ -47,33 +47,6 @@ struct __align__(16) OStat {
 struct __align__(16) Cell {
     unsigned key, cnt, lo, hi;
 };
-// Shared-memory tables rotate the four words of a cell by (slot >> 3) & 3: an atomic on ONE field of 32
-// random cells then spreads over all 32 banks (bank = 4 (slot & 7) + ((field + (slot >> 3)) & 3)); with the
-// plain layout a field can only reach 8 banks (bank = 4 slot + field mod 32), a 4-way conflict by construction.
-template <bool ROT>
-__device__ __forceinline__ unsigned *cell_word(Cell *T, int slot, int field) {
-    return reinterpret_cast<unsigned *>(T) + 4 * slot + (ROT ? ((field + (slot >> 3)) & 3) : field);
-}
-template <bool ROT>
-__device__ __forceinline__ uint4 cell_unrot(uint4 v, int slot) {       // stored words -> (key, cnt, lo, hi)
-    if (!ROT) return v;
-    switch ((slot >> 3) & 3) {
-        case 1: return make_uint4(v.y, v.z, v.w, v.x);
-        case 2: return make_uint4(v.z, v.w, v.x, v.y);
-        case 3: return make_uint4(v.w, v.x, v.y, v.z);
-        default: return v;
-    }
-}
-template <bool ROT>
-__device__ __forceinline__ uint4 cell_rot(uint4 v, int slot) {         // (key, cnt, lo, hi) -> stored words
-    if (!ROT) return v;
-    switch ((slot >> 3) & 3) {
-        case 1: return make_uint4(v.w, v.x, v.y, v.z);
-        case 2: return make_uint4(v.z, v.w, v.x, v.y);
-        case 3: return make_uint4(v.y, v.z, v.w, v.x);
-        default: return v;
-    }
-}
 
 // 16-byte neighbour record: bits of sim, other_item | mutu << 32; the co-rating count n of the record at
 // position p lives in the parallel array rec_n[p] (only the winners of the selection ever read it), so the item
@@ -180,7 +153,6 @@ struct SplitCtx {
 template <bool CTA_ROW, class IDX>
 __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__restrict__ occ_list, int *s_cnt,
                         int cells_cap, const RowHdr *hdr_p, const SplitCtx *sp = nullptr) {
-    constexpr bool ROT = sizeof(IDX) == 2;                 // shared-memory tables only (global ones use 64-bit atomics)
     const int lane = threadIdx.x & 31;
     const int gwarps = CTA_ROW ? (blockDim.x >> 5) : 1;
     const int gw = CTA_ROW ? (threadIdx.x >> 5) : 0;
@@ -252,52 +224,32 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__res
             }
 #pragma unroll
             for (int u = 0; u < UC; ++u) {
-                int oj = 0;
-                long long fx = 0;
-                unsigned agree = 0u;
-                if (valid[u]) {
-                    oj = ent_item(en[u].x);
-                    const double cj = (double)__uint_as_float(en[u].y) - mu_l[u];
-                    const double p = __dmul_rn(ci_l[u], cj);
-                    const int q = qbase - min(cls_i, ent_cls(en[u].x));
-                    fx = __double2ll_rn(p * pow2d(q));
-                    agree = ((unsigned)ent_ge(en[u].x) == (st_l[u] >> 31)) ? 1u : 0u;
-                }
+                if (!valid[u]) continue;
+                const int oj = ent_item(en[u].x);
+                const double cj = (double)__uint_as_float(en[u].y) - mu_l[u];
+                const double p = __dmul_rn(ci_l[u], cj);
+                const int q = qbase - min(cls_i, ent_cls(en[u].x));
+                const long long fx = __double2ll_rn(p * pow2d(q));
+                const unsigned agree = ((unsigned)ent_ge(en[u].x) == (st_l[u] >> 31)) ? 1u : 0u;
                 int slot;
-                bool ok = valid[u];
-                unsigned add_a = agree, add_d = 1u - agree;   // agreeing / disagreeing co-raters this lane adds
+                bool ok = true;
                 if (direct) {
-                    // popular rows have few columns: lanes of a chunk that hit the same column are summed first
-                    // (exact integer sums, order-free), the lowest lane of each group does the atomics
-                    slot = valid[u] ? top_ord - oj : -1 - lane;                   // in [0, rtop)
-                    const unsigned grp = __match_any_sync(0xffffffffu, slot);
-                    if (__any_sync(0xffffffffu, (grp & (grp - 1u)) != 0u)) {      // some column repeats in this chunk
-                        add_a = __reduce_add_sync(grp, agree);
-                        add_d = (unsigned)__popc(grp) - add_a;
-                        const unsigned s0 = __reduce_add_sync(grp, (unsigned)((unsigned long long)fx & 0x1FFFFFull));
-                        const unsigned s1 = __reduce_add_sync(grp, (unsigned)(((unsigned long long)fx >> 21) & 0x1FFFFFull));
-                        const int s2 = __reduce_add_sync(grp, (int)(fx >> 42));
-                        fx = (long long)s2 * (1ll << 42) + (long long)(((unsigned long long)s1 << 21) + (unsigned long long)s0);
-                        ok = valid[u] && (__ffs(grp) - 1) == lane;
-                    }
-                    if (ok) {
-                        if (add_a) atomicAdd(cell_word<ROT>(T, slot, 0), add_a);
-                        if (add_d) atomicAdd(cell_word<ROT>(T, slot, 1), add_d);
-                    }
-                } else if (ok) {
+                    slot = top_ord - oj;                   // in [0, rtop)
+                    atomicAdd(agree ? &T[slot].key : &T[slot].cnt, 1u);
+                } else {
                     const unsigned key = (unsigned)oj + 1u;
                     slot = (int)__umulhi((unsigned)oj * 2654435761u, (unsigned)ncell);
                     ok = false;
                     for (int probe = 0; probe < ncell; ++probe) {
-                        unsigned c = *(volatile unsigned *)cell_word<ROT>(T, slot, 0);
+                        unsigned c = *(volatile unsigned *)&T[slot].key;
                         if (c != key) {
-                            if (c == 0u) c = atomicCAS(cell_word<ROT>(T, slot, 0), 0u, key);
+                            if (c == 0u) c = atomicCAS(&T[slot].key, 0u, key);
                             if (c != 0u && c != key) { slot = (slot + 1 == ncell) ? 0 : slot + 1; continue; }
                         }
                         ok = true;
                         break;
                     }
-                    if (ok) atomicAdd(cell_word<ROT>(T, slot, 1), (1u << 16) | agree);
+                    if (ok) atomicAdd(&T[slot].cnt, (1u << 16) | agree);
                     else atomicExch(a.error_flag, 1);
                 }
                 if (ok) {
@@ -308,10 +260,10 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__res
                         const unsigned flo = (unsigned)(unsigned long long)fx;
                         unsigned fhi = (unsigned)((unsigned long long)fx >> 32);
                         if (flo) {
-                            const unsigned old = atomicAdd(cell_word<ROT>(T, slot, 2), flo);
+                            const unsigned old = atomicAdd(&T[slot].lo, flo);
                             fhi += ((unsigned)(old + flo) < old) ? 1u : 0u;
                         }
-                        if (fhi) atomicAdd(cell_word<ROT>(T, slot, 3), fhi);
+                        if (fhi) atomicAdd(&T[slot].hi, fhi);
                     }
                 }
             }
@@ -325,7 +277,7 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__res
             return;
         }
         for (int s = gtid; s < ncell; s += gthreads) {
-            const uint4 v = cell_unrot<ROT>(T4[s], s);
+            const uint4 v = T4[s];
             if (v.x) atomicAdd(&sp->gtab[s].x, v.x);
             if (v.y) atomicAdd(&sp->gtab[s].y, v.y);
             const unsigned long long fx = ((unsigned long long)v.w << 32) | v.z;
@@ -340,7 +292,7 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__res
         if (!last) return;
         __threadfence();
         for (int s = gtid; s < ncell; s += gthreads) {
-            T4[s] = cell_rot<ROT>(__ldcg(sp->gtab + s), s);
+            T4[s] = __ldcg(sp->gtab + s);
             sp->gtab[s] = make_uint4(0u, 0u, 0u, 0u);
         }
         if (gtid == 0) { *sp->done = 0; *s_cnt = 0; }
@@ -353,7 +305,7 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__res
         const int s = s0 + lane;
         bool occ = false;
         if (s < ncell) {
-            const uint4 kc = cell_unrot<ROT>(T4[s], s);
+            const uint2 kc = *reinterpret_cast<const uint2 *>(&T[s]);
             occ = direct ? (kc.x | kc.y) != 0u : kc.x != 0u;
         }
         const unsigned m = __ballot_sync(0xffffffffu, occ);
@@ -389,7 +341,7 @@ __device__ void tri_row(const xmap_sim_args &a, Cell *__restrict__ T, IDX *__res
             sidx[u] = -1;
             if (i < n_ent) {
                 sidx[u] = (int)occ_list[i];
-                cv[u] = cell_unrot<ROT>(T4[sidx[u]], sidx[u]);
+                cv[u] = T4[sidx[u]];
                 int oj;
                 if (direct) { n[u] = cv[u].x + cv[u].y; mutu[u] = cv[u].x; oj = top_ord - sidx[u]; }
                 else { oj = (int)cv[u].x - 1; n[u] = cv[u].y >> 16; mutu[u] = cv[u].y & 0xFFFFu; }

@@ -145,11 +145,15 @@ __global__ void __launch_bounds__(XT_MAX, 1) xsim_warp_kernel(xmap_xsim_args a) 
                     const long long v = __ldg(a.lp_ptr + cur_leg + lane) - q0;
                     lpv = (int)max(-(1ll << 30), min((1ll << 30), v));
                 }
-                int cntle = 0;                             // number of legs whose first pair is <= lane
+                int cntle = 0;                             // number of legs whose first pair is <= lane, 1 .. 32
 #pragma unroll
                 for (int step = 16; step >= 1; step >>= 1) {
                     const int v = __shfl_sync(0xffffffffu, lpv, cntle + step - 1);
                     if (v <= lane) cntle += step;
+                }
+                {   // the halving steps stop at 31: 32 single-pair legs in a row need one more probe
+                    const int v = __shfl_sync(0xffffffffu, lpv, 31);
+                    if (cntle == 31 && v <= lane) cntle = 32;
                 }
                 const int aslot = max(cntle - 1, 0);
                 const int lp_a = __shfl_sync(0xffffffffu, lpv, aslot);

@@ -241,7 +241,7 @@ XSIM_MAX_PASSES = int(os.environ.get("XMAP_XSIM_MAX_PASSES", "1000000000"))   # 
                                 # global memory (L2).  Measured at cfg2: 32 passes + L2 tables 968 ms, shared memory only
                                 # (no cap) 732 ms -- dependent read-modify-writes at L2 latency lose to narrow passes
 XSIM_GCELLS_LG = 16             # largest global-memory table of a unit (cells)
-XSIM_MODE = os.environ.get("XMAP_XSIM_MODE", "warp")               # "warp": one warp per unit (xsim.cu); "cta": one CTA per
+XSIM_MODE = os.environ.get("XMAP_XSIM_MODE", "cta")                # "warp": one warp per unit (xsim.cu); "cta": one CTA per
                                                                    # unit with one 8x larger table (xsim_cta.cu)
 XSIM_CTA_CELLS_LG = int(os.environ.get("XMAP_XSIM_CTA_CELLS_LG", "12"))
 XSIM_CTA_UNIT_LG = int(os.environ.get("XMAP_XSIM_CTA_UNIT_LG", "20"))

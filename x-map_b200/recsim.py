@@ -73,3 +73,61 @@ def cosine_item(user, item, rating, n_items, num_atleast=50, device="cuda"):
                                 n_items, n_pairs, int(num_atleast), N.ptr(out_i), N.ptr(out_j), N.ptr(out_n),
                                 N.ptr(out_sim), N.ptr(out_ls), _st()), "xmap_recsim_pairs")
     return RecSim(out_i, out_j, out_n, out_sim, out_ls, info, total)
+
+
+@dataclass
+class Neighbors:
+    idx: torch.Tensor        # int32 [n_items, k]
+    sim: torch.Tensor        # f64   [n_items, k]
+    len: torch.Tensor        # int32 [n_items]
+
+
+def neighbors(rs, n_items, k=10):
+    """RecommenderPrivacy.nonprivate_neighbor_selection + nonnoise_perturbation (recommenderPrivacy.py:141-189):
+    {item: [(neighbour, sim)] first k by |sim|} as fixed-width tables."""
+    L = N.lib()
+    dev = rs.i.device
+    row_ptr = torch.zeros(n_items + 1, dtype=torch.int64, device=dev)
+    row_ptr[1:] = torch.cumsum(torch.bincount(rs.i.long(), minlength=n_items), 0)
+    nb_idx = torch.full((n_items, k), -1, dtype=torch.int32, device=dev)
+    nb_sim = torch.zeros((n_items, k), dtype=torch.float64, device=dev)
+    nb_len = torch.zeros(n_items, dtype=torch.int32, device=dev)
+    N.check(L.xmap_recsim_neighbors(N.ptr(row_ptr), N.ptr(rs.j.contiguous()), N.ptr(rs.sim.contiguous()), n_items, int(k),
+                                    N.ptr(nb_idx), N.ptr(nb_sim), N.ptr(nb_len), _st()), "xmap_recsim_neighbors")
+    return Neighbors(nb_idx, nb_sim, nb_len)
+
+
+def predict(user, item, rating, ts, n_users, rs, nb, test_user, test_item, test_rating=None, alpha=0.03):
+    """RecommenderPrediction.item_based_recommendation + calculate_mae (recommenderPrediction.py:26-139) on the
+    profile records (list order).  Returns (pred_nodecay, pred_decay, mae_nodecay, mae_decay); predictions are -1
+    where the test item has no neighbour list, the MAEs are None without test ratings."""
+    L = N.lib()
+    dev = rs.i.device
+    user = torch.as_tensor(user, dtype=torch.int64).to(dev)
+    ou = torch.argsort(user, stable=True)
+    prof_ptr = torch.zeros(n_users + 1, dtype=torch.int64, device=dev)
+    prof_ptr[1:] = torch.cumsum(torch.bincount(user, minlength=n_users), 0)
+    p_item = torch.as_tensor(item, dtype=torch.int32).to(dev)[ou].contiguous()
+    p_rating = torch.as_tensor(rating, dtype=torch.float64).to(dev)[ou].contiguous()
+    p_ts = torch.as_tensor(ts, dtype=torch.int64).to(dev)[ou].contiguous()
+    tu = torch.as_tensor(test_user, dtype=torch.int32).to(dev).contiguous()
+    ti = torch.as_tensor(test_item, dtype=torch.int32).to(dev).contiguous()
+    n_test = int(tu.numel())
+    p0 = torch.empty(n_test, dtype=torch.float64, device=dev)
+    p1 = torch.empty(n_test, dtype=torch.float64, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    k = int(nb.idx.shape[1])
+    N.check(L.xmap_recsim_predict(N.ptr(prof_ptr), N.ptr(p_item), N.ptr(p_rating), N.ptr(p_ts), N.ptr(rs.info),
+                                  N.ptr(nb.idx), N.ptr(nb.sim), N.ptr(nb.len), k, N.ptr(tu), N.ptr(ti), n_test,
+                                  float(alpha), N.ptr(p0), N.ptr(p1), N.ptr(err), _st()), "xmap_recsim_predict")
+    if int(err.item()):
+        raise N.NativeError("prediction kernel error %d (4: more than 128 matching profile records)" % int(err.item()))
+    mae0 = mae1 = None
+    if test_rating is not None:
+        tr = torch.as_tensor(test_rating, dtype=torch.float64).to(dev)
+        ok = p0 >= 0
+        cnt = int(ok.sum().item())
+        if cnt:
+            mae0 = float((tr[ok] - p0[ok]).abs().sum().item()) / cnt          # recommenderPrediction.py:116-139
+            mae1 = float((tr[ok] - p1[ok]).abs().sum().item()) / cnt
+    return p0, p1, mae0, mae1
