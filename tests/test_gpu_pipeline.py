@@ -155,3 +155,38 @@ def test_facade_methods_match_reference_golden():
     for nbr_id, (s_, m_, f_) in knn_BB.value[some].items():
         w = key[(some, nbr_id)]
         assert m_ == w[1] and f_ == w[2] and abs(s_ - w[0]) <= PT.SIM_RTOL * abs(w[0])
+
+
+@pytest.mark.parametrize("name", ["adj_low_overlap", "adj_all_bridge"])
+def test_recommender_pipelines_match_reference(name):
+    """twodomain_demo.py:107-134 after the AlterEgo profile: recommender_calculate_sim_pipeline ->
+    recommender_privacy_pipeline (non-private) -> recommender_prediction_pipeline, reference names and record
+    shapes, against what the unmodified reference produced (tests/golden/*_recpred.npz)."""
+    from xmap_b200.rdd import LocalRDD, Broadcast
+    from xmap_b200.core import (RecommenderSim, RecommenderPrivacy, RecommenderPrediction,
+                                recommender_calculate_sim_pipeline, recommender_privacy_pipeline,
+                                recommender_prediction_pipeline)
+    g0, g = PT.load_golden(name), PT.load_golden(name + "_recpred")
+    iids, uids = [str(s) for s in g0["iids"]], [str(s) for s in g0["uids"]]
+    profile = LocalRDD([(uids[u], iids[i], float(r), datetime.utcfromtimestamp(int(t)))
+                        for u, i, r, t in zip(g["ae_user"], g["ae_item"], g["ae_rating"], g["ae_ts"])])
+    sim_tool = RecommenderSim("cosine_item", int(g["num_atleast"]))
+    out = recommender_calculate_sim_pipeline(None, sim_tool, profile)
+    item_info = out[5].value
+    assert len(out) == 7 and set(item_info) == {iids[i] for i in np.unique(g["ae_item"])}
+    neigh = recommender_privacy_pipeline(RecommenderPrivacy(int(g["mapping_range"]), 0.6, 0.1), out[6], False).collectAsMap()
+    for q, it in enumerate(g["nb_item"]):
+        a, b = g["nb_ptr"][q], g["nb_ptr"][q + 1]
+        got = neigh[iids[it]]
+        if [x[0] for x in got] != [iids[j] for j in g["nb_idx"][a:b]]:        # only a near-tie may reorder a list
+            assert np.allclose(np.abs([x[1] for x in got]), np.abs(g["nb_sim"][a:b]), rtol=1e-9, atol=0)
+    # test records: one per user, in the golden's order
+    test, cur = [], None
+    for u, i, r in zip(g["test_user"], g["test_item"], g["test_rating"]):
+        if cur is None or cur[0] != uids[u]:
+            cur = (uids[u], []); test.append(cur)
+        cur[1].append((iids[i], float(r), datetime(2013, 1, 1)))
+    mae = recommender_prediction_pipeline(RecommenderPrediction(float(g["alpha"]), "cosine_item"), sim_tool, LocalRDD(test),
+                                          Broadcast(neigh), out[2], out[3], out[4], out[5])
+    m0, m1 = (float(x) for x in mae.split(";"))
+    assert abs(m0 - float(g["mae_nodecay"])) < 1e-2 and abs(m1 - float(g["mae_decay"])) < 1e-2

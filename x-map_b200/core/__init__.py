@@ -6,9 +6,14 @@ from .baselinerSplit import BaselinerSplit
 from .baselinerSim import BaselinerSim
 from .extender import ExtendSim
 from .generator import Generator
+from .recommender import (RecommenderSim, RecommenderPrivacy, RecommenderPrediction,
+                          recommender_calculate_sim_pipeline, recommender_privacy_pipeline,
+                          recommender_prediction_pipeline)
 from ..utils.assist import (baseliner_clean_data_pipeline, baseliner_split_data_pipeline,
                             baseliner_calculate_sim_pipeline, extender_pipeline, generator_pipeline)
 
 __all__ = ["BaselinerClean", "BaselinerSplit", "BaselinerSim", "ExtendSim", "Generator",
+           "RecommenderSim", "RecommenderPrivacy", "RecommenderPrediction", "recommender_calculate_sim_pipeline",
+           "recommender_privacy_pipeline", "recommender_prediction_pipeline",
            "baseliner_clean_data_pipeline", "baseliner_split_data_pipeline",
            "baseliner_calculate_sim_pipeline", "extender_pipeline", "generator_pipeline"]

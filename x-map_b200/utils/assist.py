@@ -90,3 +90,8 @@ def write_to_disk(results, out_dict, path):
     out_dict["result"] = results
     with open(join(out_folder, "info.yaml"), "w") as f:
         f.write(yaml.dump(out_dict, default_flow_style=False))
+
+
+# downstream recommender stages on the AlterEgo profile (assist.py:153-207): see core/recommender.py
+from ..core.recommender import (recommender_calculate_sim_pipeline, recommender_privacy_pipeline,  # noqa: E402,F401
+                                recommender_prediction_pipeline)
