@@ -216,10 +216,22 @@ def cpu_baseline(wl, method="adjust_cosine", num_atleast=50, target_ratings=250_
             res = pool.map(_cpu_block, jobs)
     dt = time.perf_counter() - t0
     n_pairs = sum(r[0] for r in res)
-    return {"value": n_pairs / dt, "unit": "item pairs/s", "cores": cores, "kind": "port",
-            "sample": "%d sample(s), every %d-th user of %s (%d ratings, %d co-rated pairs, %.1f s wall): "
-                      "oracle/restate.py, the numpy/scipy restatement of the reference arithmetic "
-                      "(no Spark/JVM/shuffle serialisation)" % (cores, stride, wl["name"], nr, n_pairs, dt)}
+    out = {"value": n_pairs / dt, "unit": "item pairs/s", "cores": cores, "kind": "port",
+           "sample": "%d sample(s), every %d-th user of %s (%d ratings, %d co-rated pairs, %.1f s wall): "
+                     "oracle/restate.py, the numpy/scipy restatement of the reference arithmetic "
+                     "(no Spark/JVM/shuffle serialisation)" % (cores, stride, wl["name"], nr, n_pairs, dt)}
+    # the reference's OWN Python on the same kind of sample cannot be timed here (/root/reference does not travel to
+    # the GPU box): quote the measurement taken in the build container (tools/ref_shim_time.py), labelled as such
+    p = os.path.join(ROOT, "profiles", "r2_reference_own_python_sample.json")
+    if os.path.isfile(p):
+        try:
+            r = json.load(open(p))
+            out["reference_own_python"] = {"value": r["pairs_per_s"], "unit": "item pairs/s", "cores": r["cores"],
+                                           "sample": r["sample"], "seconds": r["seconds"], "what": r["what"],
+                                           "measured": "build container, not this box"}
+        except Exception:
+            pass
+    return out
 
 
 def run_reference_arm(args, emit):
