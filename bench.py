@@ -324,6 +324,7 @@ def main():
     budget = None if len(pipes) == 1 else int(free_b * 0.6 / len(pipes))
     for wl in pipes:
         wl["lay"] = E.build_layout(*wl["h"], wl["n_users"], wl["n_items"], device=dev)
+        wl["ts_dev"] = torch.as_tensor(wl["ts"], dtype=torch.int64).to(dev)       # rating times, resident like the layout
         wl["eng"] = E.SimEngine(wl["lay"], wl["dmeta"], args.method, 50, k, rec_budget=budget)
         wl["shard"] = MG.similarity_shard(wl["eng"], rank, world)
 
@@ -425,7 +426,7 @@ def main():
             barrier(); t2 = time.perf_counter()
             ch = G.choose_mapping(res, "argmax", sim_method=args.method)
             mp = G.invert_mapping(res.start_item, ch, wl["n_items"])
-            ou, oi, orr, ot = MG.build_alterego_sharded(lay, wl["ts"], mp, MG.UserShard(lay.csr_ptr, rank, world))
+            ou, oi, orr, ot = MG.build_alterego_sharded(lay, wl["ts_dev"], mp, MG.UserShard(lay.csr_ptr, rank, world))
             n_rec = torch.tensor([ou.numel()], dtype=torch.int64, device=dev)
             if world > 1:
                 dist.all_reduce(n_rec)

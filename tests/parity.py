@@ -246,6 +246,14 @@ def run_smoke():
     out = check_sim_against_restatement(case, "adjust_cosine", 50, 4)
     print("smoke: %d kept pairs, sim max rel err %.3g, launches %d" % (
         len(out["P"]["i"]), out["rel"], out["eng"].launches))
+    # the rest of the path on the same case: X-SIM extension (both kernels) and the argmax mapping vs the oracle
+    from oracle import restate as RS
+    X = RS.xsim_extend(out["P"], out["knn"], case["n_items"], case["meta"]["has_S"], case["meta"]["has_T"])
+    for mode in ("cta", "warp"):
+        plan, xe, res, (s, e, v) = run_gpu_extend(out["tabs"], out["lay"], case["meta"], mode=mode)
+        rel = compare_xsim(s, e, v, X["start"], X["end"], X["xsim"])
+        assert int(res.combos.sum()) == X["combos"]
+        print("smoke: X-SIM (%s kernel) %d pairs from %d paths, max rel err %.3g" % (mode, len(v), X["combos"], rel))
 
 
 # --------------------------------------------------------------------------

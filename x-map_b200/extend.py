@@ -230,8 +230,8 @@ def build_plan(tabs, item_count, has_S, has_T):
 PI_MULT = 0x9E3779B1            # pi(y) = (y * PI_MULT) mod 2^32 orders every right-segment list (csrc/xsim.cu)
 XSIM_CELLS_LG = int(os.environ.get("XMAP_XSIM_CELLS_LG", "9"))    # 512-cell shared-memory table per warp ...
 XSIM_WARPS = int(os.environ.get("XMAP_XSIM_WARPS", "20"))         # ... 20 warps per CTA (limited by registers: 94 x 640)
-XSIM_LOAD = 0.62                # target fill of a table
-XSIM_RHO = 1.25                 # assumed paths per distinct end when a start's pass count is chosen
+XSIM_LOAD = float(os.environ.get("XMAP_XSIM_LOAD", "0.62"))       # target fill of a table
+XSIM_RHO = float(os.environ.get("XMAP_XSIM_RHO", "1.25"))         # assumed paths per distinct end when a start's pass count is chosen
                                 # (measured at cfg2: 10 % quantile 1.30, median 1.62; a pass that turns out
                                 # too full is split on the device)
 XSIM_UNIT_WORK = 1 << int(os.environ.get("XMAP_XSIM_UNIT_LG", "17"))   # paths per unit (= per warp): heavier starts are
@@ -244,7 +244,7 @@ XSIM_GCELLS_LG = 16             # largest global-memory table of a unit (cells)
 XSIM_MODE = os.environ.get("XMAP_XSIM_MODE", "cta")                # "warp": one warp per unit (xsim.cu); "cta": one CTA per
                                                                    # unit with one 8x larger table (xsim_cta.cu)
 XSIM_CTA_CELLS_LG = int(os.environ.get("XMAP_XSIM_CTA_CELLS_LG", "12"))
-XSIM_CTA_UNIT_LG = int(os.environ.get("XMAP_XSIM_CTA_UNIT_LG", "20"))
+XSIM_CTA_UNIT_LG = int(os.environ.get("XMAP_XSIM_CTA_UNIT_LG", "17"))     # 2^17 paths per unit: short critical path when units are dealt to 8 GPUs
 
 
 @dataclass
