@@ -322,6 +322,52 @@ def eval_plan_numpy(plan):
     return np.array(S)[o], np.array(E)[o], np.array(X)[o], combos
 
 
+def eval_engine_numpy(xe, g_ranges=None):
+    """Evaluates the arrays an extend.XsimEngine hands to the kernel (legs, partner lists incl. the virtual
+    partners of the fused bridge lists, pi-ordered right-segment / fused lists, tile pointers) the way the kernel
+    does, in numpy: pins the engine's host-side index building (small cases only).  g_ranges: tile ranges to walk
+    (default one pass over every tile); the union must cover [0, 2^gb)."""
+    g = lambda t: t.cpu().numpy()
+    p = xe.plan
+    leg_ptr, start_item = g(p.leg_ptr), g(p.start_item)
+    lp_base, lp_n = g(xe.leg_par_base), g(xe.leg_npar)
+    lN, lD, lC = g(xe.leg_n), g(xe.leg_d), g(xe.leg_c)
+    ps, pe, pm, pf = g(xe.par_s), g(xe.par_e), g(xe.par_m), g(xe.par_f)
+    rs_ptr, rs_end = g(xe.rs_ptr), g(xe.rs_end)
+    rN, rD, rC = (g(v) for v in xe.rs_ndc)
+    tp = g(xe.tile_ptr)
+    G = 1 << xe.gb
+    assert np.array_equal(tp[:, G], rs_ptr[1:] - rs_ptr[:-1]) and (tp[:, 0] == 0).all() and (np.diff(tp, axis=1) >= 0).all()
+    pi = (rs_end.astype(np.int64) * 0x9E3779B1) & 0xFFFFFFFF
+    tile = pi >> (32 - xe.gb)
+    for s_ in range(len(rs_ptr) - 1):                     # every list is ordered by pi and cut by tile_ptr
+        a, b = rs_ptr[s_], rs_ptr[s_ + 1]
+        assert (np.diff(pi[a:b]) >= 0).all()
+        assert np.array_equal(np.searchsorted(tile[a:b], np.arange(G + 1), side="left"), tp[s_])
+    g_ranges = g_ranges or [(0, G)]
+    S, E, X = [], [], []
+    combos = 0
+    for x in range(len(start_item)):
+        acc = {}
+        for g0, g1 in g_ranges:
+            for lg in range(leg_ptr[x], leg_ptr[x + 1]):
+                for pp in range(lp_base[lg], lp_base[lg] + lp_n[lg]):
+                    s_ = ps[pp]
+                    Nm = lN[lg] + pe[pp]; Dm = lD[lg] + pm[pp]; Cm = lC[lg] * pf[pp]
+                    a, b = rs_ptr[s_] + tp[s_, g0], rs_ptr[s_] + tp[s_, g1]
+                    Nn = Nm + rN[a:b]; Dd = Dm + rD[a:b]; cp = Cm * rC[a:b]
+                    with np.errstate(invalid="ignore", divide="ignore"):
+                        sp = np.where(Dd != 0, Nn / Dd, 0.0)
+                    combos += b - a
+                    for y, n_, d_ in zip(rs_end[a:b], sp * cp, cp):
+                        c = acc.setdefault(int(y), [0.0, 0.0])
+                        c[0] += n_; c[1] += d_
+        for y in sorted(acc):
+            S.append(int(start_item[x])); E.append(y); X.append(acc[y][0] / acc[y][1])
+    o = np.lexsort((E, S))
+    return np.array(S)[o], np.array(E)[o], np.array(X)[o], combos
+
+
 def eval_plan_starts(plan, starts):
     """X-SIM rows of a few starts (plan indices) evaluated in numpy straight from the plan arrays, one start
     at a time with the terms of a cell in path order: {start index: (ends sorted, xsim, n_paths)}.  Checks

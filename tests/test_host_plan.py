@@ -32,6 +32,35 @@ def test_plan_builder_reproduces_reference_xsim(name):
     assert int(plan.ub.sum()) == combos            # the per-start bound is exact in total
 
 
+@pytest.mark.parametrize("name", PT.GOLDEN_CASES)
+@pytest.mark.parametrize("fuse", [False, True])
+def test_engine_arrays_reproduce_the_plan(name, fuse, native_built):
+    """The arrays XsimEngine hands to the kernel -- with and without the fused bridge lists B(t) -- evaluated in
+    numpy give the plan's X-SIM: same keys, same path count, values within the reassociation bound."""
+    import torch
+    from xmap_b200 import extend as X
+    g = PT.load_golden(name)
+    meta = PT.golden_meta(g)
+    nU, nI = len(g["uids"]), len(g["iids"])
+    P = RS.sim_pairs(g["user"].astype(np.int64), g["item"].astype(np.int64), g["rating"], nU, nI,
+                     meta["prefix_code"], str(g["method"]), int(g["num_atleast"]))
+    knn = RS.select_knn(P, nI, int(g["k"]), meta["dom_code"], meta["contains"])
+    tabs = PT.tables_from_restatement(P, knn, nI, int(g["k"]))
+    plan = X.build_plan(tabs, torch.as_tensor(P["stats"]["count"]), torch.as_tensor(meta["has_S"]),
+                        torch.as_tensor(meta["has_T"]))
+    xe = X.XsimEngine(plan, 10, fuse=fuse)
+    assert (xe.fused_entries > 0) == (fuse and plan.n_joint > 0)     # adj_all_bridge has no joint pair
+    if fuse:                                              # every joint-only leg walks exactly one list
+        jo = plan.leg_joint_only.bool()
+        assert bool((xe.leg_npar[jo] == 1).all())
+    G = 1 << xe.gb
+    s, e, v, combos = PT.eval_engine_numpy(xe, [(0, G // 3), (G // 3, G)])
+    s0, e0, v0, combos0 = PT.eval_plan_numpy(plan)
+    assert combos == combos0 == int(plan.ub.sum())
+    PT.compare_xsim(s, e, v, s0, e0, v0, rtol=1e-12)
+    PT.compare_xsim(s, e, v, g["xs_start"], g["xs_end"], g["xs_val"], rtol=1e-9)
+
+
 def test_library_exports_every_declared_symbol(native_built):
     from xmap_b200 import _native
     hdr = open(os.path.join(PT.ROOT, "include", "xmap_b200.h")).read()

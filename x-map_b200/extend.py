@@ -243,6 +243,9 @@ XSIM_MAX_PASSES = int(os.environ.get("XMAP_XSIM_MAX_PASSES", "1000000000"))   # 
 XSIM_GCELLS_LG = 16             # largest global-memory table of a unit (cells)
 XSIM_MODE = os.environ.get("XMAP_XSIM_MODE", "cta")                # "warp": one warp per unit (xsim.cu); "cta": one CTA per
                                                                    # unit with one 8x larger table (xsim_cta.cu)
+XSIM_FUSE = os.environ.get("XMAP_XSIM_FUSE", "1") != "0"          # fused bridge lists B(t) for the joint-only legs
+XSIM_FUSE_MAX = 1 << 31         # entries (28 B each + sort scratch) above which the lists are not fused: a fixed number, not a
+                                # function of free memory, so that every rank takes the same decision
 XSIM_CTA_CELLS_LG = int(os.environ.get("XMAP_XSIM_CTA_CELLS_LG", "12"))
 XSIM_CTA_UNIT_LG = int(os.environ.get("XMAP_XSIM_CTA_UNIT_LG", "17"))     # 2^17 paths per unit: short critical path when units are dealt to 8 GPUs
 
@@ -269,10 +272,13 @@ class XsimEngine:
     are bit-identical from run to run and for any number of GPUs."""
 
     def __init__(self, plan, top_m=10, cells_lg=None, rho=XSIM_RHO, unit_work=None,
-                 load=XSIM_LOAD, warps=XSIM_WARPS, max_passes=XSIM_MAX_PASSES, mode=XSIM_MODE):
+                 load=XSIM_LOAD, warps=XSIM_WARPS, max_passes=XSIM_MAX_PASSES, mode=XSIM_MODE, fuse=None,
+                 fuse_max_entries=XSIM_FUSE_MAX):
         if mode not in ("warp", "cta"):
             raise ValueError("mode must be 'warp' or 'cta'")
         self.mode = mode
+        if fuse is None:
+            fuse = XSIM_FUSE
         if cells_lg is None:
             cells_lg = XSIM_CTA_CELLS_LG if mode == "cta" else XSIM_CELLS_LG
         if unit_work is None:
@@ -304,32 +310,86 @@ class XsimEngine:
         par_cnt = p.par_ptr[1:] - p.par_ptr[:-1]
         t_of_par = _segment_ids(par_cnt)
         joint = p.par_joint.long()
-        perm = torch.argsort(t_of_par * 2 + (1 - joint), stable=True) if joint.numel() else joint
-        self.par_s = p.par_s[perm].contiguous()
-        self.par_e, self.par_m, self.par_f = (v[perm].contiguous() for v in p.par_vals)
+        perm_par = torch.argsort(t_of_par * 2 + (1 - joint), stable=True) if joint.numel() else joint
+        self.par_s = p.par_s[perm_par].contiguous()
+        self.par_e, self.par_m, self.par_f = (v[perm_par].contiguous() for v in p.par_vals)
         jcnt = torch.zeros_like(par_cnt)
         if joint.numel():
             jcnt.index_add_(0, t_of_par, joint)
         lt = p.leg_t.long()
-        self.leg_npar = torch.where(p.leg_joint_only.bool(), jcnt[lt], par_cnt[lt]).to(i32).contiguous() \
-            if lt.numel() else torch.zeros(0, dtype=i32, device=dev)
-        self.leg_par_base = p.par_ptr[lt].contiguous() if lt.numel() else torch.zeros(0, dtype=i64, device=dev)
-        self.lp_ptr = torch.zeros(lt.numel() + 1, dtype=i64, device=dev)
-        self.lp_ptr[1:] = torch.cumsum(self.leg_npar.long(), 0)
+        leg_npar = torch.where(p.leg_joint_only.bool(), jcnt[lt], par_cnt[lt]) if lt.numel() else \
+            torch.zeros(0, dtype=i64, device=dev)
+        leg_par_base = p.par_ptr[lt] if lt.numel() else torch.zeros(0, dtype=i64, device=dev)
         # ---- right segments: the two edges folded into one (N, D, C) triple (the sums are reassociated
         # by at most one rounding; D is an exact integer either way), every list ordered by pi(end) ------
         r1, rm1, rf1, r2, rm2, rf2 = p.rs_vals
         rl = p.rs_ptr[1:] - p.rs_ptr[:-1]
         n_s = int(rl.numel())
-        if n_s and int(rl.max()) >= (1 << 26):
-            raise N.NativeError("a right-segment list has >= 2^26 entries: the per-batch product counter is 32-bit")
         seg = _segment_ids(rl)
         pi = (p.rs_end.long() * PI_MULT) & 0xFFFFFFFF
         perm = torch.argsort(seg * (1 << 32) + pi, stable=True) if seg.numel() else seg
-        self.rs_end = p.rs_end[perm].contiguous()
-        self.rs_ndc = ((r1 + r2)[perm].contiguous(), (rm1 + rm2)[perm].contiguous(), (rf1 * rf2)[perm].contiguous())
+        rs_end = p.rs_end[perm].contiguous()
+        rs_ndc = [(r1 + r2)[perm].contiguous(), (rm1 + rm2)[perm].contiguous(), (rf1 * rf2)[perm].contiguous()]
         pi = pi[perm] if seg.numel() else pi
+        rs_ptr = p.rs_ptr
         self.end_cap = int(torch.unique(p.rs_end).numel()) if p.rs_end.numel() else 1
+        # ---- fused bridge lists: what follows a joint-only leg (x .. t) does not depend on the start, so
+        # for every bridge target t the (bridge edge, right segment) combinations of its joint partners are
+        # materialised once as ONE list B(t) = {(end, e + N_r, m + D_r, f * C_r)}, ordered by pi(end) like any
+        # right-segment list.  A joint-only leg then has a single (virtual) partner whose list is B(t): a pass
+        # resolves one sub-range per LEG instead of one per (leg, partner) pair, and the sub-ranges are as many
+        # times longer.  (N_l + (e + N_r) instead of (N_l + e) + N_r: one more reassociation)
+        # The legs of type 0 (the bridge target itself, all partners) keep the pair lists.
+        self.fused_entries = 0
+        n_t = int(par_cnt.numel())
+        jl = p.leg_joint_only.bool() if lt.numel() else torch.zeros(0, dtype=torch.bool, device=dev)
+        if fuse and n_t and joint.numel() and bool(jl.any()):
+            used = torch.zeros(n_t, dtype=torch.bool, device=dev)
+            used[lt[jl]] = True
+            jp = torch.nonzero((joint[perm_par] == 1) & used[t_of_par]).flatten()      # joint partners, (t, joint-first) order
+            ln = rl[self.par_s[jp].long()]
+            F = int(ln.sum().item())
+            if 0 < F <= fuse_max_entries:
+                a_of = _segment_ids(ln)
+                q = torch.arange(F, device=dev) - _excl_cumsum(ln)[a_of]
+                r = rs_ptr[self.par_s[jp].long()][a_of] + q
+                pa = jp[a_of]
+                tt = t_of_par[pa]
+                o = torch.argsort(tt * (1 << 32) + pi[r], stable=True)
+                del q, a_of
+                r, pa, tt = r[o], pa[o], tt[o]
+                del o
+                f_end = rs_end[r]
+                f_n = self.par_e[pa] + rs_ndc[0][r]
+                f_d = self.par_m[pa] + rs_ndc[1][r]
+                f_c = self.par_f[pa] * rs_ndc[2][r]
+                f_pi = pi[r]
+                del r, pa
+                fl = torch.bincount(tt, minlength=n_t)
+                total_rs = int(rs_ptr[-1].item())
+                rs_ptr = torch.cat([rs_ptr[:-1], total_rs + _excl_cumsum(fl), rs_ptr.new_tensor([total_rs + F])])
+                seg = torch.cat([seg, n_s + tt]); del tt
+                pi = torch.cat([pi, f_pi]); del f_pi
+                rs_end = torch.cat([rs_end, f_end]); del f_end
+                rs_ndc = [torch.cat([rs_ndc[0], f_n]), torch.cat([rs_ndc[1], f_d]), torch.cat([rs_ndc[2], f_c])]
+                del f_n, f_d, f_c
+                rl = torch.cat([rl, fl])
+                n_par = int(self.par_s.numel())
+                self.par_s = torch.cat([self.par_s, (n_s + torch.arange(n_t, device=dev)).to(i32)])
+                zt = torch.zeros(n_t, dtype=torch.float64, device=dev)
+                self.par_e = torch.cat([self.par_e, zt]); self.par_m = torch.cat([self.par_m, zt])
+                self.par_f = torch.cat([self.par_f, torch.ones_like(zt)])
+                leg_par_base = torch.where(jl, n_par + lt, leg_par_base)
+                leg_npar = torch.where(jl, torch.ones_like(leg_npar), leg_npar)
+                n_s += n_t
+                self.fused_entries = F
+        if n_s and int(rl.max()) >= (1 << 26):
+            raise N.NativeError("a right-segment list has >= 2^26 entries: the per-batch product counter is 32-bit")
+        self.rs_ptr, self.rs_end, self.rs_ndc = rs_ptr.contiguous(), rs_end.contiguous(), tuple(v.contiguous() for v in rs_ndc)
+        self.leg_npar = leg_npar.to(i32).contiguous()
+        self.leg_par_base = leg_par_base.contiguous()
+        self.lp_ptr = torch.zeros(lt.numel() + 1, dtype=i64, device=dev)
+        self.lp_ptr[1:] = torch.cumsum(self.leg_npar.long(), 0)
         # ---- passes per start: enough for the estimated distinct ends, and enough units for its paths ---
         cap = max(16.0, load * (1 << self.cells_lg))
         ub = p.ub.double()
@@ -350,11 +410,21 @@ class XsimEngine:
         n_units_x = torch.clamp(n_units_x, max=G)
         ppu = (T + n_units_x - 1) // n_units_x                                 # passes per unit
         tile = (pi >> (32 - self.gb)) if self.gb else torch.zeros_like(pi)
-        cnt = torch.bincount(seg * G + tile, minlength=n_s * G).view(n_s, G) if seg.numel() else \
-            torch.zeros((n_s, G), dtype=i64, device=dev)
+        # tile_ptr[s][g] = entries of list s in tiles < g.  Built a block of lists at a time (32-bit counts scattered
+        # into the pointer rows, then a row-wise scan), so the scratch stays ~1 GB whatever the number of lists.
         self.tile_ptr = torch.zeros((n_s, G + 1), dtype=i32, device=dev)
-        self.tile_ptr[:, 1:] = torch.cumsum(cnt, 1).to(i32)
-        del cnt
+        if seg.numel():
+            blk = max(1, (1 << 27) // (G + 1))
+            cuts = list(range(0, n_s, blk)) + [n_s]
+            ent = self.rs_ptr[torch.tensor(cuts, device=dev)].tolist()
+            for a0, a1, e0, e1 in zip(cuts[:-1], cuts[1:], ent[:-1], ent[1:]):
+                if e1 == e0:
+                    continue
+                rows = self.tile_ptr[a0:a1]
+                rows.view(-1).scatter_add_(0, (seg[e0:e1] - a0) * (G + 1) + tile[e0:e1] + 1,
+                                           torch.ones(e1 - e0, dtype=i32, device=dev))
+                rows.copy_(torch.cumsum(rows, 1, dtype=i32))
+        del tile, seg, pi
         # ---- units -------------------------------------------------------------------------------------
         self.start_unit_ptr = torch.zeros(n + 1, dtype=i32, device=dev)
         self.start_unit_ptr[1:] = torch.cumsum(n_units_x, 0).to(i32)
@@ -397,7 +467,7 @@ class XsimEngine:
         a.lp_ptr, a.leg_par_base, a.leg_npar = P(self.lp_ptr), P(self.leg_par_base), P(self.leg_npar)
         a.leg_n, a.leg_d, a.leg_c = P(self.leg_n), P(self.leg_d), P(self.leg_c)
         a.par_s, a.par_e, a.par_m, a.par_f = P(self.par_s), P(self.par_e), P(self.par_m), P(self.par_f)
-        a.rs_ptr, a.rs_end = P(p.rs_ptr), P(self.rs_end)
+        a.rs_ptr, a.rs_end = P(self.rs_ptr), P(self.rs_end)
         a.rs_n, a.rs_d, a.rs_c = [P(v) for v in self.rs_ndc]
         a.tile_ptr, a.gb = P(self.tile_ptr), self.gb
         a.cells_lg, a.top_m, a.warps = self.cells_lg, self.top_m, self.warps
