@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define XMAP_B200_ABI_VERSION 3
+#define XMAP_B200_ABI_VERSION 4
 #define XMAP_KMAX 64                 /* largest supported top-k (extend_among_topk) */
 #define XMAP_METHOD_ADJUST_COSINE 0  /* baselinerSim.py:144-174 */
 #define XMAP_METHOD_COSINE 1         /* baselinerSim.py:115-142 */
@@ -264,6 +264,7 @@ typedef struct xmap_xsim_args {
     /* optional: every (end, xsim) of unit u written at emit_ptr[u] + 0 .. unit_count[u]-1 (order unspecified) */
     const int64_t *emit_ptr; int32_t *emit_end; double *emit_xsim;
     int32_t *error_flag;                      /* 2: a pass overflowed at the finest split */
+    int32_t batch_lg;                         /* xmap_xsim_extend_ll: log2 of the paths per batch, 9 .. 11 */
 } xmap_xsim_args;
 
 int64_t xmap_xsim_smem_bytes(int32_t cells_lg, int32_t warps);
@@ -274,6 +275,13 @@ int xmap_xsim_extend(const xmap_xsim_args *args_h, void *stream);
  * gws are not used. */
 int64_t xmap_xsim_cta_smem_bytes(int32_t cells_lg);
 int xmap_xsim_extend_cta(const xmap_xsim_args *args_h, void *stream);
+/* Record-list variant (the default): one CTA of `warps` x 32 threads (warps = 8 or 16) per unit with ONE table of
+ * 2^cells_lg cells; a batch of 2^batch_lg paths is evaluated without routing -- every path pushes its record on
+ * the list of its cell (atomicExch on a per-cell head) and, after a block barrier, the thread that found the list
+ * empty adds the cell's records in ascending record (= path) order.  Same unit arrays, outputs and determinism
+ * contract; unit_counter / unit_clg / gws are not used. */
+int64_t xmap_xsim_ll_smem_bytes(int32_t cells_lg, int32_t batch_lg);
+int xmap_xsim_extend_ll(const xmap_xsim_args *args_h, void *stream);
 /* only the per-start merge (multi-GPU: after the unit results of all ranks have been summed) */
 int xmap_xsim_merge(const xmap_xsim_args *args_h, void *stream);
 

@@ -170,7 +170,8 @@ def test_recommender_pipelines_match_reference(name):
     iids, uids = [str(s) for s in g0["iids"]], [str(s) for s in g0["uids"]]
     profile = LocalRDD([(uids[u], iids[i], float(r), datetime.utcfromtimestamp(int(t)))
                         for u, i, r, t in zip(g["ae_user"], g["ae_item"], g["ae_rating"], g["ae_ts"])])
-    sim_tool = RecommenderSim("cosine_item", int(g["num_atleast"]))
+    # "adjust_cosine_item" runs the cosine_item branch in the reference (substring dispatch, recommenderSim.py:188)
+    sim_tool = RecommenderSim("adjust_cosine_item" if name == "adj_all_bridge" else "cosine_item", int(g["num_atleast"]))
     out = recommender_calculate_sim_pipeline(None, sim_tool, profile)
     item_info = out[5].value
     assert len(out) == 7 and set(item_info) == {iids[i] for i in np.unique(g["ae_item"])}

@@ -29,6 +29,14 @@ def _worker(rank, world, port, q):
     flags[sh.lo:sh.hi] = (torch.arange(sh.lo, sh.hi) % 3 == 0).to(torch.uint8)
     allgather_rows(flags, sh)
     ok = bool(torch.equal(mine, full)) and bool(torch.equal(flags, (torch.arange(1001) % 3 == 0).to(torch.uint8)))
+    # several tensors of different dtypes / row widths packed into ONE all-gather
+    fulls = [torch.arange(1001, dtype=torch.int64) * 7, torch.arange(1001 * 4, dtype=torch.int32).reshape(1001, 2, 2),
+             torch.arange(1001 * 2, dtype=torch.float64).reshape(1001, 2) / 3.0, (torch.arange(1001) % 5).to(torch.uint8)]
+    parts = []
+    for f in fulls:
+        m = torch.zeros_like(f); m[sh.lo:sh.hi] = f[sh.lo:sh.hi]; parts.append(m)
+    allgather_rows(parts, sh)
+    ok = ok and all(bool(torch.equal(a, b)) for a, b in zip(parts, fulls))
     loads = [float(work[sh.bounds[r]:sh.bounds[r + 1]].sum()) for r in range(world)]
     q.put((rank, ok, loads))
     dist.destroy_process_group()

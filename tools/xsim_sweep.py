@@ -1,7 +1,7 @@
 """X-SIM variants on ONE bench workload (built once): engine build and kernel time per configuration, path counts
 against the plan's exact bound, distinct ends and top-m rows against the first configuration.
 
-usage: xsim_sweep.py <workload> "<mode> <fuse> <cells_lg> <unit_lg> [rho] [load]" ..."""
+usage: xsim_sweep.py <workload> "<mode> <fuse> <cells_lg> <unit_lg> [rho] [load] [ll_warps] [batch_lg]" ..."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bench
@@ -23,10 +23,15 @@ for spec in sys.argv[2:]:
     mode, fuse, clg, ulg = f[0], f[1] != "0", int(f[2]), int(f[3])
     rho = float(f[4]) if len(f) > 4 else X.XSIM_RHO
     load = float(f[5]) if len(f) > 5 else X.XSIM_LOAD
+    kw = {}
+    if len(f) > 6:
+        kw["ll_warps"] = int(f[6])
+    if len(f) > 7:
+        kw["batch_lg"] = int(f[7])
     best = None
     for rep in range(2):
         torch.cuda.synchronize(); t1 = time.perf_counter()
-        xe = X.XsimEngine(plan, 10, cells_lg=clg, unit_work=1 << ulg, rho=rho, load=load, mode=mode, fuse=fuse)
+        xe = X.XsimEngine(plan, 10, cells_lg=clg, unit_work=1 << ulg, rho=rho, load=load, mode=mode, fuse=fuse, **kw)
         torch.cuda.synchronize(); t2 = time.perf_counter()
         res = xe.run()
         torch.cuda.synchronize(); t3 = time.perf_counter()

@@ -2,8 +2,9 @@
 (xmap/core/recommenderSim.py:9-195, recommenderPrivacy.py:9-189, recommenderPrediction.py:6-139).
 
 Offered: item-based `cosine_item` similarity with local sensitivity, NON-private neighbour selection, item-based
-prediction with and without temporal decay, MAE.  Not offered (ValueError): `adjust_cosine_item`, the user-based
-variants (absent from the reference's own source tree) and the private neighbour selection
+prediction with and without temporal decay, MAE.  `adjust_cosine_item` is accepted and, as in the reference (whose
+dispatch tests the substring "cosine_item" first, recommenderSim.py:188), runs the same cosine_item path.  Not offered
+(ValueError): the user-based variants (absent from the reference's own source tree) and the private neighbour selection
 (recommenderPrivacy.py:70-139: unseeded np.random draws).  The work happens in csrc/recsim.cu; these classes
 encode the flat (uid, iid, rating, time) records once and keep the device state on the objects they return.
 """
@@ -59,9 +60,12 @@ class RecommenderSim(object):
         return out
 
     def calculate_sim(self, state):
-        """((iid1, iid2), [sim, local sensitivity])* -- recommenderSim.py:186-195 with method cosine_item."""
-        if "cosine_item" not in self.method or "adjust" in self.method:
-            raise ValueError("only the item-based 'cosine_item' similarity is offered (got %r)" % (self.method,))
+        """((iid1, iid2), [sim, local sensitivity])* -- recommenderSim.py:186-195.  The reference dispatches on
+        `"cosine_item" in self.method` FIRST (:188), and "adjust_cosine_item" contains that substring, so both method
+        names run cosine_sim there (adjusted_cosine_sim, :135-184, is unreachable); both are accepted here and mean
+        the same.  Anything else (the user-based names) returns None in the reference and raises here."""
+        if "cosine_item" not in self.method:
+            raise ValueError("only the item-based similarities are offered (got %r)" % (self.method,))
         if state.sim is None:
             state.sim = RS.cosine_item(state.user, state.item, state.rating, len(state.iids), self.num_atleast)
 

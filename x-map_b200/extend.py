@@ -241,8 +241,12 @@ XSIM_MAX_PASSES = int(os.environ.get("XMAP_XSIM_MAX_PASSES", "1000000000"))   # 
                                 # global memory (L2).  Measured at cfg2: 32 passes + L2 tables 968 ms, shared memory only
                                 # (no cap) 732 ms -- dependent read-modify-writes at L2 latency lose to narrow passes
 XSIM_GCELLS_LG = 16             # largest global-memory table of a unit (cells)
-XSIM_MODE = os.environ.get("XMAP_XSIM_MODE", "cta")                # "warp": one warp per unit (xsim.cu); "cta": one CTA per
-                                                                   # unit with one 8x larger table (xsim_cta.cu)
+XSIM_MODE = os.environ.get("XMAP_XSIM_MODE", "warp")                # "ll": one CTA per unit, record lists (xsim_ll.cu, default);
+                                                                   # "cta": one CTA per unit, products routed to owner warps
+                                                                   # (xsim_cta.cu); "warp": one warp per unit (xsim.cu)
+XSIM_LL_CELLS_LG = int(os.environ.get("XMAP_XSIM_LL_CELLS_LG", "12"))
+XSIM_LL_WARPS = int(os.environ.get("XMAP_XSIM_LL_WARPS", "16"))
+XSIM_LL_BATCH_LG = int(os.environ.get("XMAP_XSIM_LL_BATCH_LG", "11"))
 XSIM_FUSE = os.environ.get("XMAP_XSIM_FUSE", "1") != "0"          # fused bridge lists B(t) for the joint-only legs
 XSIM_FUSE_MAX = 1 << 31         # entries (28 B each + sort scratch) above which the lists are not fused: a fixed number, not a
                                 # function of free memory, so that every rank takes the same decision
@@ -273,26 +277,32 @@ class XsimEngine:
 
     def __init__(self, plan, top_m=10, cells_lg=None, rho=XSIM_RHO, unit_work=None,
                  load=XSIM_LOAD, warps=XSIM_WARPS, max_passes=XSIM_MAX_PASSES, mode=XSIM_MODE, fuse=None,
-                 fuse_max_entries=XSIM_FUSE_MAX):
-        if mode not in ("warp", "cta"):
-            raise ValueError("mode must be 'warp' or 'cta'")
+                 fuse_max_entries=XSIM_FUSE_MAX, ll_warps=None, batch_lg=None):
+        if mode not in ("warp", "cta", "ll"):
+            raise ValueError("mode must be 'warp', 'cta' or 'll'")
         self.mode = mode
         if fuse is None:
             fuse = XSIM_FUSE
         if cells_lg is None:
-            cells_lg = XSIM_CTA_CELLS_LG if mode == "cta" else XSIM_CELLS_LG
+            cells_lg = {"cta": XSIM_CTA_CELLS_LG, "ll": XSIM_LL_CELLS_LG, "warp": XSIM_CELLS_LG}[mode]
         if unit_work is None:
-            unit_work = (1 << XSIM_CTA_UNIT_LG) if mode == "cta" else XSIM_UNIT_WORK
-        if mode == "cta":
+            unit_work = XSIM_UNIT_WORK if mode == "warp" else (1 << XSIM_CTA_UNIT_LG)
+        if mode != "warp":
             max_passes = 10 ** 9                 # shared memory only
             if cells_lg < 9:
-                raise ValueError("cta mode needs cells_lg >= 9")
+                raise ValueError("cta / ll modes need cells_lg >= 9")
+        self.batch_lg = 0
+        if mode == "ll":
+            warps = XSIM_LL_WARPS if ll_warps is None else int(ll_warps)
+            self.batch_lg = XSIM_LL_BATCH_LG if batch_lg is None else int(batch_lg)
+            if N.lib().xmap_xsim_ll_smem_bytes(int(cells_lg), self.batch_lg) > 227 * 1024:
+                raise ValueError("ll mode: table (24 B x 2^cells_lg) + batch (18 B x 2^batch_lg) exceed shared memory")
         if not (1 <= top_m <= N.KMAX):
             raise ValueError("top_m must be in [1, %d]" % N.KMAX)
         if not (6 <= cells_lg <= N.XSIM_MAX_CELLS_LG):
             raise ValueError("cells_lg must be in [6, %d]" % N.XSIM_MAX_CELLS_LG)
         warps = int(warps)
-        while warps > 1 and N.lib().xmap_xsim_smem_bytes(int(cells_lg), warps) > 227 * 1024:
+        while mode == "warp" and warps > 1 and N.lib().xmap_xsim_smem_bytes(int(cells_lg), warps) > 227 * 1024:
             warps -= 1
         self.plan, self.top_m, self.cells_lg, self.warps = plan, int(top_m), int(cells_lg), warps
         self.unit_counter = torch.zeros(1, dtype=torch.int32, device=plan.start_item.device)
@@ -383,8 +393,9 @@ class XsimEngine:
                 leg_npar = torch.where(jl, torch.ones_like(leg_npar), leg_npar)
                 n_s += n_t
                 self.fused_entries = F
-        if n_s and int(rl.max()) >= (1 << 26):
-            raise N.NativeError("a right-segment list has >= 2^26 entries: the per-batch product counter is 32-bit")
+        if n_s and int(rl.max()) >= (1 << (26 if mode == "warp" else 23)):
+            raise N.NativeError("a right-segment list is too long for the 32-bit product counter of a macro-batch "
+                                "(2^26 entries, warp mode; 2^23, cta / ll modes)")
         self.rs_ptr, self.rs_end, self.rs_ndc = rs_ptr.contiguous(), rs_end.contiguous(), tuple(v.contiguous() for v in rs_ndc)
         self.leg_npar = leg_npar.to(i32).contiguous()
         self.leg_par_base = leg_par_base.contiguous()
@@ -470,11 +481,15 @@ class XsimEngine:
         a.rs_ptr, a.rs_end = P(self.rs_ptr), P(self.rs_end)
         a.rs_n, a.rs_d, a.rs_c = [P(v) for v in self.rs_ndc]
         a.tile_ptr, a.gb = P(self.tile_ptr), self.gb
-        a.cells_lg, a.top_m, a.warps = self.cells_lg, self.top_m, self.warps
+        a.cells_lg, a.top_m, a.warps, a.batch_lg = self.cells_lg, self.top_m, self.warps, self.batch_lg
         a.unit_counter = N.ptr(self.unit_counter)
         a.unit_clg, a.gws, a.gcells_lg = P(self.unit_clg), N.ptr(self.gws), self.gcells_lg
         a.error_flag = N.ptr(self.error_flag)
         return a
+
+    def _entry(self):
+        L = N.lib()
+        return {"ll": L.xmap_xsim_extend_ll, "cta": L.xmap_xsim_extend_cta, "warp": L.xmap_xsim_extend}[self.mode]
 
     def _check(self):
         e = int(self.error_flag.item())
@@ -504,7 +519,7 @@ class XsimEngine:
         a.unit_order, a.n_units = N.ptr(order), int(order.numel())
         a.merge = 1 if world == 1 else 0
         st = torch.cuda.current_stream().cuda_stream
-        run_units = L.xmap_xsim_extend_cta if self.mode == "cta" else L.xmap_xsim_extend
+        run_units = self._entry()
         if n and nu:
             N.check(run_units(a, st), "xmap_xsim_extend")
             self.launches += 1 + a.merge
@@ -536,8 +551,7 @@ class XsimEngine:
             a.unit_count, a.unit_combos, a.unit_top_end, a.unit_top_xsim, a.unit_top_len = [N.ptr(t) for t in scratch]
             a.unit_order, a.n_units, a.merge = N.ptr(self.unit_order), nu, 0
             a.emit_ptr, a.emit_end, a.emit_xsim = N.ptr(ptr), N.ptr(e_end), N.ptr(e_x)
-            run_units = L.xmap_xsim_extend_cta if self.mode == "cta" else L.xmap_xsim_extend
-            N.check(run_units(a, torch.cuda.current_stream().cuda_stream), "xmap_xsim_extend(emit)")
+            N.check(self._entry()(a, torch.cuda.current_stream().cuda_stream), "xmap_xsim_extend(emit)")
             self.launches += 1
             self._check()
             if not torch.equal(scratch[0], res.unit_count):

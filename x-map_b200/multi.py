@@ -58,21 +58,36 @@ class RowShard(object):
 
 
 def allgather_rows(t, shard, group=None):
-    """t: tensor whose dim 0 is the item axis, valid on [shard.lo, shard.hi).
-    After the call every rank holds every row.  Blocks are padded to the largest
-    block so a single equal-size all-gather moves them."""
-    if shard.world == 1:
+    """t: tensor (or list of tensors) whose dim 0 is the item axis, valid on [shard.lo, shard.hi).
+    After the call every rank holds every row.  The rows of all the tensors are packed side by side into
+    one byte matrix, padded to the largest block, so that ONE equal-size all-gather moves everything."""
+    ts = list(t) if isinstance(t, (list, tuple)) else [t]
+    if shard.world == 1 or not ts:
         return t
-    tail = t.shape[1:]
-    send = torch.zeros((shard.max_rows,) + tuple(tail), dtype=t.dtype, device=t.device)
-    send[: shard.hi - shard.lo] = t[shard.lo:shard.hi]
-    recv = torch.empty((shard.world * shard.max_rows,) + tuple(tail), dtype=t.dtype, device=t.device)
+    dev = ts[0].device
+    own = shard.hi - shard.lo
+    flat = [x[shard.lo:shard.hi].contiguous().view(own, -1).view(torch.uint8) if own else
+            x.new_zeros((0, 1)).view(torch.uint8).view(0, -1) for x in ts]
+    width = [int(x[:1].numel()) * x.element_size() for x in ts]       # bytes per row of every tensor
+    W = sum(width)
+    send = torch.zeros((shard.max_rows, W), dtype=torch.uint8, device=dev)
+    if own:
+        col = 0
+        for f, w in zip(flat, width):
+            send[:own, col:col + w] = f.view(own, w)
+            col += w
+    recv = torch.empty((shard.world * shard.max_rows, W), dtype=torch.uint8, device=dev)
     dist.all_gather_into_tensor(recv, send, group=group)
-    recv = recv.view((shard.world, shard.max_rows) + tuple(tail))
+    recv = recv.view(shard.world, shard.max_rows, W)
     for r in range(shard.world):
         lo, hi = shard.bounds[r], shard.bounds[r + 1]
-        if r != shard.rank and hi > lo:
-            t[lo:hi] = recv[r, : hi - lo]
+        if r == shard.rank or hi <= lo:
+            continue
+        col = 0
+        for x, w in zip(ts, width):
+            blk = recv[r, : hi - lo, col:col + w].contiguous().view(x.dtype)
+            x[lo:hi] = blk.view((hi - lo,) + tuple(x.shape[1:]))
+            col += w
     return t
 
 
@@ -230,9 +245,8 @@ def similarity_step(engine, shard, group=None):
     nkept = None
     if shard.world > 1:
         nkept = engine.rec_cnt.clone()          # the lists stay sharded: only the lengths are gathered
-        for t in (engine.row_npairs, nkept, engine.tab_len, engine.tab_idx, engine.tab_sim,
-                  engine.tab_mutu, engine.tab_n):
-            allgather_rows(t, shard, group)
+        allgather_rows([engine.row_npairs, nkept, engine.tab_len, engine.tab_idx, engine.tab_sim,
+                        engine.tab_mutu, engine.tab_n], shard, group)
     return engine.tables(dict(accumulate=stats, rows=(shard.lo, shard.hi)), row_nkept=nkept)
 
 
