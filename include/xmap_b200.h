@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define XMAP_B200_ABI_VERSION 4
+#define XMAP_B200_ABI_VERSION 5
 #define XMAP_KMAX 64                 /* largest supported top-k (extend_among_topk) */
 #define XMAP_METHOD_ADJUST_COSINE 0  /* baselinerSim.py:144-174 */
 #define XMAP_METHOD_COSINE 1         /* baselinerSim.py:115-142 */
@@ -239,12 +239,12 @@ typedef struct xmap_xsim_args {
     const int32_t *unit_g0, *unit_g1;         /* the unit's range of hash tiles, 0 <= g0 < g1 <= 2^gb ... */
     const int32_t *unit_npass;                /* ... which it covers in npass equal passes (<= g1 - g0) */
     const int32_t *start_unit_ptr;            /* [n_starts + 1] unit id range of every start (merge) */
-    /* legs: left segment folded to (N, D, C); partners [par_base, par_base + npar); lp_ptr = exclusive
-     * scan of npar over ALL legs (lp_ptr[n_legs] = number of (leg, partner) pairs) */
-    const int64_t *lp_ptr; const int64_t *leg_par_base; const int32_t *leg_npar;
-    const double *leg_n, *leg_d, *leg_c;
-    const int32_t *par_s;                     /* index into rseg lists */
-    const double *par_e, *par_m, *par_f;      /* the bridge edge: sim*mutu, mutu, frac */
+    /* (leg, partner) pairs in (start, leg, partner) order: lp_ptr = exclusive scan of the partners per leg over ALL
+     * legs (lp_ptr[n_legs] = number of pairs; the kernels read it only at the unit's leg range); per pair the list it
+     * walks and the left segment + bridge edge folded in path order: N = sum sim*mutu, D = sum mutu, C = prod frac */
+    const int64_t *lp_ptr;
+    const int32_t *pd_s;                      /* index into the right-segment / fused lists */
+    const double *pd_n, *pd_d, *pd_c;
     const int64_t *rs_ptr;                    /* [n_s + 1] */
     const int32_t *rs_end;                    /* per right segment: end item, sorted by pi within a list */
     const double *rs_n, *rs_d, *rs_c;         /* sum sim*mutu, sum mutu, prod frac of its edges */
@@ -264,7 +264,6 @@ typedef struct xmap_xsim_args {
     /* optional: every (end, xsim) of unit u written at emit_ptr[u] + 0 .. unit_count[u]-1 (order unspecified) */
     const int64_t *emit_ptr; int32_t *emit_end; double *emit_xsim;
     int32_t *error_flag;                      /* 2: a pass overflowed at the finest split */
-    int32_t batch_lg;                         /* xmap_xsim_extend_ll: log2 of the paths per batch, 9 .. 11 */
 } xmap_xsim_args;
 
 int64_t xmap_xsim_smem_bytes(int32_t cells_lg, int32_t warps);
@@ -275,13 +274,6 @@ int xmap_xsim_extend(const xmap_xsim_args *args_h, void *stream);
  * gws are not used. */
 int64_t xmap_xsim_cta_smem_bytes(int32_t cells_lg);
 int xmap_xsim_extend_cta(const xmap_xsim_args *args_h, void *stream);
-/* Record-list variant (the default): one CTA of `warps` x 32 threads (warps = 8 or 16) per unit with ONE table of
- * 2^cells_lg cells; a batch of 2^batch_lg paths is evaluated without routing -- every path pushes its record on
- * the list of its cell (atomicExch on a per-cell head) and, after a block barrier, the thread that found the list
- * empty adds the cell's records in ascending record (= path) order.  Same unit arrays, outputs and determinism
- * contract; unit_counter / unit_clg / gws are not used. */
-int64_t xmap_xsim_ll_smem_bytes(int32_t cells_lg, int32_t batch_lg);
-int xmap_xsim_extend_ll(const xmap_xsim_args *args_h, void *stream);
 /* only the per-start merge (multi-GPU: after the unit results of all ranks have been summed) */
 int xmap_xsim_merge(const xmap_xsim_args *args_h, void *stream);
 

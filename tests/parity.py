@@ -249,7 +249,7 @@ def run_smoke():
     # the rest of the path on the same case: X-SIM extension (both kernels) and the argmax mapping vs the oracle
     from oracle import restate as RS
     X = RS.xsim_extend(out["P"], out["knn"], case["n_items"], case["meta"]["has_S"], case["meta"]["has_T"])
-    for mode in ("ll", "cta", "warp"):
+    for mode in ("warp", "cta"):
         plan, xe, res, (s, e, v) = run_gpu_extend(out["tabs"], out["lay"], case["meta"], mode=mode)
         rel = compare_xsim(s, e, v, X["start"], X["end"], X["xsim"])
         assert int(res.combos.sum()) == X["combos"]
@@ -330,9 +330,17 @@ def eval_engine_numpy(xe, g_ranges=None):
     g = lambda t: t.cpu().numpy()
     p = xe.plan
     leg_ptr, start_item = g(p.leg_ptr), g(p.start_item)
+    lp_ptr = g(xe.lp_ptr)
+    pd_s, pd_n, pd_d, pd_c = g(xe.pd_s), g(xe.pd_n), g(xe.pd_d), g(xe.pd_c)
+    # the pair descriptors restate (leg, partner): list of the partner, leg and bridge edge folded in path order
     lp_base, lp_n = g(xe.leg_par_base), g(xe.leg_npar)
     lN, lD, lC = g(xe.leg_n), g(xe.leg_d), g(xe.leg_c)
     ps, pe, pm, pf = g(xe.par_s), g(xe.par_e), g(xe.par_m), g(xe.par_f)
+    assert np.array_equal(np.diff(lp_ptr), lp_n) and len(pd_s) == lp_ptr[-1]
+    for lg in range(len(lp_n)):
+        for k in range(lp_n[lg]):
+            q, pp = lp_ptr[lg] + k, lp_base[lg] + k
+            assert pd_s[q] == ps[pp] and pd_n[q] == lN[lg] + pe[pp] and pd_d[q] == lD[lg] + pm[pp] and pd_c[q] == lC[lg] * pf[pp]
     rs_ptr, rs_end = g(xe.rs_ptr), g(xe.rs_end)
     rN, rD, rC = (g(v) for v in xe.rs_ndc)
     tp = g(xe.tile_ptr)
@@ -350,10 +358,10 @@ def eval_engine_numpy(xe, g_ranges=None):
     for x in range(len(start_item)):
         acc = {}
         for g0, g1 in g_ranges:
-            for lg in range(leg_ptr[x], leg_ptr[x + 1]):
-                for pp in range(lp_base[lg], lp_base[lg] + lp_n[lg]):
-                    s_ = ps[pp]
-                    Nm = lN[lg] + pe[pp]; Dm = lD[lg] + pm[pp]; Cm = lC[lg] * pf[pp]
+            for q in range(lp_ptr[leg_ptr[x]], lp_ptr[leg_ptr[x + 1]]):
+                if True:
+                    s_ = pd_s[q]
+                    Nm, Dm, Cm = pd_n[q], pd_d[q], pd_c[q]
                     a, b = rs_ptr[s_] + tp[s_, g0], rs_ptr[s_] + tp[s_, g1]
                     Nn = Nm + rN[a:b]; Dd = Dm + rD[a:b]; cp = Cm * rC[a:b]
                     with np.errstate(invalid="ignore", divide="ignore"):

@@ -55,16 +55,17 @@ def test_generation_matches_reference_golden(name):
 
 
 def test_xsim_vs_restatement_and_pass_splits():
-    """A larger case against oracle/restate.py in every kernel variant.  Warp kernel: tiny tables, tiny units and a
-    wildly optimistic pass estimate (device-side splits) must not change a single bit -- every (start, end) sum is
-    formed in path order.  CTA kernels (record lists = the default, routed): same keys, counts and path counts, sums in
-    another association (<= 1e-10 relative), identical from run to run."""
+    """A larger case against oracle/restate.py in both kernels and many pass plans: tiny tables, tiny units, a wildly
+    optimistic pass estimate (device-side splits), tables in global memory, with and without the fused bridge lists.
+    Every plan gives the same keys, distinct-end counts and path counts; the sums are formed in an order that depends
+    on the plan (runs of equal ends inside a 32-path chunk are summed by a shuffle tree), so values agree to <= 1e-10
+    relative between plans -- and bit for bit from run to run of the same plan."""
     from oracle import restate as RS
     case = PT.synth_case(4000, 900, 60000, 0.04, seed=21)
     out = PT.check_sim_against_restatement(case, "adjust_cosine", 50, 5)
     X = RS.xsim_extend(out["P"], out["knn"], case["n_items"], case["meta"]["has_S"], case["meta"]["has_T"])
-    plan, xe, res, (s, e, v) = PT.run_gpu_extend(out["tabs"], out["lay"], case["meta"])          # default: ll, fused lists
-    assert xe.fused_entries > 0
+    plan, xe, res, (s, e, v) = PT.run_gpu_extend(out["tabs"], out["lay"], case["meta"])          # default: warp kernel, fused lists
+    assert xe.mode == "warp" and xe.fused_entries > 0
     assert plan.n_src == X["n_src"] and plan.n_joint == X["n_joint"]
     PT.compare_xsim(s, e, v, X["start"], X["end"], X["xsim"])
     assert int(res.combos.sum()) == X["combos"]
@@ -78,12 +79,7 @@ def test_xsim_vs_restatement_and_pass_splits():
                     both=dict(W, cells_lg=7, unit_work=300, rho=3.0, warps=5),
                     cta=dict(mode="cta"), cta_small=dict(mode="cta", cells_lg=9, unit_work=400),
                     cta_splits=dict(mode="cta", cells_lg=9, rho=1e9),
-                    ll_small=dict(mode="ll", cells_lg=9, unit_work=400, batch_lg=9, ll_warps=8),
-                    ll_splits=dict(mode="ll", cells_lg=9, rho=1e9, batch_lg=10),
-                    ll_big_batch=dict(mode="ll", cells_lg=11, batch_lg=11, ll_warps=8),
-                    ll_one_per_thread=dict(mode="ll", cells_lg=10, batch_lg=9, ll_warps=16),
-                    ll_unfused=dict(mode="ll", fuse=False), warp_unfused=dict(W, fuse=False))
-    warp_base = None
+                    cta_unfused=dict(mode="cta", fuse=False), warp_unfused=dict(W, fuse=False))
     for name, kw in variants.items():
         plan2, xe2, res2, (s2, e2, v2) = PT.run_gpu_extend(out["tabs"], out["lay"], case["meta"], **kw)
         if name == "small_tables":
@@ -95,22 +91,14 @@ def test_xsim_vs_restatement_and_pass_splits():
         if name.endswith("unfused"):
             assert xe2.fused_entries == 0
         assert np.array_equal(s, s2) and np.array_equal(e, e2), name
-        np.testing.assert_allclose(v2, v, rtol=1e-10, atol=0, err_msg=name)      # observed: 1 of 426 625 at 1.4e-12 (a cancelling sum)
+        np.testing.assert_allclose(v2, v, rtol=1e-10, atol=0, err_msg=name)      # observed: <= 1.4e-12 (a cancelling sum)
         for f in ("count", "combos", "top_len"):
             assert np.array_equal(getattr(res, f).cpu().numpy(), getattr(res2, f).cpu().numpy()), (name, f)
-        if kw["mode"] != "warp":
-            _, _, res3, (s3, e3, v3) = PT.run_gpu_extend(out["tabs"], out["lay"], case["meta"], **kw)
-            assert np.array_equal(v2, v3) and np.array_equal(res2.top_end.cpu().numpy(), res3.top_end.cpu().numpy()), name
-            assert np.array_equal(res2.top_xsim.cpu().numpy(), res3.top_xsim.cpu().numpy()), name
-            continue
-        if name == "warp_unfused":
-            continue
-        if warp_base is None:
-            warp_base = (v2, res2)
-            continue
-        assert np.array_equal(warp_base[0], v2), name                        # bit-identical for any pass plan
-        for f in ("count", "combos", "top_end", "top_xsim", "top_len"):
-            assert np.array_equal(getattr(warp_base[1], f).cpu().numpy(), getattr(res2, f).cpu().numpy()), (name, f)
+        if name == "warp":
+            assert np.array_equal(v, v2)                                         # the default plan again: bit-identical
+        _, _, res3, (s3, e3, v3) = PT.run_gpu_extend(out["tabs"], out["lay"], case["meta"], **kw)
+        assert np.array_equal(v2, v3) and np.array_equal(res2.top_end.cpu().numpy(), res3.top_end.cpu().numpy()), name
+        assert np.array_equal(res2.top_xsim.cpu().numpy(), res3.top_xsim.cpu().numpy()), name
     # top-m rows = first m of the full rows ordered by |xsim| desc, ties to smaller end
     rows, cands = RS.candidates(X["start"], X["end"], X["xsim"], 10)
     te, tl = res.top_end.cpu().numpy(), res.top_len.cpu().numpy()

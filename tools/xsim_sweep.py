@@ -1,7 +1,7 @@
 """X-SIM variants on ONE bench workload (built once): engine build and kernel time per configuration, path counts
 against the plan's exact bound, distinct ends and top-m rows against the first configuration.
 
-usage: xsim_sweep.py <workload> "<mode> <fuse> <cells_lg> <unit_lg> [rho] [load] [ll_warps] [batch_lg]" ..."""
+usage: xsim_sweep.py <workload> "<mode> <fuse> <cells_lg> <unit_lg> [rho] [load] [warps]" ..."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bench
@@ -25,9 +25,7 @@ for spec in sys.argv[2:]:
     load = float(f[5]) if len(f) > 5 else X.XSIM_LOAD
     kw = {}
     if len(f) > 6:
-        kw["ll_warps"] = int(f[6])
-    if len(f) > 7:
-        kw["batch_lg"] = int(f[7])
+        kw["warps"] = int(f[6])
     best = None
     for rep in range(2):
         torch.cuda.synchronize(); t1 = time.perf_counter()

@@ -14,7 +14,7 @@ KMAX = 64
 XSIM_MAX_CELLS_LG = 13    # XMAP_XSIM_MAX_CELLS_LG
 METHODS = {"adjust_cosine": 0, "cosine": 1}
 SELECT_LONG = 8192            # XMAP_SELECT_LONG
-ABI_VERSION = 4
+ABI_VERSION = 5
 ROW_HDR_BYTES = 48          # XMAP_SIM_ROW_HDR_BYTES
 
 _p = C.c_void_p
@@ -29,7 +29,7 @@ class SimArgs(C.Structure):
         ("k", C.c_int32), ("r2_bits", C.c_int32), ("count_only", C.c_int32),
         ("rec_ptr", _p), ("rec_cnt", _p), ("rec", _p), ("rec_n", _p), ("bb", _p), ("row_npairs", _p),
         ("tab_idx", _p), ("tab_sim", _p), ("tab_mutu", _p), ("tab_n", _p), ("tab_len", _p),
-        ("error_flag", _p), ("batch_lg", C.c_int32),
+        ("error_flag", _p),
     ]
 
 
@@ -38,8 +38,7 @@ class XsimArgs(C.Structure):
         ("n_starts", C.c_int32), ("n_units", C.c_int32),
         ("unit_order", _p), ("unit_counter", _p), ("warps", C.c_int32), ("unit_leg_lo", _p), ("unit_leg_hi", _p),
         ("unit_g0", _p), ("unit_g1", _p), ("unit_npass", _p), ("start_unit_ptr", _p),
-        ("lp_ptr", _p), ("leg_par_base", _p), ("leg_npar", _p), ("leg_n", _p), ("leg_d", _p), ("leg_c", _p),
-        ("par_s", _p), ("par_e", _p), ("par_m", _p), ("par_f", _p),
+        ("lp_ptr", _p), ("pd_s", _p), ("pd_n", _p), ("pd_d", _p), ("pd_c", _p),
         ("rs_ptr", _p), ("rs_end", _p), ("rs_n", _p), ("rs_d", _p), ("rs_c", _p),
         ("tile_ptr", _p), ("gb", C.c_int32),
         ("cells_lg", C.c_int32), ("unit_clg", _p), ("gws", _p), ("gcells_lg", C.c_int32),
@@ -47,7 +46,7 @@ class XsimArgs(C.Structure):
         ("unit_count", _p), ("unit_combos", _p), ("unit_top_end", _p), ("unit_top_xsim", _p), ("unit_top_len", _p),
         ("out_count", _p), ("out_combos", _p), ("top_end", _p), ("top_xsim", _p), ("top_len", _p),
         ("emit_ptr", _p), ("emit_end", _p), ("emit_xsim", _p),
-        ("error_flag", _p), ("batch_lg", C.c_int32),
+        ("error_flag", _p),
     ]
 
 
@@ -73,8 +72,6 @@ _SIGS = {
     "xmap_xsim_merge": (C.c_int, [C.POINTER(XsimArgs), _p]),
     "xmap_xsim_cta_smem_bytes": (C.c_int64, [C.c_int32]),
     "xmap_xsim_extend_cta": (C.c_int, [C.POINTER(XsimArgs), _p]),
-    "xmap_xsim_ll_smem_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
-    "xmap_xsim_extend_ll": (C.c_int, [C.POINTER(XsimArgs), _p]),
     "xmap_recsim_item_info": (C.c_int, [_p, _p, C.c_int32, _p, _p]),
     "xmap_recsim_fill_entries": (C.c_int, [_p, _p, C.c_int32, _p, C.c_int64, C.c_int64, _p, _p, _p]),
     "xmap_recsim_pairs": (C.c_int, [_p, _p, _p, _p, _p, C.c_int64, C.c_int64, C.c_int32, _p, _p, _p, _p, _p, _p]),

@@ -9,15 +9,17 @@
 // memory; a pass covers a range of the hashed end axis pi(y) = y * 0x9E3779B1 (every right-segment list
 // is stored sorted by pi, and a per-source pointer table gives the sub-range of a pass without a search),
 // chosen so that the distinct ends of the pass fit the table.  Inside a pass the warp walks the
-// (leg, partner) pairs of its start 32 at a time: each lane resolves one pair to a descriptor
-// {right-segment sub-range, folded (N, D, C) of leg + bridge edge}, a shuffle scan numbers the products
+// (leg, partner) pairs of its start 32 at a time: each lane loads one pair descriptor {list, folded (N, D, C)
+// of leg + bridge edge} and resolves the list's sub-range of the pass, a shuffle scan numbers the products
 // of the batch and they are dealt to the lanes in chunks of 32 whatever the sub-range lengths.  A lane
 // loads one 28-byte right segment (the next chunk's loads are issued before the current chunk is
-// processed), evaluates the path, lanes that hit the same end are grouped (MATCH.ANY) and the group's
-// lowest lane adds the terms one by one in lane (= path) order to the cell: plain shared-memory loads
-// and stores, no atomics on values, no block barrier.  The summation order of a (start, end) cell is a
-// function of the path structure and the pass plan only, so results are bit-identical from run to run
-// and for any number of GPUs (every rank builds the same plan).
+// processed) and evaluates the path.  Lanes that hit the same end: adjacent ones (the lists are ordered
+// by pi(end), so a run of equal ends is the rule in a fused list) are summed by a segmented shuffle scan,
+// the heads of the runs are grouped (MATCH.ANY) and the group's lowest lane adds the run totals in lane
+// (= path) order to the cell: plain shared-memory loads and stores, no atomics on values, no block
+// barrier.  The summation order of a (start, end) cell is a function of the path structure and the pass
+// plan only, so results are bit-identical from run to run and for any number of GPUs (every rank builds
+// the same plan).
 //
 // A pass whose table overflows is split in two on the device (the tile range halves) and redone; the top-m
 // of a unit is kept in shared memory across its passes and a small kernel merges the units of a start.
@@ -82,6 +84,32 @@ __device__ __forceinline__ Fetched fetch_chunk(const xmap_xsim_args &a, int c, i
     return f;
 }
 
+struct PairDesc {
+    double N, D, C;
+    long long base;
+    int len;
+};
+
+// pair q of the unit: its descriptor {list, folded (N, D, C)} (one coalesced load per lane) and the sub-range of the
+// list that falls into the pass (empty beyond q_hi)
+__device__ __forceinline__ PairDesc load_pair(const xmap_xsim_args &a, long long q, long long q_hi, bool whole,
+                                              int g0, int g1, int G1) {
+    PairDesc d;
+    d.N = d.D = d.C = 0.0; d.base = 0; d.len = 0;
+    if (q < q_hi) {
+        const int s = __ldg(a.pd_s + q);
+        d.N = __ldg(a.pd_n + q); d.D = __ldg(a.pd_d + q); d.C = __ldg(a.pd_c + q);
+        const long long rb = __ldg(a.rs_ptr + s);
+        if (whole) { d.base = rb; d.len = (int)(__ldg(a.rs_ptr + s + 1) - rb); }
+        else {
+            const int32_t *tp = a.tile_ptr + (size_t)s * G1;
+            const int b0 = __ldg(tp + g0), b1 = __ldg(tp + g1);
+            d.base = rb + b0; d.len = b1 - b0;
+        }
+    }
+    return d;
+}
+
 // One warp = one unit at a time (fetched from a global counter in descending-work order); the warps of a
 // CTA are independent: no block barrier anywhere.
 __global__ void __launch_bounds__(XT_MAX, 1) xsim_warp_kernel(xmap_xsim_args a) {
@@ -133,54 +161,18 @@ __global__ void __launch_bounds__(XT_MAX, 1) xsim_warp_kernel(xmap_xsim_args a) 
             __syncwarp();
 
             // =================== accumulate ======================================================
-            long long q0 = q_lo, cur_leg = leg_lo, pass_combos = 0;
+            long long q0 = q_lo, pass_combos = 0;
             bool ovf = false;
             int n_ins = 0;                                 // occupied cells of the table
+            PairDesc nxd = load_pair(a, q0 + lane, q_hi, whole, g0, g1, G1);
             while (q0 < q_hi && !ovf) {
                 const int nq = (int)min(32ll, q_hi - q0);
-                // first pair of the 32 legs from cur_leg on, relative to q0 (every leg holds >= 1 pair, so pair
-                // q0 + i belongs to one of the legs cur_leg .. cur_leg + i)
-                int lpv = 0x3FFFFFFF;
-                if (cur_leg + lane < leg_hi) {
-                    const long long v = __ldg(a.lp_ptr + cur_leg + lane) - q0;
-                    lpv = (int)max(-(1ll << 30), min((1ll << 30), v));
-                }
-                int cntle = 0;                             // number of legs whose first pair is <= lane, 1 .. 32
-#pragma unroll
-                for (int step = 16; step >= 1; step >>= 1) {
-                    const int v = __shfl_sync(0xffffffffu, lpv, cntle + step - 1);
-                    if (v <= lane) cntle += step;
-                }
-                {   // the halving steps stop at 31: 32 single-pair legs in a row need one more probe
-                    const int v = __shfl_sync(0xffffffffu, lpv, 31);
-                    if (cntle == 31 && v <= lane) cntle = 32;
-                }
-                const int aslot = max(cntle - 1, 0);
-                const int lp_a = __shfl_sync(0xffffffffu, lpv, aslot);
-                int len = 0;
-                long long base = 0, myleg = cur_leg;
-                double dN = 0.0, dD = 0.0, dC = 0.0;
-                bool last_of_leg = false;
-                if (lane < nq) {
-                    const long long L = cur_leg + aslot;
-                    const int pidx = lane - lp_a;
-                    const long long p = __ldg(a.leg_par_base + L) + pidx;
-                    const int s = __ldg(a.par_s + p);
-                    dN = __dadd_rn(__ldg(a.leg_n + L), __ldg(a.par_e + p));      // sums in path order (extender.py:85-88)
-                    dD = __dadd_rn(__ldg(a.leg_d + L), __ldg(a.par_m + p));
-                    dC = __dmul_rn(__ldg(a.leg_c + L), __ldg(a.par_f + p));
-                    const long long rb = __ldg(a.rs_ptr + s);
-                    if (whole) { base = rb; len = (int)(__ldg(a.rs_ptr + s + 1) - rb); }
-                    else {
-                        const int32_t *tp = a.tile_ptr + (size_t)s * G1;
-                        const int b0 = __ldg(tp + g0), b1 = __ldg(tp + g1);
-                        base = rb + b0; len = b1 - b0;
-                    }
-                    myleg = L;
-                    last_of_leg = pidx + 1 == __ldg(a.leg_npar + L);
-                }
-                // the leg that holds pair q0 + nq
-                const long long nl = __shfl_sync(0xffffffffu, myleg + (last_of_leg ? 1 : 0), nq - 1);
+                const PairDesc pd = nxd;
+                q0 += nq;
+                nxd = load_pair(a, q0 + lane, q_hi, whole, g0, g1, G1);   // the next 32 pairs resolve while these are walked
+                const int len = pd.len;
+                const long long base = pd.base;
+                const double dN = pd.N, dD = pd.D, dC = pd.C;
                 int incl = len;
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) {
@@ -188,7 +180,6 @@ __global__ void __launch_bounds__(XT_MAX, 1) xsim_warp_kernel(xmap_xsim_args a) 
                     if (lane >= off) incl += t;
                 }
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
-                cur_leg = nl; q0 += nq;
                 pass_combos += total;
 
                 const int nchunk = (total + 31) >> 5;
@@ -204,12 +195,29 @@ __global__ void __launch_bounds__(XT_MAX, 1) xsim_warp_kernel(xmap_xsim_args a) 
                         const double sp = (Dd != 0.0) ? __ddiv_rn(Nn, Dd) : 0.0;      // extender.py:88-89
                         num = __dmul_rn(sp, den);
                     }
-                    W.u.acc.c_num[lane] = num; W.u.acc.c_den[lane] = den;
+                    // Lanes that hit the same end.  The lists are ordered by pi(end), so equal ends sit in ADJACENT lanes
+                    // (a fused list holds an end once per way of reaching it): a run of equal ends is summed by a
+                    // segmented suffix scan over the lanes (a fixed tree), and only the heads of the runs go on;
+                    // heads with equal ends (a chunk that spans several lists) are grouped by MATCH.ANY below.
                     const int y = cur.valid ? cur.y : (-1 - lane);
-                    const unsigned grp = __match_any_sync(0xffffffffu, y);
+                    const int y_prev = __shfl_up_sync(0xffffffffu, y, 1);
+                    const bool head = lane == 0 || y != y_prev;
+                    const unsigned heads = __ballot_sync(0xffffffffu, head);
+                    if (heads != 0xffffffffu) {
+                        const unsigned later = lane == 31 ? 0u : (heads >> (lane + 1));
+                        const int run_end = later ? lane + __ffs(later) - 1 : 31;
+#pragma unroll
+                        for (int off = 1; off < 32; off <<= 1) {
+                            const double vn = __shfl_down_sync(0xffffffffu, num, off);
+                            const double vd = __shfl_down_sync(0xffffffffu, den, off);
+                            if (lane + off <= run_end) { num = __dadd_rn(num, vn); den = __dadd_rn(den, vd); }
+                        }
+                    }
+                    W.u.acc.c_num[lane] = num; W.u.acc.c_den[lane] = den;
+                    const unsigned grp = __match_any_sync(0xffffffffu, head ? y : (-1 - lane));
                     __syncwarp();
                     bool lane_ovf = false, inserted = false;
-                    if (cur.valid && (__ffs(grp) - 1) == lane) {
+                    if (cur.valid && head && (__ffs(grp) - 1) == lane) {
                         // find-or-insert (only this warp touches the table; the CAS settles lanes racing for one empty cell)
                         const int key = y + 1;
                         int pos = (int)(((unsigned)y * XGOLD2) >> (32 - clg));
@@ -228,7 +236,7 @@ __global__ void __launch_bounds__(XT_MAX, 1) xsim_warp_kernel(xmap_xsim_args a) 
                         inserted = isnew;
                         if (slot < 0) lane_ovf = true;
                         else {
-                            // the terms of this end, one by one in lane (= path) order
+                            // the runs of this end, one by one in lane (= path) order
                             double an = 0.0, ad = 0.0;
                             if (!isnew) { const double2 v = vals[slot]; an = v.x; ad = v.y; }
                             unsigned rem = grp;

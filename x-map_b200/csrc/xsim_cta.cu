@@ -43,7 +43,6 @@ struct CShared {
     long long d_base[XMB];
     double p_num[2][XW][32], p_den[2][XW][32];   // payload slots, double-buffered; finalize scratch aliases them
     int d_cum[XMB + 4];                        // exclusive product prefix, d_cum[n_desc] = total
-    int s_lp[XMB + 4];
     int p_y[2][XW][32];
     unsigned p_mask[2][XW][XW];                // [owner][producer]
     int c_loc[XW][32];                         // consumer: payload slot (producer << 5 | lane) of the 32 items in flight
@@ -56,7 +55,6 @@ struct CShared {
     int stack_n, next_pass, cur_g0, cur_g1;
     int s_nd, s_total, s_overflow;
     int s_ins[XW];                             // occupied cells per owner region
-    long long s_nextleg;
     int s_cnt, s_nsurv, s_bstar, s_emit;
     int status;
     unsigned long long r_key[XW]; int r_tie[XW], r_pos[XW];   // block arg-best exchange (fallback path)
@@ -148,33 +146,19 @@ __global__ void __launch_bounds__(XT, 2) xsim_cta_kernel(xmap_xsim_args a) {
         const bool whole = g0 == 0 && g1 == G;
 
         // =================== accumulate ======================================================
-        long long q0 = q_lo, cur_leg = leg_lo;
+        long long q0 = q_lo;
         long long pass_combos = 0;
         while (q0 < q_hi) {
             const int nq = (int)min((long long)XMB, q_hi - q0);
-            const int nl = (int)min((long long)XMB, leg_hi - cur_leg);
-            if (tid < nl) {
-                const long long v = __ldg(a.lp_ptr + cur_leg + tid) - q0;
-                S.s_lp[tid] = (int)max(-(1ll << 30), min(1ll << 30, v));
-            }
             __syncthreads();
             if (S.s_overflow) break;                       // uniform: nobody writes the flag before the next barrier
             int len = 0;
             long long b = 0;
             double Nm = 0.0, Dm = 0.0, Cm = 0.0;
             if (tid < nq) {
-                int lo = 0, hi = nl;                       // largest leg slot with first pair <= tid
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (S.s_lp[mid] <= tid) lo = mid; else hi = mid;
-                }
-                const long long L = cur_leg + lo;
-                const int pidx = tid - S.s_lp[lo];
-                const long long p = __ldg(a.leg_par_base + L) + pidx;
-                const int s = __ldg(a.par_s + p);
-                Nm = __dadd_rn(__ldg(a.leg_n + L), __ldg(a.par_e + p));      // sums in path order (extender.py:85-88)
-                Dm = __dadd_rn(__ldg(a.leg_d + L), __ldg(a.par_m + p));
-                Cm = __dmul_rn(__ldg(a.leg_c + L), __ldg(a.par_f + p));
+                const long long q = q0 + tid;              // pair descriptors: one coalesced load each
+                const int s = __ldg(a.pd_s + q);
+                Nm = __ldg(a.pd_n + q); Dm = __ldg(a.pd_d + q); Cm = __ldg(a.pd_c + q);
                 const long long rb = __ldg(a.rs_ptr + s);
                 if (whole) { b = rb; len = (int)(__ldg(a.rs_ptr + s + 1) - rb); }
                 else {
@@ -182,7 +166,6 @@ __global__ void __launch_bounds__(XT, 2) xsim_cta_kernel(xmap_xsim_args a) {
                     const int b0 = __ldg(tp + g0), b1 = __ldg(tp + g1);
                     b = rb + b0; len = b1 - b0;
                 }
-                if (tid == nq - 1) S.s_nextleg = (pidx + 1 == __ldg(a.leg_npar + L)) ? L + 1 : L;
             }
             // block scan of (non-empty flag, len)
             const unsigned long long mine = (len > 0 ? (1ull << 40) : 0ull) | (unsigned long long)len;
@@ -211,7 +194,7 @@ __global__ void __launch_bounds__(XT, 2) xsim_cta_kernel(xmap_xsim_args a) {
             const int nd = (int)(tot >> 40), total = (int)(tot & ((1ull << 40) - 1ull));
             if (tid == 0) S.d_cum[nd] = total;
             __syncthreads();
-            cur_leg = S.s_nextleg; q0 += nq;
+            q0 += nq;
             pass_combos += total;
 
             // ---- supersteps: 16 chunks of 32 products, one per warp -------------------------------
@@ -223,22 +206,41 @@ __global__ void __launch_bounds__(XT, 2) xsim_cta_kernel(xmap_xsim_args a) {
                 const int buf = ss & 1u; ++ss;
                 // produce: evaluate, then sum the lanes of this chunk that hit the same end (lane = path order)
                 int y = -1 - lane;
+                double num = 0.0, den = 0.0;
                 if (cur.valid) {
                     const double Nn = __dadd_rn(cur.N, cur.rn);
                     const double Dd = __dadd_rn(cur.D, cur.rd);
-                    const double cp = __dmul_rn(cur.C, cur.rc);
+                    den = __dmul_rn(cur.C, cur.rc);
                     const double sp = (Dd != 0.0) ? __ddiv_rn(Nn, Dd) : 0.0;      // extender.py:88-89
-                    S.p_num[buf][warp][lane] = __dmul_rn(sp, cp);
-                    S.p_den[buf][warp][lane] = cp;
-                    S.p_y[buf][warp][lane] = cur.y;
+                    num = __dmul_rn(sp, den);
                     y = cur.y;
                 }
+                // runs of equal ends in adjacent lanes (the lists are ordered by pi(end)) are summed by a segmented
+                // suffix scan; only the heads of the runs go on
+                const int y_prev = __shfl_up_sync(0xffffffffu, y, 1);
+                const bool head = lane == 0 || y != y_prev;
+                const unsigned heads = __ballot_sync(0xffffffffu, head);
+                if (heads != 0xffffffffu) {
+                    const unsigned later = lane == 31 ? 0u : (heads >> (lane + 1));
+                    const int run_end = later ? lane + __ffs(later) - 1 : 31;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const double vn = __shfl_down_sync(0xffffffffu, num, off);
+                        const double vd = __shfl_down_sync(0xffffffffu, den, off);
+                        if (lane + off <= run_end) { num = __dadd_rn(num, vn); den = __dadd_rn(den, vd); }
+                    }
+                }
+                if (cur.valid) {
+                    S.p_num[buf][warp][lane] = num;
+                    S.p_den[buf][warp][lane] = den;
+                    S.p_y[buf][warp][lane] = cur.y;
+                }
                 if (lane < XW) S.p_mask[buf][lane][warp] = 0u;
-                const unsigned gy = __match_any_sync(0xffffffffu, y);
+                const unsigned gy = __match_any_sync(0xffffffffu, head ? y : (-1 - lane));
                 __syncwarp();
-                const bool lead = cur.valid && (__ffs(gy) - 1) == lane;
+                const bool lead = cur.valid && head && (__ffs(gy) - 1) == lane;
                 if (lead && (gy & (gy - 1u))) {
-                    double an = S.p_num[buf][warp][lane], ad = S.p_den[buf][warp][lane];
+                    double an = num, ad = den;
                     unsigned rem = gy & ~(1u << lane);
                     while (rem) {
                         const int b = __ffs(rem) - 1;

@@ -241,12 +241,8 @@ XSIM_MAX_PASSES = int(os.environ.get("XMAP_XSIM_MAX_PASSES", "1000000000"))   # 
                                 # global memory (L2).  Measured at cfg2: 32 passes + L2 tables 968 ms, shared memory only
                                 # (no cap) 732 ms -- dependent read-modify-writes at L2 latency lose to narrow passes
 XSIM_GCELLS_LG = 16             # largest global-memory table of a unit (cells)
-XSIM_MODE = os.environ.get("XMAP_XSIM_MODE", "warp")                # "ll": one CTA per unit, record lists (xsim_ll.cu, default);
-                                                                   # "cta": one CTA per unit, products routed to owner warps
-                                                                   # (xsim_cta.cu); "warp": one warp per unit (xsim.cu)
-XSIM_LL_CELLS_LG = int(os.environ.get("XMAP_XSIM_LL_CELLS_LG", "12"))
-XSIM_LL_WARPS = int(os.environ.get("XMAP_XSIM_LL_WARPS", "16"))
-XSIM_LL_BATCH_LG = int(os.environ.get("XMAP_XSIM_LL_BATCH_LG", "11"))
+XSIM_MODE = os.environ.get("XMAP_XSIM_MODE", "warp")                # "warp": one warp per unit (xsim.cu, default); "cta": one CTA
+                                                                   # per unit with one 8x larger table (xsim_cta.cu)
 XSIM_FUSE = os.environ.get("XMAP_XSIM_FUSE", "1") != "0"          # fused bridge lists B(t) for the joint-only legs
 XSIM_FUSE_MAX = 1 << 31         # entries (28 B each + sort scratch) above which the lists are not fused: a fixed number, not a
                                 # function of free memory, so that every rank takes the same decision
@@ -277,26 +273,20 @@ class XsimEngine:
 
     def __init__(self, plan, top_m=10, cells_lg=None, rho=XSIM_RHO, unit_work=None,
                  load=XSIM_LOAD, warps=XSIM_WARPS, max_passes=XSIM_MAX_PASSES, mode=XSIM_MODE, fuse=None,
-                 fuse_max_entries=XSIM_FUSE_MAX, ll_warps=None, batch_lg=None):
-        if mode not in ("warp", "cta", "ll"):
-            raise ValueError("mode must be 'warp', 'cta' or 'll'")
+                 fuse_max_entries=XSIM_FUSE_MAX):
+        if mode not in ("warp", "cta"):
+            raise ValueError("mode must be 'warp' or 'cta'")
         self.mode = mode
         if fuse is None:
             fuse = XSIM_FUSE
         if cells_lg is None:
-            cells_lg = {"cta": XSIM_CTA_CELLS_LG, "ll": XSIM_LL_CELLS_LG, "warp": XSIM_CELLS_LG}[mode]
+            cells_lg = XSIM_CTA_CELLS_LG if mode == "cta" else XSIM_CELLS_LG
         if unit_work is None:
             unit_work = XSIM_UNIT_WORK if mode == "warp" else (1 << XSIM_CTA_UNIT_LG)
         if mode != "warp":
             max_passes = 10 ** 9                 # shared memory only
             if cells_lg < 9:
-                raise ValueError("cta / ll modes need cells_lg >= 9")
-        self.batch_lg = 0
-        if mode == "ll":
-            warps = XSIM_LL_WARPS if ll_warps is None else int(ll_warps)
-            self.batch_lg = XSIM_LL_BATCH_LG if batch_lg is None else int(batch_lg)
-            if N.lib().xmap_xsim_ll_smem_bytes(int(cells_lg), self.batch_lg) > 227 * 1024:
-                raise ValueError("ll mode: table (24 B x 2^cells_lg) + batch (18 B x 2^batch_lg) exceed shared memory")
+                raise ValueError("cta mode needs cells_lg >= 9")
         if not (1 <= top_m <= N.KMAX):
             raise ValueError("top_m must be in [1, %d]" % N.KMAX)
         if not (6 <= cells_lg <= N.XSIM_MAX_CELLS_LG):
@@ -395,12 +385,21 @@ class XsimEngine:
                 self.fused_entries = F
         if n_s and int(rl.max()) >= (1 << (26 if mode == "warp" else 23)):
             raise N.NativeError("a right-segment list is too long for the 32-bit product counter of a macro-batch "
-                                "(2^26 entries, warp mode; 2^23, cta / ll modes)")
+                                "(2^26 entries, warp mode; 2^23, cta mode)")
         self.rs_ptr, self.rs_end, self.rs_ndc = rs_ptr.contiguous(), rs_end.contiguous(), tuple(v.contiguous() for v in rs_ndc)
         self.leg_npar = leg_npar.to(i32).contiguous()
         self.leg_par_base = leg_par_base.contiguous()
         self.lp_ptr = torch.zeros(lt.numel() + 1, dtype=i64, device=dev)
         self.lp_ptr[1:] = torch.cumsum(self.leg_npar.long(), 0)
+        # ---- pair descriptors: one record per (leg, partner) pair in walking order, so that the kernels resolve a
+        # pair with one coalesced load instead of a leg search and a chain of dependent gathers ------------------
+        lop = _segment_ids(self.leg_npar.long())
+        pp = self.leg_par_base[lop] + (torch.arange(lop.numel(), device=dev) - self.lp_ptr[:-1][lop])
+        self.pd_s = self.par_s[pp].contiguous()
+        self.pd_n = (self.leg_n[lop] + self.par_e[pp]).contiguous()           # sums in path order (extender.py:85-88)
+        self.pd_d = (self.leg_d[lop] + self.par_m[pp]).contiguous()
+        self.pd_c = (self.leg_c[lop] * self.par_f[pp]).contiguous()
+        del lop, pp
         # ---- passes per start: enough for the estimated distinct ends, and enough units for its paths ---
         cap = max(16.0, load * (1 << self.cells_lg))
         ub = p.ub.double()
@@ -475,13 +474,12 @@ class XsimEngine:
         a.unit_leg_lo, a.unit_leg_hi = P(self.unit_leg_lo), P(self.unit_leg_hi)
         a.unit_g0, a.unit_g1, a.unit_npass = P(self.unit_g0), P(self.unit_g1), P(self.unit_npass)
         a.start_unit_ptr = P(self.start_unit_ptr)
-        a.lp_ptr, a.leg_par_base, a.leg_npar = P(self.lp_ptr), P(self.leg_par_base), P(self.leg_npar)
-        a.leg_n, a.leg_d, a.leg_c = P(self.leg_n), P(self.leg_d), P(self.leg_c)
-        a.par_s, a.par_e, a.par_m, a.par_f = P(self.par_s), P(self.par_e), P(self.par_m), P(self.par_f)
+        a.lp_ptr = P(self.lp_ptr)
+        a.pd_s, a.pd_n, a.pd_d, a.pd_c = P(self.pd_s), P(self.pd_n), P(self.pd_d), P(self.pd_c)
         a.rs_ptr, a.rs_end = P(self.rs_ptr), P(self.rs_end)
         a.rs_n, a.rs_d, a.rs_c = [P(v) for v in self.rs_ndc]
         a.tile_ptr, a.gb = P(self.tile_ptr), self.gb
-        a.cells_lg, a.top_m, a.warps, a.batch_lg = self.cells_lg, self.top_m, self.warps, self.batch_lg
+        a.cells_lg, a.top_m, a.warps = self.cells_lg, self.top_m, self.warps
         a.unit_counter = N.ptr(self.unit_counter)
         a.unit_clg, a.gws, a.gcells_lg = P(self.unit_clg), N.ptr(self.gws), self.gcells_lg
         a.error_flag = N.ptr(self.error_flag)
@@ -489,7 +487,7 @@ class XsimEngine:
 
     def _entry(self):
         L = N.lib()
-        return {"ll": L.xmap_xsim_extend_ll, "cta": L.xmap_xsim_extend_cta, "warp": L.xmap_xsim_extend}[self.mode]
+        return L.xmap_xsim_extend_cta if self.mode == "cta" else L.xmap_xsim_extend
 
     def _check(self):
         e = int(self.error_flag.item())
