@@ -112,7 +112,8 @@ __device__ __forceinline__ PairDesc load_pair(const xmap_xsim_args &a, long long
 
 // One warp = one unit at a time (fetched from a global counter in descending-work order); the warps of a
 // CTA are independent: no block barrier anywhere.
-__global__ void __launch_bounds__(XT_MAX, 1) xsim_warp_kernel(xmap_xsim_args a) {
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) xsim_warp_kernel(xmap_xsim_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nw = blockDim.x >> 5;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -453,13 +454,15 @@ extern "C" int xmap_xsim_extend(const xmap_xsim_args *args_h, void *stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     const size_t smem = (size_t)xmap_xsim_smem_bytes(a.cells_lg, a.warps);
     if (smem > 227 * 1024) return fail_msg("xmap_xsim_extend: warps x table exceed shared memory");
-    XMAP_CUDA(cudaFuncSetAttribute(xsim_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // two register budgets: up to 16 warps per CTA get 128 registers per thread, up to 20 get 96
+    auto kern = a.warps * 32 <= 512 ? xsim_warp_kernel<512> : xsim_warp_kernel<XT_MAX>;
+    XMAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     XMAP_CUDA(cudaMemsetAsync(a.unit_counter, 0, sizeof(int32_t), st));
     int dev = 0, sms = 148;
     XMAP_CUDA(cudaGetDevice(&dev));
     XMAP_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long long ctas = min((long long)sms, ((long long)a.n_units + a.warps - 1) / a.warps);
-    xsim_warp_kernel<<<(unsigned)ctas, a.warps * 32, smem, st>>>(a);
+    kern<<<(unsigned)ctas, a.warps * 32, smem, st>>>(a);
     XMAP_LAUNCH_CHECK();
     if (a.merge) {
         xsim_merge_kernel<<<(unsigned)((a.n_starts + 7) / 8), 256, 0, st>>>(a);
