@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define XMAP_B200_ABI_VERSION 5
+#define XMAP_B200_ABI_VERSION 6
 #define XMAP_KMAX 64                 /* largest supported top-k (extend_among_topk) */
 #define XMAP_METHOD_ADJUST_COSINE 0  /* baselinerSim.py:144-174 */
 #define XMAP_METHOD_COSINE 1         /* baselinerSim.py:115-142 */
@@ -264,6 +264,7 @@ typedef struct xmap_xsim_args {
     /* optional: every (end, xsim) of unit u written at emit_ptr[u] + 0 .. unit_count[u]-1 (order unspecified) */
     const int64_t *emit_ptr; int32_t *emit_end; double *emit_xsim;
     int32_t *error_flag;                      /* 2: a pass overflowed at the finest split */
+    int64_t *unit_cycles;                     /* optional (NULL: off): SM clock cycles every unit took (xmap_xsim_extend only; tools/) */
 } xmap_xsim_args;
 
 int64_t xmap_xsim_smem_bytes(int32_t cells_lg, int32_t warps);

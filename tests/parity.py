@@ -249,7 +249,7 @@ def run_smoke():
     # the rest of the path on the same case: X-SIM extension (both kernels) and the argmax mapping vs the oracle
     from oracle import restate as RS
     X = RS.xsim_extend(out["P"], out["knn"], case["n_items"], case["meta"]["has_S"], case["meta"]["has_T"])
-    for mode in ("warp", "cta"):
+    for mode in ("hybrid", "warp", "cta"):
         plan, xe, res, (s, e, v) = run_gpu_extend(out["tabs"], out["lay"], case["meta"], mode=mode)
         rel = compare_xsim(s, e, v, X["start"], X["end"], X["xsim"])
         assert int(res.combos.sum()) == X["combos"]

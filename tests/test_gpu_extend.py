@@ -64,8 +64,8 @@ def test_xsim_vs_restatement_and_pass_splits():
     case = PT.synth_case(4000, 900, 60000, 0.04, seed=21)
     out = PT.check_sim_against_restatement(case, "adjust_cosine", 50, 5)
     X = RS.xsim_extend(out["P"], out["knn"], case["n_items"], case["meta"]["has_S"], case["meta"]["has_T"])
-    plan, xe, res, (s, e, v) = PT.run_gpu_extend(out["tabs"], out["lay"], case["meta"])          # default: warp kernel, fused lists
-    assert xe.mode == "warp" and xe.fused_entries > 0
+    plan, xe, res, (s, e, v) = PT.run_gpu_extend(out["tabs"], out["lay"], case["meta"])          # default: hybrid, fused lists
+    assert xe.mode == "hybrid" and xe.fused_entries > 0
     assert plan.n_src == X["n_src"] and plan.n_joint == X["n_joint"]
     PT.compare_xsim(s, e, v, X["start"], X["end"], X["xsim"])
     assert int(res.combos.sum()) == X["combos"]
@@ -79,7 +79,9 @@ def test_xsim_vs_restatement_and_pass_splits():
                     both=dict(W, cells_lg=7, unit_work=300, rho=3.0, warps=5),
                     cta=dict(mode="cta"), cta_small=dict(mode="cta", cells_lg=9, unit_work=400),
                     cta_splits=dict(mode="cta", cells_lg=9, rho=1e9),
-                    cta_unfused=dict(mode="cta", fuse=False), warp_unfused=dict(W, fuse=False))
+                    cta_unfused=dict(mode="cta", fuse=False), warp_unfused=dict(W, fuse=False),
+                    hybrid_some_hot=dict(hot_paths=3000.0), hybrid_all_hot=dict(hot_paths=0.0),
+                    hybrid_small=dict(hot_paths=800.0, cells_lg=6, unit_work=500, max_passes=10 ** 9))
     for name, kw in variants.items():
         plan2, xe2, res2, (s2, e2, v2) = PT.run_gpu_extend(out["tabs"], out["lay"], case["meta"], **kw)
         if name == "small_tables":
@@ -90,12 +92,12 @@ def test_xsim_vs_restatement_and_pass_splits():
             assert xe2.n_units > plan2.start_item.numel()
         if name.endswith("unfused"):
             assert xe2.fused_entries == 0
+        if name.startswith("hybrid"):
+            assert xe2.hot_order.numel() > 0 and (name == "hybrid_all_hot") == (xe2.cold_order.numel() == 0)
         assert np.array_equal(s, s2) and np.array_equal(e, e2), name
         np.testing.assert_allclose(v2, v, rtol=1e-10, atol=0, err_msg=name)      # observed: <= 1.4e-12 (a cancelling sum)
         for f in ("count", "combos", "top_len"):
             assert np.array_equal(getattr(res, f).cpu().numpy(), getattr(res2, f).cpu().numpy()), (name, f)
-        if name == "warp":
-            assert np.array_equal(v, v2)                                         # the default plan again: bit-identical
         _, _, res3, (s3, e3, v3) = PT.run_gpu_extend(out["tabs"], out["lay"], case["meta"], **kw)
         assert np.array_equal(v2, v3) and np.array_equal(res2.top_end.cpu().numpy(), res3.top_end.cpu().numpy()), name
         assert np.array_equal(res2.top_xsim.cpu().numpy(), res3.top_xsim.cpu().numpy()), name
@@ -161,6 +163,14 @@ def test_exponential_mechanism_injected_uniforms_and_philox():
     a = G.choose_mapping(res, "exp_mech", epsilon=3.0, seed=seed).cpu().numpy()
     b = G.choose_mapping(res, "exp_mech", epsilon=3.0, uniforms=PT.philox_uniforms(seed, n)).cpu().numpy()
     assert np.array_equal(a, b)
+    # non-private mapping with another `topn` than the reference's default (generator.py:100: any topn is legal there)
+    tl = rng.integers(1, m + 1, size=n).astype(np.int32)
+    res_v = XsimResult(res.start_item, res.count, res.combos, res.top_end, res.top_xsim, torch.as_tensor(tl, device="cuda"), 0)
+    for topn in (2, 4, 7):
+        got = G.choose_mapping(res_v, "nonprivate", uniforms=u, topn=topn).cpu().numpy()
+        want, _ = RS.choose(np.arange(n), [(ends[r, :min(tl[r], topn)], xs[r, :min(tl[r], topn)]) for r in range(n)],
+                            "nonprivate", uniforms=u)
+        assert np.array_equal(got, want), topn
     # chi-square: 9 dof, 99.9% quantile = 27.88
     w = np.exp(3.0 * xs[0] / (2 * 1 * 2)); p = w / w.sum()
     obs = np.bincount(a, minlength=m)

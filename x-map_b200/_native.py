@@ -14,7 +14,7 @@ KMAX = 64
 XSIM_MAX_CELLS_LG = 13    # XMAP_XSIM_MAX_CELLS_LG
 METHODS = {"adjust_cosine": 0, "cosine": 1}
 SELECT_LONG = 8192            # XMAP_SELECT_LONG
-ABI_VERSION = 5
+ABI_VERSION = 6
 ROW_HDR_BYTES = 48          # XMAP_SIM_ROW_HDR_BYTES
 
 _p = C.c_void_p
@@ -29,7 +29,7 @@ class SimArgs(C.Structure):
         ("k", C.c_int32), ("r2_bits", C.c_int32), ("count_only", C.c_int32),
         ("rec_ptr", _p), ("rec_cnt", _p), ("rec", _p), ("rec_n", _p), ("bb", _p), ("row_npairs", _p),
         ("tab_idx", _p), ("tab_sim", _p), ("tab_mutu", _p), ("tab_n", _p), ("tab_len", _p),
-        ("error_flag", _p),
+        ("error_flag", _p), ("unit_cycles", _p),
     ]
 
 
@@ -46,7 +46,7 @@ class XsimArgs(C.Structure):
         ("unit_count", _p), ("unit_combos", _p), ("unit_top_end", _p), ("unit_top_xsim", _p), ("unit_top_len", _p),
         ("out_count", _p), ("out_combos", _p), ("top_end", _p), ("top_xsim", _p), ("top_len", _p),
         ("emit_ptr", _p), ("emit_end", _p), ("emit_xsim", _p),
-        ("error_flag", _p),
+        ("error_flag", _p), ("unit_cycles", _p),
     ]
 
 

@@ -43,14 +43,14 @@ class Generator(object):
             return h.result
         return _encode_xsim_rows(records_of(rdd), session)
 
-    def _map(self, rdd, session, mode):
+    def _map(self, rdd, session, mode, topn=G.NONPRIVATE_TOPN):
         xres = self._xres(rdd, session)
         seed = self.seed
         if self._fresh:
             seed = (self.seed + 0x9E3779B97F4A7C15 * self._calls) & (2 ** 64 - 1)
             self._calls += 1
         ch = G.choose_mapping(xres, mode, self.privacy_epsilon, self.mapping_range, self.sim_method,
-                              self.uniforms, seed)
+                              self.uniforms, seed, topn=topn)
         if mode == "nonprivate":
             self.single_candidate_rows = int((xres.top_len == 1).sum().item())
         return xres, ch
@@ -62,11 +62,10 @@ class Generator(object):
         return LocalRDD(_pairs(session, xres, ch))
 
     def cross_nonprivate_mapping(self, rdd, topn=4, session=None):
-        """generator.py:100-111 (topn is fixed at the reference's default of 4)."""
-        if topn != G.NONPRIVATE_TOPN:
-            raise ValueError("only the reference's default topn=4 is supported")
+        """generator.py:100-111: one of the first `topn` candidates by |xsim| (the X-SIM stage keeps top_m = 10 of
+        them, so topn <= 10 unless extender_pipeline ran with a larger top_m)."""
         session = session or rdd.handle.session
-        xres, ch = self._map(rdd, session, "nonprivate")
+        xres, ch = self._map(rdd, session, "nonprivate", topn=topn)
         return LocalRDD(_pairs(session, xres, ch))
 
     # ---- profile rewrite -----------------------------------------------------

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(MAXT, 1) xsim_warp_kernel(xmap_xsim_args a) {
         uq = __shfl_sync(0xffffffffu, uq, 0);
         if (uq >= a.n_units) break;
         const int u = a.unit_order ? __ldg(a.unit_order + uq) : uq;
+        const long long t_unit = a.unit_cycles ? clock64() : 0ll;
         const long long leg_lo = a.unit_leg_lo[u], leg_hi = a.unit_leg_hi[u];
         const long long q_lo = a.lp_ptr[leg_lo], q_hi = a.lp_ptr[leg_hi];
         const int ug0 = a.unit_g0[u], ug1 = a.unit_g1[u], unpass = a.unit_npass[u];
@@ -383,6 +384,7 @@ __global__ void __launch_bounds__(MAXT, 1) xsim_warp_kernel(xmap_xsim_args a) {
             a.unit_combos[u] = combos;
             a.unit_top_len[u] = best_len;
             if (status) atomicExch(a.error_flag, 2);
+            if (a.unit_cycles) a.unit_cycles[u] = clock64() - t_unit;
         }
         for (int q = lane; q < best_len; q += 32) {
             a.unit_top_end[(size_t)u * M + q] = W.best_end[q];

@@ -241,11 +241,13 @@ XSIM_MAX_PASSES = int(os.environ.get("XMAP_XSIM_MAX_PASSES", "1000000000"))   # 
                                 # global memory (L2).  Measured at cfg2: 32 passes + L2 tables 968 ms, shared memory only
                                 # (no cap) 732 ms -- dependent read-modify-writes at L2 latency lose to narrow passes
 XSIM_GCELLS_LG = 16             # largest global-memory table of a unit (cells)
-XSIM_MODE = os.environ.get("XMAP_XSIM_MODE", "warp")                # "warp": one warp per unit (xsim.cu, default); "cta": one CTA
+XSIM_MODE = os.environ.get("XMAP_XSIM_MODE", "hybrid")                # "warp": one warp per unit (xsim.cu, default); "cta": one CTA
                                                                    # per unit with one 8x larger table (xsim_cta.cu)
 XSIM_FUSE = os.environ.get("XMAP_XSIM_FUSE", "1") != "0"          # fused bridge lists B(t) for the joint-only legs
 XSIM_FUSE_MAX = 1 << 31         # entries (28 B each + sort scratch) above which the lists are not fused: a fixed number, not a
                                 # function of free memory, so that every rank takes the same decision
+XSIM_HOT_PATHS = float(os.environ.get("XMAP_XSIM_HOT_PATHS", str(1 << 19)))   # hybrid mode: a unit expected to hold more paths
+                                # than this is run by the CTA kernel (8 warps on one unit) instead of one warp
 XSIM_CTA_CELLS_LG = int(os.environ.get("XMAP_XSIM_CTA_CELLS_LG", "12"))
 XSIM_CTA_UNIT_LG = int(os.environ.get("XMAP_XSIM_CTA_UNIT_LG", "17"))     # 2^17 paths per unit: short critical path when units are dealt to 8 GPUs
 
@@ -273,17 +275,18 @@ class XsimEngine:
 
     def __init__(self, plan, top_m=10, cells_lg=None, rho=XSIM_RHO, unit_work=None,
                  load=XSIM_LOAD, warps=XSIM_WARPS, max_passes=XSIM_MAX_PASSES, mode=XSIM_MODE, fuse=None,
-                 fuse_max_entries=XSIM_FUSE_MAX):
-        if mode not in ("warp", "cta"):
-            raise ValueError("mode must be 'warp' or 'cta'")
+                 fuse_max_entries=XSIM_FUSE_MAX, hot_paths=None):
+        if mode not in ("hybrid", "warp", "cta"):
+            raise ValueError("mode must be 'hybrid', 'warp' or 'cta'")
         self.mode = mode
+        self.hot_paths = float(XSIM_HOT_PATHS if hot_paths is None else hot_paths)
         if fuse is None:
             fuse = XSIM_FUSE
         if cells_lg is None:
             cells_lg = XSIM_CTA_CELLS_LG if mode == "cta" else XSIM_CELLS_LG
         if unit_work is None:
-            unit_work = XSIM_UNIT_WORK if mode == "warp" else (1 << XSIM_CTA_UNIT_LG)
-        if mode != "warp":
+            unit_work = (1 << XSIM_CTA_UNIT_LG) if mode == "cta" else XSIM_UNIT_WORK
+        if mode == "cta":
             max_passes = 10 ** 9                 # shared memory only
             if cells_lg < 9:
                 raise ValueError("cta mode needs cells_lg >= 9")
@@ -292,7 +295,7 @@ class XsimEngine:
         if not (6 <= cells_lg <= N.XSIM_MAX_CELLS_LG):
             raise ValueError("cells_lg must be in [6, %d]" % N.XSIM_MAX_CELLS_LG)
         warps = int(warps)
-        while mode == "warp" and warps > 1 and N.lib().xmap_xsim_smem_bytes(int(cells_lg), warps) > 227 * 1024:
+        while mode != "cta" and warps > 1 and N.lib().xmap_xsim_smem_bytes(int(cells_lg), warps) > 227 * 1024:
             warps -= 1
         self.plan, self.top_m, self.cells_lg, self.warps = plan, int(top_m), int(cells_lg), warps
         self.unit_counter = torch.zeros(1, dtype=torch.int32, device=plan.start_item.device)
@@ -434,6 +437,16 @@ class XsimEngine:
                 rows.view(-1).scatter_add_(0, (seg[e0:e1] - a0) * (G + 1) + tile[e0:e1] + 1,
                                            torch.ones(e1 - e0, dtype=i32, device=dev))
                 rows.copy_(torch.cumsum(rows, 1, dtype=i32))
+        # tile heat: the paths a start's walk is expected to spend in every tile = entries per tile weighted by the number
+        # of (leg, partner) pairs that walk the list.  Popular ends are popular for every start, so this global profile
+        # tells which tile range of a heavy start is hot (cfg2: one 2-tile unit of the heaviest start holds 7.8 M paths
+        # where a uniform split expects 0.36 M).
+        heat = torch.zeros(G, dtype=torch.float64, device=dev)
+        if seg.numel() and self.pd_s.numel():
+            usage = torch.bincount(self.pd_s.long(), minlength=n_s).double()
+            heat.index_add_(0, tile, usage[seg])
+        cum_heat = torch.zeros(G + 1, dtype=torch.float64, device=dev)
+        cum_heat[1:] = torch.cumsum(heat, 0)
         del tile, seg, pi
         # ---- units -------------------------------------------------------------------------------------
         self.start_unit_ptr = torch.zeros(n + 1, dtype=i32, device=dev)
@@ -457,9 +470,31 @@ class XsimEngine:
         if self.gcells_lg > self.cells_lg:
             sms = torch.cuda.get_device_properties(dev).multi_processor_count if dev.type == "cuda" else 1
             self.gws = torch.empty(sms * self.warps * (20 << self.gcells_lg), dtype=torch.uint8, device=dev)
-        unit_work_est = ub[us] / nu.double()
+        # expected paths of a unit: the start's paths times the heat share of the unit's tile range
+        tot_heat = float(cum_heat[-1].item()) if G else 0.0
+        share = (cum_heat[self.unit_g1.long()] - cum_heat[self.unit_g0.long()]) / max(tot_heat, 1e-300) if tot_heat > 0 else \
+            (self.unit_g1 - self.unit_g0).double() / float(G)
+        unit_work_est = ub[us] * share
+        self.unit_est_paths = unit_work_est
         self.unit_order = torch.argsort(unit_work_est, descending=True, stable=True).to(i32).contiguous()
         self.T, self.n_units_x = T, n_units_x
+        # ---- hybrid: the units one warp would take too long over (a straggler bounds the multi-GPU time) are run by the
+        # CTA kernel, 8 warps on one unit with one 8x larger table, the rest by the warp kernel.  The class of a unit is a
+        # function of the plan only, so results do not depend on the number of GPUs.
+        self.cta_cells_lg = XSIM_CTA_CELLS_LG
+        if mode == "hybrid":
+            hot = unit_work_est > self.hot_paths
+            # fewer passes on the larger table (never more than the unit has tiles)
+            grow = 1 << max(0, self.cta_cells_lg - self.cells_lg)
+            np_hot = torch.clamp((self.unit_npass.long() + grow - 1) // grow, min=1)
+            self.unit_npass = torch.where(hot, np_hot, self.unit_npass.long()).to(i32).contiguous()
+            uo = self.unit_order.long()
+            self.hot_order = self.unit_order[hot[uo]].contiguous()
+            self.cold_order = self.unit_order[~hot[uo]].contiguous()
+        elif mode == "cta":
+            self.hot_order, self.cold_order = self.unit_order, self.unit_order[:0]
+        else:
+            self.hot_order, self.cold_order = self.unit_order[:0], self.unit_order
 
     # ------------------------------------------------------------------
     def _args(self, keep):
@@ -485,9 +520,35 @@ class XsimEngine:
         a.error_flag = N.ptr(self.error_flag)
         return a
 
-    def _entry(self):
+    def _launch_units(self, a, rank, world, st):
+        """This rank's units: the hot ones first (CTA kernel: they are the long poles), then the rest (warp kernel).
+        Every world-th unit of either descending-work order."""
         L = N.lib()
-        return L.xmap_xsim_extend_cta if self.mode == "cta" else L.xmap_xsim_extend
+        hot = self.hot_order if world == 1 else self.hot_order[rank::world].contiguous()
+        cold = self.cold_order if world == 1 else self.cold_order[rank::world].contiguous()
+        a.merge = 0
+        self._orders = (hot, cold)                         # keep the device arrays alive until the kernels ran
+        side = None
+        if hot.numel() and cold.numel() and self.device.type == "cuda":
+            # the two kernels run side by side: the hot CTAs are dispatched first, the persistent CTAs of the warp
+            # kernel take the SMs over as the hot ones drain
+            if getattr(self, "_side", None) is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            side = self._side
+            side.wait_stream(torch.cuda.current_stream(self.device))
+        if hot.numel():
+            clg = a.cells_lg
+            a.cells_lg = self.cta_cells_lg if self.mode == "hybrid" else self.cells_lg
+            a.unit_order, a.n_units = N.ptr(hot), int(hot.numel())
+            N.check(L.xmap_xsim_extend_cta(a, side.cuda_stream if side is not None else st), "xmap_xsim_extend_cta")
+            a.cells_lg = clg
+            self.launches += 1
+        if cold.numel():
+            a.unit_order, a.n_units = N.ptr(cold), int(cold.numel())
+            N.check(L.xmap_xsim_extend(a, st), "xmap_xsim_extend")
+            self.launches += 1
+        if side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(side)
 
     def _check(self):
         e = int(self.error_flag.item())
@@ -513,19 +574,14 @@ class XsimEngine:
         a.unit_top_end, a.unit_top_xsim, a.unit_top_len = N.ptr(ute), N.ptr(utx), N.ptr(utl)
         a.out_count, a.out_combos = N.ptr(cnt), N.ptr(comb)
         a.top_end, a.top_xsim, a.top_len = N.ptr(te), N.ptr(tx), N.ptr(tl)
-        order = self.unit_order if world == 1 else self.unit_order[rank::world].contiguous()
-        a.unit_order, a.n_units = N.ptr(order), int(order.numel())
-        a.merge = 1 if world == 1 else 0
         st = torch.cuda.current_stream().cuda_stream
-        run_units = self._entry()
         if n and nu:
-            N.check(run_units(a, st), "xmap_xsim_extend")
-            self.launches += 1 + a.merge
+            self._launch_units(a, rank, world, st)
             if world > 1:
                 from .multi import sum_unit_results
                 sum_unit_results((ucount, ucombos, ute, utx, utl), group)
-                N.check(L.xmap_xsim_merge(a, st), "xmap_xsim_merge")
-                self.launches += 1
+            N.check(L.xmap_xsim_merge(a, st), "xmap_xsim_merge")
+            self.launches += 1
         self._check()
         return XsimResult(p.start_item, cnt, comb, te, tx, tl, self.launches, ucount)
 
@@ -547,10 +603,8 @@ class XsimEngine:
             scratch = [z(nu, torch.int32), z(nu, torch.int64), z((nu, m), torch.int32), z((nu, m), torch.float64),
                        z(nu, torch.int32)]
             a.unit_count, a.unit_combos, a.unit_top_end, a.unit_top_xsim, a.unit_top_len = [N.ptr(t) for t in scratch]
-            a.unit_order, a.n_units, a.merge = N.ptr(self.unit_order), nu, 0
             a.emit_ptr, a.emit_end, a.emit_xsim = N.ptr(ptr), N.ptr(e_end), N.ptr(e_x)
-            N.check(self._entry()(a, torch.cuda.current_stream().cuda_stream), "xmap_xsim_extend(emit)")
-            self.launches += 1
+            self._launch_units(a, 0, 1, torch.cuda.current_stream().cuda_stream)
             self._check()
             if not torch.equal(scratch[0], res.unit_count):
                 raise N.NativeError("X-SIM emit pass disagrees with the counting pass")

@@ -25,13 +25,16 @@ def global_sensitivity(sim_method):
 
 
 def choose_mapping(xres, mode, epsilon=0.6, mapping_range=1, sim_method="adjust_cosine",
-                   uniforms=None, seed=0):
-    """Per start row pick one end item.  mode: 'argmax' | 'exp_mech' | 'nonprivate'.
-    `uniforms` (float64 per row, in [0,1)) are injected draws; None -> Philox(seed, row)."""
+                   uniforms=None, seed=0, topn=NONPRIVATE_TOPN):
+    """Per start row pick one end item.  mode: 'argmax' | 'exp_mech' | 'nonprivate' (one of the first `topn`
+    candidates, generator.py:100-111).  `uniforms` (float64 per row, in [0,1)) are injected draws; None ->
+    Philox(seed, row)."""
     L = N.lib()
     n, top_m = xres.top_end.shape
     dev = xres.top_end.device
-    n_cand = NONPRIVATE_TOPN if mode == "nonprivate" else PRIVATE_CANDIDATES
+    n_cand = int(topn) if mode == "nonprivate" else PRIVATE_CANDIDATES
+    if not (1 <= n_cand <= 16):
+        raise ValueError("topn must be in [1, 16]")
     if top_m < n_cand:
         raise ValueError("X-SIM top_m=%d is smaller than the %d candidates %s mapping needs"
                          % (top_m, n_cand, mode))
