@@ -41,8 +41,8 @@ WORKLOADS = {
 METRIC = "item_pair_sims_per_sec"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
 # (profiles/), keyed by kernel group; None until captured.
-NCU_TRAFFIC = {"tri_cta_kernel": 5.857e9 / 14}   # (2.883 GB read + 2.974 GB written) over the 14 launches of one stage,
-                                                 # profiles/r1_ncu_full_cfg2.csv; per launch like `achieved`
+NCU_TRAFFIC = {"tri_cta_kernel": 7.229e9 / 14}   # dram__bytes_read + dram__bytes_write summed over the 14 launches of one stage,
+                                                 # profiles/r2_ncu_full_cfg2.csv; per launch like `achieved` (cfg2 only)
 
 
 def _compact(name, sr, keep, k, tag):
@@ -539,8 +539,10 @@ def main():
             # figure is an equivalent-traffic rate, next to the 28 B right-segment read each path really makes
             xk = pipe["xsim_kernels_ms"] * 1e-3
             gb16, gb28 = 16.0 * pipe["xsim_paths"] / xk / 1e9, 28.0 * pipe["xsim_paths"] / xk / 1e9
-            line["pipeline_roofline"] = {"kernel": "xsim_%s_kernel" % X.XSIM_MODE, "bound": "hbm", "achieved": gb16, "peak": peaks["hbm_gbs"],
-                                         "unit": "GB/s", "frac": gb16 / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC.get("xsim_%s_kernel" % X.XSIM_MODE),
+            xname = {"hybrid": "xsim_warp_kernel (+ xsim_cta_kernel for the hot units)", "warp": "xsim_warp_kernel",
+                     "cta": "xsim_cta_kernel"}[X.XSIM_MODE]
+            line["pipeline_roofline"] = {"kernel": xname, "bound": "hbm", "achieved": gb16, "peak": peaks["hbm_gbs"],
+                                         "unit": "GB/s", "frac": gb16 / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC.get(xname.split()[0]),
                                          "algorithmic_bytes_per_path": 16, "paths": pipe["xsim_paths"],
                                          "kernel_ms": pipe["xsim_kernels_ms"], "right_segment_read_gbs": gb28,
                                          "note": "host wall-clock around the kernel launches + merge (max over ranks via the barrier)"}

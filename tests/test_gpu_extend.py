@@ -81,7 +81,8 @@ def test_xsim_vs_restatement_and_pass_splits():
                     cta_splits=dict(mode="cta", cells_lg=9, rho=1e9),
                     cta_unfused=dict(mode="cta", fuse=False), warp_unfused=dict(W, fuse=False),
                     hybrid_some_hot=dict(hot_paths=3000.0), hybrid_all_hot=dict(hot_paths=0.0),
-                    hybrid_small=dict(hot_paths=800.0, cells_lg=6, unit_work=500, max_passes=10 ** 9))
+                    hybrid_small=dict(hot_paths=800.0, cells_lg=6, unit_work=500, max_passes=10 ** 9),
+                    uniform_cuts=dict(balance="uniform", unit_work=500), heat_cuts=dict(W, balance="heat", cells_lg=6, unit_work=300))
     for name, kw in variants.items():
         plan2, xe2, res2, (s2, e2, v2) = PT.run_gpu_extend(out["tabs"], out["lay"], case["meta"], **kw)
         if name == "small_tables":

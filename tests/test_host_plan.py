@@ -61,6 +61,38 @@ def test_engine_arrays_reproduce_the_plan(name, fuse, native_built):
     PT.compare_xsim(s, e, v, g["xs_start"], g["xs_end"], g["xs_val"], rtol=1e-9)
 
 
+@pytest.mark.parametrize("balance", ["heat", "uniform"])
+def test_units_partition_the_tile_axis(balance, native_built):
+    """Every start's units cut [0, 2^gb) into consecutive, non-empty tile ranges (equal heat or equal width); the hot /
+    cold classes of the hybrid schedule partition the units; the heat estimate adds up to the plan's paths."""
+    import torch
+    from xmap_b200 import extend as X
+    g = PT.load_golden("adj_low_overlap")
+    meta = PT.golden_meta(g)
+    nU, nI = len(g["uids"]), len(g["iids"])
+    P = RS.sim_pairs(g["user"].astype(np.int64), g["item"].astype(np.int64), g["rating"], nU, nI,
+                     meta["prefix_code"], str(g["method"]), int(g["num_atleast"]))
+    knn = RS.select_knn(P, nI, int(g["k"]), meta["dom_code"], meta["contains"])
+    tabs = PT.tables_from_restatement(P, knn, nI, int(g["k"]))
+    plan = X.build_plan(tabs, torch.as_tensor(P["stats"]["count"]), torch.as_tensor(meta["has_S"]),
+                        torch.as_tensor(meta["has_T"]))
+    xe = X.XsimEngine(plan, 10, cells_lg=6, unit_work=200, balance=balance, hot_paths=1500.0)
+    G = 1 << xe.gb
+    g0, g1, sp = xe.unit_g0.numpy(), xe.unit_g1.numpy(), xe.start_unit_ptr.numpy()
+    assert (np.diff(sp) > 1).sum() > 50                                  # many starts are cut into several units
+    for x in range(len(sp) - 1):
+        a, b = sp[x], sp[x + 1]
+        assert g0[a] == 0 and g1[b - 1] == G and (g1[a:b] > g0[a:b]).all() and (g0[a + 1:b] == g1[a:b - 1]).all()
+    npass = xe.unit_npass.numpy()
+    assert (npass >= 1).all() and (npass <= g1 - g0).all()
+    hot, cold = xe.hot_order.numpy(), xe.cold_order.numpy()
+    assert len(hot) > 0 and len(cold) > 0 and np.array_equal(np.sort(np.concatenate([hot, cold])), np.arange(xe.n_units))
+    est = xe.unit_est_paths.numpy()
+    assert (est[hot] > 1500.0).all() and (est[cold] <= 1500.0).all()
+    per_start = np.add.reduceat(est, sp[:-1])
+    np.testing.assert_allclose(per_start, plan.ub.numpy().astype(np.float64), rtol=1e-9)
+
+
 def test_library_exports_every_declared_symbol(native_built):
     from xmap_b200 import _native
     hdr = open(os.path.join(PT.ROOT, "include", "xmap_b200.h")).read()

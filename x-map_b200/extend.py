@@ -246,6 +246,8 @@ XSIM_MODE = os.environ.get("XMAP_XSIM_MODE", "hybrid")                # "warp": 
 XSIM_FUSE = os.environ.get("XMAP_XSIM_FUSE", "1") != "0"          # fused bridge lists B(t) for the joint-only legs
 XSIM_FUSE_MAX = 1 << 31         # entries (28 B each + sort scratch) above which the lists are not fused: a fixed number, not a
                                 # function of free memory, so that every rank takes the same decision
+XSIM_BALANCE = os.environ.get("XMAP_XSIM_BALANCE", "heat")     # how a heavy start's tiles are cut into units: equal "heat"
+                                # (expected paths) or "uniform" (equal numbers of tiles)
 XSIM_HOT_PATHS = float(os.environ.get("XMAP_XSIM_HOT_PATHS", str(1 << 19)))   # hybrid mode: a unit expected to hold more paths
                                 # than this is run by the CTA kernel (8 warps on one unit) instead of one warp
 XSIM_CTA_CELLS_LG = int(os.environ.get("XMAP_XSIM_CTA_CELLS_LG", "12"))
@@ -275,7 +277,7 @@ class XsimEngine:
 
     def __init__(self, plan, top_m=10, cells_lg=None, rho=XSIM_RHO, unit_work=None,
                  load=XSIM_LOAD, warps=XSIM_WARPS, max_passes=XSIM_MAX_PASSES, mode=XSIM_MODE, fuse=None,
-                 fuse_max_entries=XSIM_FUSE_MAX, hot_paths=None):
+                 fuse_max_entries=XSIM_FUSE_MAX, hot_paths=None, balance=XSIM_BALANCE):
         if mode not in ("hybrid", "warp", "cta"):
             raise ValueError("mode must be 'hybrid', 'warp' or 'cta'")
         self.mode = mode
@@ -456,9 +458,25 @@ class XsimEngine:
         kq = torch.arange(self.n_units, device=dev) - self.start_unit_ptr[:-1].long()[us]
         nu = n_units_x[us]
         self.unit_start = us
-        self.unit_g0 = (kq * G // nu).to(i32).contiguous()
-        self.unit_g1 = ((kq + 1) * G // nu).to(i32).contiguous()
-        self.unit_npass = torch.minimum(ppu[us], (self.unit_g1 - self.unit_g0).long()).to(i32).contiguous()
+        tot_heat = float(cum_heat[-1].item()) if G else 0.0
+        if balance == "heat" and tot_heat > 0 and self.n_units:
+            # the units of a start take equal shares of the tile HEAT, not equal numbers of tiles (every unit keeps at
+            # least one tile): cut k of nu sits where the cumulative heat reaches k / nu of the total
+            cut = torch.searchsorted(cum_heat, kq.double() / nu.double() * tot_heat, right=False)
+            cut = torch.where(kq == 0, torch.zeros_like(cut), cut)
+            big = 2 * (G + 1)
+            v = torch.cummax(cut - kq + us * big, 0).values - us * big + kq       # strictly increasing inside a start
+            g0 = torch.minimum(v, G - (nu - kq))                                      # room for the units that follow
+            nxt = torch.cat([g0[1:], g0.new_tensor([G])])
+            g1 = torch.where(kq + 1 == nu, torch.full_like(g0, G), nxt)
+            self.unit_g0, self.unit_g1 = g0.to(i32).contiguous(), g1.to(i32).contiguous()
+            width = (g1 - g0)
+            need = torch.clamp((T[us] * width + G - 1) // G, min=1)                   # ends are spread evenly over the tiles
+            self.unit_npass = torch.minimum(need, width).to(i32).contiguous()
+        else:
+            self.unit_g0 = (kq * G // nu).to(i32).contiguous()
+            self.unit_g1 = ((kq + 1) * G // nu).to(i32).contiguous()
+            self.unit_npass = torch.minimum(ppu[us], (self.unit_g1 - self.unit_g0).long()).to(i32).contiguous()
         self.unit_leg_lo = p.leg_ptr[:-1][us].contiguous()
         self.unit_leg_hi = p.leg_ptr[1:][us].contiguous()
         # table a unit wants: its share of the start's estimated ends at the target load
@@ -471,7 +489,6 @@ class XsimEngine:
             sms = torch.cuda.get_device_properties(dev).multi_processor_count if dev.type == "cuda" else 1
             self.gws = torch.empty(sms * self.warps * (20 << self.gcells_lg), dtype=torch.uint8, device=dev)
         # expected paths of a unit: the start's paths times the heat share of the unit's tile range
-        tot_heat = float(cum_heat[-1].item()) if G else 0.0
         share = (cum_heat[self.unit_g1.long()] - cum_heat[self.unit_g0.long()]) / max(tot_heat, 1e-300) if tot_heat > 0 else \
             (self.unit_g1 - self.unit_g0).double() / float(G)
         unit_work_est = ub[us] * share
