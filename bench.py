@@ -41,8 +41,9 @@ WORKLOADS = {
 METRIC = "item_pair_sims_per_sec"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
 # (profiles/), keyed by kernel group; None until captured.
-NCU_TRAFFIC = {"tri_cta_kernel": 7.229e9 / 14}   # dram__bytes_read + dram__bytes_write summed over the 14 launches of one stage,
-                                                 # profiles/r2_ncu_full_cfg2.csv; per launch like `achieved` (cfg2 only)
+NCU_TRAFFIC = {"tri_cta_kernel": 7.229e9 / 14,   # dram__bytes_read + dram__bytes_write summed over the 14 launches of one stage,
+               "xsim_warp_kernel": 3.688e11}     # ... and of the one X-SIM launch: profiles/r2_ncu_full_cfg2.csv; per launch like
+                                                 # `achieved` (cfg2, one GPU)
 
 
 def _compact(name, sr, keep, k, tag):
@@ -413,7 +414,7 @@ def main():
     # source -> target pipeline, summed
     pipe = None
     for timed in ((False, True, True) if not args.no_pipeline else ()):  # one untimed pass, then the faster of two
-        acc = dict(plan=0.0, xsim=0.0, xsim_kernel=0.0, gen=0.0, combos=0, starts=0, pairs=0, recs=0, src=0, joint=0, units=0)
+        acc = dict(plan=0.0, xsim=0.0, xsim_kernel=0.0, gen=0.0, combos=0, starts=0, pairs=0, recs=0, src=0, joint=0, units=0, hot=0)
         for q, wl in enumerate(pipes):
             lay, meta, tabs = wl["lay"], wl["dmeta"], tabs_all[q]
             barrier()
@@ -434,7 +435,7 @@ def main():
             acc["plan"] += t1 - t0; acc["xsim"] += t2 - t1; acc["xsim_kernel"] += t2 - t1b; acc["gen"] += t3 - t2
             acc["combos"] += int(res.combos.sum().item()); acc["starts"] += int(res.start_item.numel())
             acc["pairs"] += int(res.count.sum().item()); acc["recs"] += int(n_rec.item())
-            acc["src"] += plan.n_src; acc["joint"] += plan.n_joint; acc["units"] += xe.n_units
+            acc["src"] += plan.n_src; acc["joint"] += plan.n_joint; acc["units"] += xe.n_units; acc["hot"] += int(xe.hot_order.numel())
             if world > 1 and q == 0 and multi_parity is not None and "xsim_top_m" not in multi_parity:
                 ok = True
                 if rank == 0:
@@ -456,6 +457,7 @@ def main():
                 "generate_ms": acc["gen"] * 1e3, "alterego_pipeline_ms": total_ms,
                 "xsim_paths": acc["combos"], "xsim_paths_per_s": acc["combos"] / max(acc["xsim_kernel"], 1e-9),
                 "xsim_starts": acc["starts"], "xsim_pairs": acc["pairs"], "xsim_units": acc["units"],
+                "xsim_hot_units": acc["hot"],
                 "alterego_synthetic_records": acc["recs"], "bridge_pairs": acc["src"], "joint_pairs": acc["joint"],
                 "pipelines": len(pipes),
                 "sharding": "X-SIM by work unit x%d, generation by user x%d (host wall-clock of rank 0 between barriers, "
