@@ -11,7 +11,7 @@ tabs = E.SimEngine(lay, meta, "adjust_cosine", 50, wl["k"]).run()
 plan = X.build_plan(tabs, lay.item_stats[:, 3].contiguous(), meta.has_S, meta.has_T)
 print("plan ub sum", int(plan.ub.sum()))
 out = {}
-for mode in ("warp", "cta"):
+for mode in ("hybrid", "warp", "cta"):
     xe = X.XsimEngine(plan, 10, mode=mode)
     torch.cuda.synchronize(); t = time.perf_counter()
     res = xe.run()
@@ -21,10 +21,10 @@ for mode in ("warp", "cta"):
     for x in bad[:5].tolist():
         print("   start", x, "ub", int(plan.ub[x]), "combos", int(res.combos[x]), "T", int(xe.T[x]), "units", int(xe.n_units_x[x]), "count", int(res.count[x]))
     out[mode] = res
-a, b = out["warp"], out["cta"]
+a, b = out["hybrid"], out["cta"]
 dc = (a.count != b.count).nonzero().flatten()
 print("starts with different distinct-end counts:", int(dc.numel()))
 for x in dc[:5].tolist():
-    print("   start", x, "warp", int(a.count[x]), "cta", int(b.count[x]), "ub", int(plan.ub[x]))
+    print("   start", x, "hybrid", int(a.count[x]), "cta", int(b.count[x]), "ub", int(plan.ub[x]))
 print("top_end equal rows:", int((a.top_end == b.top_end).all(1).sum()), "of", a.top_end.shape[0],
       "max |xsim| diff", float((a.top_xsim - b.top_xsim).abs().max()))
