@@ -349,6 +349,20 @@ int xmap_recsim_predict(const int64_t *prof_ptr, const int32_t *prof_item, const
                         const int32_t *nb_len, int32_t k, const int32_t *t_user, const int32_t *t_item, int64_t n_test,
                         double alpha, double *pred_nodecay, double *pred_decay, int32_t *error_flag, void *stream);
 
+/* ---------------------------------------------------------------------------
+ * (6) Clean stage on encoded records.
+ * Replaces the data-parallel part of BaselinerClean: the period test of parse_data (baselinerClean.py:47-52, given as
+ * the two instants [t_lo, t_hi) the local-time years [date_from, date_to] span), filter_data (:62-92: per (user, item)
+ * the strictly latest rating, the first seen winning ties) and clean_data (:94-97: users with fewer than num_atleast
+ * items are dropped).  Splitting the text lines and the id dictionaries stay on the host.
+ *   order      : [n] record indices sorted, stable, by (out-of-period last, user, item)
+ *   keep       : [n] out, 1 for the records that survive
+ *   user_items : [n_users] out, distinct in-period items per user (before the num_atleast test)
+ * ------------------------------------------------------------------------- */
+int xmap_clean_records(const int32_t *user, const int32_t *item, const double *ts, const int64_t *order,
+                       int64_t n, int32_t n_users, double t_lo, double t_hi, int32_t num_atleast,
+                       uint8_t *keep, int32_t *user_items, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

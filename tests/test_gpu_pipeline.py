@@ -191,3 +191,31 @@ def test_recommender_pipelines_match_reference(name):
                                           Broadcast(neigh), out[2], out[3], out[4], out[5])
     m0, m1 = (float(x) for x in mae.split(";"))
     assert abs(m0 - float(g["mae_nodecay"])) < 1e-2 and abs(m1 - float(g["mae_decay"])) < 1e-2
+
+
+def test_device_clean_matches_host_clean():
+    """the clean stage's record-level rules on the device (xmap_clean_records) against the host class,
+    which tests/test_host_cleansplit.py pins to the unmodified reference: same users, same (item, rating, time) lists in
+    the same order -- with duplicates at other timestamps, exact timestamp ties and out-of-period years in the input."""
+    from xmap_b200 import synth
+    from xmap_b200.core import BaselinerClean
+    from xmap_b200.rdd import LocalRDD
+    sr = synth.make_ratings(600, 80, 14000, overlap=0.3, seed=9)
+    lines = synth.to_text_lines(sr, 0)
+    bump = lambda l, dt: l.rsplit("\t", 1)[0] + "\t" + str(int(l.rsplit("\t", 1)[1]) + dt)
+    rerate = lambda l, r: "\t".join(l.split("\t")[:2] + [str(r), l.split("\t")[3]])
+    extra = [bump(l, k * 40000000) for k, l in enumerate(lines[:300])]                 # later duplicates, some out of period
+    extra += [bump(l, -3600) for l in lines[300:500]]                                   # earlier duplicates: must lose
+    extra += [rerate(l, 1 + (k % 5)) for k, l in enumerate(lines[500:700])]             # exact ties: the first seen wins
+    extra += [bump(l, -10 * 365 * 86400) for l in lines[700:800]]                       # out of period only
+    rng = np.random.default_rng(2)
+    lines = lines + extra
+    lines = [lines[k] for k in rng.permutation(len(lines))]
+    for atleast in (1, 5, 12):
+        tool = BaselinerClean(atleast, 10 ** 9, 2012, 2013, "S:")
+        want = tool.clean_data(tool.filter_data(tool.parse_data(LocalRDD(lines)))).collect()
+        got = tool.device_pipeline(LocalRDD(lines)).collect()
+        assert len(want) > 0 and [u for u, _ in got] == [u for u, _ in want], atleast
+        for (u, a), (_, b) in zip(got, want):
+            assert a == b, (atleast, u)
+    assert len(BaselinerClean(10 ** 6, 1, 2012, 2013, "S:").device_pipeline(LocalRDD(lines)).collect()) == 0

@@ -1,4 +1,5 @@
-"""BaselinerClean -- host-side (string parsing, O(nnz); not on the measured path).
+"""BaselinerClean -- host-side string parsing; the data-parallel part (period test, latest-rating dedupe, minimum
+ratings per user) also runs on the device (`device_pipeline`, csrc/clean.cu).
 Semantics of xmap/core/baselinerClean.py:7-97: whitespace-split 4-column lines, keep ratings whose
 local-time year lies in [date_from, date_to], suffix the item id with the domain label, keep per
 (user, item) the strictly latest rating, drop users with fewer than num_atleast_rating items."""
@@ -45,3 +46,36 @@ class BaselinerClean(object):
 
     def take_partial_data(self, dataRDD):
         return records_of(dataRDD)[: self.size_subset]
+
+    def device_pipeline(self, originalRDD):
+        """parse_data -> filter_data -> clean_data with the record-level work on the GPU (xmap_clean_records): the lines
+        are split and the ids numbered on the host, the period test, the per-(user, item) latest-rating rule and the
+        minimum-ratings rule run on the device.  Same records as clean_data(filter_data(parse_data(rdd))); users in
+        first-appearance order, a user's items in first-appearance order."""
+        import numpy as np
+        import torch
+        from .. import clean as CL
+        lines = records_of(originalRDD)
+        uid, iid, rating, ts = [], [], [], []
+        for line in lines:
+            f = line.split()
+            if len(f) < 4:
+                raise IndexError("expected 'uid iid rating timestamp', got %r" % (line,))
+            uid.append(f[0]); iid.append(f[1]); rating.append(float(f[2])); ts.append(float(f[3]))
+        uids, user = np.unique(np.array(uid, dtype=object).astype(str), return_inverse=True) if uid else ([], np.zeros(0, np.int64))
+        iids, item = np.unique(np.array(iid, dtype=object).astype(str), return_inverse=True) if iid else ([], np.zeros(0, np.int64))
+        t_lo, t_hi = CL.period_bounds(self.period[0], self.period[-1])
+        keep, _ = CL.clean_encoded(user.astype(np.int32), item.astype(np.int32), np.array(ts, dtype=np.float64), len(uids),
+                                   t_lo, t_hi, self.num_atleast_rating)
+        kept = torch.nonzero(keep).flatten().cpu().numpy()
+        # the reference's per-user dict keeps a pair where it FIRST appeared among the in-period lines, and users come in
+        # first-appearance order: order the output the same way
+        tsa = np.array(ts, dtype=np.float64)
+        first_pos, first_user = {}, {}
+        for k in np.flatnonzero((tsa >= t_lo) & (tsa < t_hi)):
+            first_pos.setdefault((user[k], item[k]), k)
+            first_user.setdefault(uid[k], k)
+        users = {}
+        for k in sorted(kept, key=lambda k: first_pos[(user[k], item[k])]):
+            users.setdefault(uid[k], []).append((iid[k] + self.label, rating[k], self.parse_time(str(ts[k]))))
+        return LocalRDD(sorted(users.items(), key=lambda kv: first_user[kv[0]]))
