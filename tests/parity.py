@@ -450,3 +450,28 @@ def philox_uniforms(seed, n):
         k0 = (k0 + np.uint64(W0)) & mask; k1 = (k1 + np.uint64(W1)) & mask
     hi = (c[0] >> np.uint64(5)).astype(np.float64); lo = (c[1] >> np.uint64(6)).astype(np.float64)
     return (hi * 67108864.0 + lo) / 9007199254740992.0
+
+
+# --------------------------------------------------------------------------
+# clean stage
+# --------------------------------------------------------------------------
+def clean_encoded_numpy(user, item, ts, n_users, t_lo, t_hi, num_atleast):
+    """numpy restatement of what xmap_clean_records decides (baselinerClean.py:47-52, 62-97): a record survives if it is
+    in the period, is the STRICTLY latest of its (user, item) pair -- the first seen winning ties -- and its user keeps
+    at least num_atleast items.  Returns (keep uint8 [n], items per user int32 [n_users])."""
+    user, item, ts = np.asarray(user), np.asarray(item), np.asarray(ts, dtype=np.float64)
+    n = len(user)
+    inp = (ts >= t_lo) & (ts < t_hi)
+    keep = np.zeros(n, np.uint8)
+    best = {}
+    for r in np.flatnonzero(inp):
+        k = (int(user[r]), int(item[r]))
+        if k not in best or ts[r] > ts[best[k]]:
+            best[k] = r
+    per_user = np.zeros(max(n_users, 1), np.int32)
+    for (u, _), r in best.items():
+        per_user[u] += 1
+    for (u, _), r in best.items():
+        if per_user[u] >= num_atleast:
+            keep[r] = 1
+    return keep, per_user[:n_users]

@@ -219,3 +219,16 @@ def test_device_clean_matches_host_clean():
         for (u, a), (_, b) in zip(got, want):
             assert a == b, (atleast, u)
     assert len(BaselinerClean(10 ** 6, 1, 2012, 2013, "S:").device_pipeline(LocalRDD(lines)).collect()) == 0
+    # the kernel's keep mask and per-user item counts against the array-level restatement, bit for bit
+    from xmap_b200 import clean as CL
+    rng = np.random.default_rng(3)
+    n, nu, ni = 200000, 5000, 300
+    user, item = rng.integers(0, nu, n).astype(np.int32), rng.integers(0, ni, n).astype(np.int32)
+    ts = rng.integers(1.30e9, 1.40e9, n).astype(np.float64)
+    ts[rng.integers(0, n, 20000)] = ts[rng.integers(0, n, 20000)]                    # exact ties across records
+    t_lo, t_hi = CL.period_bounds(2012, 2013)
+    for atleast in (1, 20, 38):
+        keep, per_user = CL.clean_encoded(user, item, ts, nu, t_lo, t_hi, atleast)
+        k0, p0 = PT.clean_encoded_numpy(user, item, ts, nu, t_lo, t_hi, atleast)
+        assert np.array_equal(keep.cpu().numpy(), k0) and np.array_equal(per_user.cpu().numpy(), p0), atleast
+        assert 0 < int(k0.sum()) < n

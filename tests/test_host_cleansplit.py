@@ -88,3 +88,29 @@ def test_encoder_replicates_reference_string_tests():
         encode_records([("u", [("bkS:", 3.7000001, t)])])
     pc, dc, ct, hs, ht = item_codes(["xxT:S:"])       # a label inside the raw id still counts (substring test)
     assert ct[0] == 3 or ct[0] == 1
+
+
+def test_clean_restatement_matches_host_class(monkeypatch):
+    """The array-level restatement of the clean stage's record rules (tests/parity.clean_encoded_numpy -- what the device
+    kernel is checked against) drives BaselinerClean.device_pipeline to exactly the records of the host class, which
+    test_clean_and_split_match_reference pins to the unmodified reference."""
+    import numpy as np
+    import torch
+    from xmap_b200 import synth, clean as CL
+    from xmap_b200.core import BaselinerClean
+    from xmap_b200.rdd import LocalRDD
+    monkeypatch.setattr(CL, "clean_encoded", lambda u, i, t, nu, lo, hi, k, device="cpu":
+                        tuple(torch.as_tensor(x) for x in PT.clean_encoded_numpy(u, i, t, nu, lo, hi, k)))
+    sr = synth.make_ratings(300, 50, 6000, overlap=0.3, seed=5)
+    lines = synth.to_text_lines(sr, 1)
+    bump = lambda l, dt: l.rsplit("\t", 1)[0] + "\t" + str(int(l.rsplit("\t", 1)[1]) + dt)
+    lines = lines + [bump(l, k * 40000000) for k, l in enumerate(lines[:150])] + [bump(l, -3600) for l in lines[150:250]] + \
+        ["\t".join(l.split("\t")[:2] + ["1", l.split("\t")[3]]) for l in lines[250:350]]
+    rng = np.random.default_rng(1)
+    lines = [lines[k] for k in rng.permutation(len(lines))]
+    assert CL.period_bounds(2012, 2013)[0] < 1.34e9 < CL.period_bounds(2012, 2013)[1]
+    for atleast in (1, 4, 9):
+        tool = BaselinerClean(atleast, 10 ** 9, 2012, 2013, "T:")
+        want = tool.clean_data(tool.filter_data(tool.parse_data(LocalRDD(lines)))).collect()
+        got = tool.device_pipeline(LocalRDD(lines)).collect()
+        assert len(want) > 0 and got == want, atleast
