@@ -349,6 +349,18 @@ int xmap_recsim_predict(const int64_t *prof_ptr, const int32_t *prof_item, const
                         const int32_t *nb_len, int32_t k, const int32_t *t_user, const int32_t *t_item, int64_t n_test,
                         double alpha, double *pred_nodecay, double *pred_decay, int32_t *error_flag, void *stream);
 
+/* (5c) PRIVATE neighbour selection + noise perturbation (RecommenderPrivacy.private_neighbor_selection +
+ * noise_perturbation, recommenderPrivacy.py:35-139, 152-171) as the reference behaves under Python 3 (one neighbour per
+ * item: np.count_nonzero(map(...)), :81, counts the map object): drawn from exp(eps * max(sim, sim - w) / (2 k RS_j))
+ * over the item's neighbours in |sim|-descending order; its similarity + Laplace(|RS| / eps).
+ *   row_ptr [n_items + 1], nbr / sim / ls: per item its neighbours in |sim|-descending STABLE order (the caller sorts)
+ *   eps = privacy_epsilon / 2 (recommenderPrivacy.py:18); u_pick / u_noise [n_items]: injected uniforms or NULL ->
+ *   Philox4x32-10(seed, item, 0 / 1); scratch: one double per neighbour; out_len[i] = 0 for an item without neighbours */
+int xmap_recsim_private_neighbor(const int64_t *row_ptr, const int32_t *nbr, const double *sim, const double *ls,
+                                 int32_t n_items, int32_t mapping_range, double eps, double rpo,
+                                 const double *u_pick, const double *u_noise, uint64_t seed, double *scratch,
+                                 int32_t *out_nbr, double *out_sim, int32_t *out_len, void *stream);
+
 /* ---------------------------------------------------------------------------
  * (6) Clean stage on encoded records.
  * Replaces the data-parallel part of BaselinerClean: the period test of parse_data (baselinerClean.py:47-52, given as

@@ -214,3 +214,46 @@ def run_recommender_predict(alter_records, test_records, mapping_range=10, alpha
         preds = predicted.collect()
         mae = pred_tool.calculate_mae(sc.parallelize(preds))
     return neigh, preds, mae
+
+
+def run_recommender_private(sim_records, mapping_range=10, epsilon=0.6, rpo=0.1, np_seed=7):
+    """recommender_privacy_pipeline(policy_tool, alterEgo_sim, True) (assist.py:178-185) by the unmodified reference:
+    private_neighbor_selection (recommenderPrivacy.py:70-139) + noise_perturbation (:152-171).  Under Python 3
+    `np.count_nonzero(map(...))` (:81) counts the map OBJECT, so exactly one neighbour is drawn per item.
+
+    The reference draws from the global np.random; every draw is logged here so that it can be replayed: the uniform
+    behind the weighted pick (`np.random.rand(1)`, :118) and the uniform behind the Laplace noise (legacy
+    `RandomState.laplace` consumes one double: the state is rewound and the double read).
+
+    sim_records: ((iid1, iid2), [sim, local sensitivity]) sorted by (iid1, iid2).
+    Returns [(iid, neighbour id, noisy sim, u_pick, u_noise)] in the reference's item order."""
+    R = load_reference()
+    sc, assist = R["sc"], R["assist"]
+    tool = R["RecommenderPrivacy"](mapping_range, epsilon, rpo)
+    log = {"pick": [], "noise": []}
+    orig_rand, orig_lap = np.random.rand, np.random.laplace
+
+    def rand(*a):
+        v = orig_rand(*a)
+        log["pick"].extend(np.atleast_1d(v).tolist())
+        return v
+
+    def laplace(loc, scale):
+        st = np.random.get_state()
+        v = orig_lap(loc, scale)
+        after = np.random.get_state()
+        np.random.set_state(st)
+        log["noise"].append(float(np.random.random_sample()))
+        np.random.set_state(after)
+        return v
+    np.random.seed(np_seed)
+    np.random.rand, np.random.laplace = rand, laplace
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res = assist.recommender_privacy_pipeline(tool, sc.parallelize(list(sim_records)), True).collect()
+            res = [(iid, list(lst)) for iid, lst in res]
+    finally:
+        np.random.rand, np.random.laplace = orig_rand, orig_lap
+    assert all(len(lst) == 1 for _, lst in res) and len(log["pick"]) == len(res) == len(log["noise"])
+    return [(iid, lst[0][0], float(lst[0][1]), log["pick"][q], log["noise"][q]) for q, (iid, lst) in enumerate(res)]

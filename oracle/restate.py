@@ -513,3 +513,52 @@ def recommender_predict(p_user, p_item, p_rating, p_ts, nb_ptr, nb_idx, nb_sim, 
     mae0 = float(np.abs(t_rating[ok] - out0[ok]).sum() / ok.sum()) if ok.any() else float("nan")
     mae1 = float(np.abs(t_rating[ok] - out1[ok]).sum() / ok.sum()) if ok.any() else float("nan")
     return out0, out1, mae0, mae1
+
+
+def laplace_from_uniform(u, scale):
+    """numpy's legacy RandomState.laplace(0, scale) as a function of the one double it consumes."""
+    u = np.asarray(u, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(u >= 0.5, 0.0 - scale * np.log(2.0 - u - u), 0.0 + scale * np.log(u + u))
+
+
+def recommender_private_neighbors(pairs, n_items, mapping_range, epsilon, rpo, u_pick, u_noise):
+    """The private branch of the neighbour selection AS IT BEHAVES UNDER PYTHON 3 (recommenderPrivacy.py:35-139, 152-171):
+    per item with at least one pair, ONE neighbour is drawn (`np.count_nonzero(map(...))`, :81, counts the map object, so
+    num_selection is 1 for any mapping_range) from the exponential-mechanism weights over ALL its neighbours in
+    |sim|-descending order (stable: ties keep the (i, j) order), and Laplace noise of scale |local sensitivity| / eps is
+    added to its similarity.  eps = privacy_epsilon / 2 (:18).  u_pick / u_noise: one uniform per such item, in item order.
+
+    pairs: output of recommender_cosine_item (sorted by (i, j)).  Returns (items, chosen neighbour, noisy sim)."""
+    i, j, sim, ls = pairs["i"], pairs["j"], pairs["sim"], pairs["ls"]
+    eps, k = epsilon / 2.0, int(mapping_range)
+    ptr = np.searchsorted(i, np.arange(n_items + 1))
+    items, chosen, out = [], [], []
+    q = 0
+    for it in range(n_items):
+        a, b = ptr[it], ptr[it + 1]
+        if b == a:
+            continue
+        o = a + np.argsort(-np.abs(sim[a:b]), kind="stable")           # :123
+        s_, r_, n = sim[o], ls[o], b - a
+        max_rs = r_[np.argsort(-np.abs(r_), kind="stable")[0]]         # :103-106
+        k_sim = s_[k - 1] if n >= k else s_[-1]                        # :43-46
+        if n > k:                                                      # :54-66
+            with np.errstate(divide="ignore", invalid="ignore"):
+                w = min(k_sim, (2 * k * max_rs / eps) * np.log(k * (n - k) / rpo))
+        else:
+            w = k_sim
+        msim = np.maximum(s_, s_ - w)                                  # :71-73
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            prob = np.exp(eps * msim / (2 * k * r_))                   # :88-93
+            tot = 0.0
+            for v in prob:                                             # Python sum(): sequential
+                tot = tot + v
+            p = prob / tot                                             # :97-99
+        t = np.cumsum(p)                                               # :115
+        idx = int(np.searchsorted(t, u_pick[q] * np.sum(p)))           # :116-118
+        idx = min(idx, n - 1)
+        items.append(it); chosen.append(j[o[idx]])
+        out.append(s_[idx] + laplace_from_uniform(u_noise[q], abs(r_[idx]) / eps))      # :159-166
+        q += 1
+    return np.array(items, dtype=np.int64), np.array(chosen, dtype=np.int64), np.array(out, dtype=np.float64)

@@ -232,3 +232,34 @@ def test_device_clean_matches_host_clean():
         k0, p0 = PT.clean_encoded_numpy(user, item, ts, nu, t_lo, t_hi, atleast)
         assert np.array_equal(keep.cpu().numpy(), k0) and np.array_equal(per_user.cpu().numpy(), p0), atleast
         assert 0 < int(k0.sum()) < n
+
+
+def test_private_recommender_pipeline_matches_reference():
+    """recommender_privacy_pipeline(..., is_private=True) with the reference's draws injected: the rows the unmodified
+    reference produced (one noisy neighbour per item), then the prediction stage runs on them."""
+    from xmap_b200.rdd import LocalRDD, Broadcast
+    from xmap_b200.core import (RecommenderSim, RecommenderPrivacy, RecommenderPrediction,
+                                recommender_calculate_sim_pipeline, recommender_privacy_pipeline,
+                                recommender_prediction_pipeline)
+    name = "adj_low_overlap"
+    g0, g, gp = PT.load_golden(name), PT.load_golden(name + "_recpriv"), PT.load_golden(name + "_recpred")
+    iids, uids = [str(s) for s in g0["iids"]], [str(s) for s in g0["uids"]]
+    profile = LocalRDD([(uids[u], iids[i], float(r), datetime.utcfromtimestamp(int(t)))
+                        for u, i, r, t in zip(gp["ae_user"], gp["ae_item"], gp["ae_rating"], gp["ae_ts"])])
+    sim_tool = RecommenderSim("cosine_item", int(g["num_atleast"]))
+    out = recommender_calculate_sim_pipeline(None, sim_tool, profile)
+    tool = RecommenderPrivacy(int(g["mapping_range"]), float(g["epsilon"]), float(g["rpo"]), uniforms=(g["u_pick"], g["u_noise"]))
+    neigh = recommender_privacy_pipeline(tool, out[6], True).collectAsMap()
+    assert len(neigh) == len(g["item"])
+    for it, ch, ns in zip(g["item"], g["chosen"], g["noisy_sim"]):
+        (nid, val), = neigh[iids[it]]
+        assert nid == iids[ch] and abs(val - ns) <= 1e-9 * abs(ns) + 1e-12
+    test, cur = [], None
+    for u, i, r in zip(gp["test_user"], gp["test_item"], gp["test_rating"]):
+        if cur is None or cur[0] != uids[u]:
+            cur = (uids[u], []); test.append(cur)
+        cur[1].append((iids[i], float(r), datetime(2013, 1, 1)))
+    mae = recommender_prediction_pipeline(RecommenderPrediction(float(gp["alpha"]), "cosine_item"), sim_tool, LocalRDD(test),
+                                          Broadcast(neigh), out[2], out[3], out[4], out[5])
+    m0, m1 = (float(x) for x in mae.split(";"))
+    assert 0.0 < m0 < 5.0 and 0.0 < m1 < 5.0

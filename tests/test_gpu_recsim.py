@@ -92,3 +92,55 @@ def test_neighbors_and_prediction_match_reference_golden(name):
     # a bounded prediction is int(x + 0.5): it can differ from the reference only if x + 0.5 is an integer to ~1e-12
     assert int((p0 != g["pred_nodecay"]).sum()) <= (1 if near else 0) and int((p1 != g["pred_decay"]).sum()) <= (1 if near else 0)
     assert abs(m0 - float(g["mae_nodecay"])) <= 1e-2 * near + 1e-12 and abs(m1 - float(g["mae_decay"])) <= 1e-2 * near + 1e-12
+
+
+@pytest.mark.parametrize("name", ["adj_low_overlap", "cos_half_ratings"])
+def test_private_neighbors_match_reference_golden(name):
+    """The PRIVATE branch of SURVEY.md 8(f) #2 through the C ABI against the UNMODIFIED reference
+    (tests/golden/*_recpriv.npz: private_neighbor_selection + noise_perturbation with the reference's np.random draws
+    logged): with the same uniforms injected every item draws the same neighbour; the noisy similarity agrees to 1e-9
+    (the similarities and sensitivities it is built from come from the device kernels, device exp / log are not glibc's)."""
+    from xmap_b200 import recsim
+    g0, g = PT.load_golden(name), PT.load_golden(name + "_recpriv")
+    nI = len(g0["iids"])
+    R = recsim.cosine_item(g["ae_user"], g["ae_item"], g["ae_rating"], nI, int(g["num_atleast"]))
+    nb = recsim.private_neighbors(R, nI, int(g["mapping_range"]), float(g["epsilon"]), float(g["rpo"]), g["u_pick"], g["u_noise"])
+    ln, idx, sim = nb.len.cpu().numpy(), nb.idx.cpu().numpy()[:, 0], nb.sim.cpu().numpy()[:, 0]
+    has = np.flatnonzero(ln)
+    assert np.array_equal(has, g["item"]) and (ln[has] == 1).all()
+    assert np.array_equal(idx[has], g["chosen"])
+    np.testing.assert_allclose(sim[has], g["noisy_sim"], rtol=1e-9, atol=1e-12)
+    # Philox draws: reproducible for a seed, different for another one
+    a = recsim.private_neighbors(R, nI, 10, 0.6, 0.1, seed=11)
+    b = recsim.private_neighbors(R, nI, 10, 0.6, 0.1, seed=11)
+    c = recsim.private_neighbors(R, nI, 10, 0.6, 0.1, seed=12)
+    assert bool((a.idx == b.idx).all()) and bool((a.sim == b.sim).all()) and not bool((a.idx == c.idx).all())
+
+
+def test_private_neighbors_vs_restatement_long_lists():
+    """Long neighbour lists (up to 3 000: numpy's pairwise np.sum recurses above 128 elements, count > k exercises the w
+    term), negative and tied similarities, tiny sensitivities: the kernel against oracle/restate.py with random uniforms."""
+    import torch
+    from oracle import restate as RS
+    from xmap_b200 import recsim
+    rng = np.random.default_rng(8)
+    nI = 400
+    lens = rng.integers(0, 60, nI); lens[:12] = [1, 2, 7, 8, 9, 10, 11, 128, 129, 1000, 2047, 3000]
+    i = np.repeat(np.arange(nI), lens)
+    j = np.concatenate([np.sort(rng.choice(4000, n, replace=False)) for n in lens]).astype(np.int64)
+    sim = np.round(rng.normal(0, 0.2, len(i)), 3)                     # rounded: exact ties in |sim|
+    ls = np.abs(rng.normal(0, 0.05, len(i))) + 1e-3
+    P = dict(i=i.astype(np.int64), j=j, sim=sim, ls=ls)
+    n_have = int((lens > 0).sum())
+    up, un = rng.random(n_have), rng.random(n_have)
+    it0, ch0, out0 = RS.recommender_private_neighbors(P, nI, 10, 0.6, 0.1, up, un)
+    dev = torch.device("cuda")
+    R = recsim.RecSim(torch.as_tensor(i, dtype=torch.int32, device=dev), torch.as_tensor(j, dtype=torch.int32, device=dev),
+                      torch.ones(len(i), dtype=torch.int64, device=dev), torch.as_tensor(sim, device=dev),
+                      torch.as_tensor(ls, device=dev), torch.zeros((nI, 3), dtype=torch.float64, device=dev), len(i))
+    nb = recsim.private_neighbors(R, nI, 10, 0.6, 0.1, up, un)
+    ln, idx, out = nb.len.cpu().numpy(), nb.idx.cpu().numpy()[:, 0], nb.sim.cpu().numpy()[:, 0]
+    has = np.flatnonzero(ln)
+    assert np.array_equal(has, it0)
+    assert int((idx[has] != ch0).sum()) == 0
+    np.testing.assert_allclose(out[has], out0, rtol=1e-12, atol=1e-15)

@@ -144,3 +144,20 @@ def test_restatement_neighbors_and_prediction_vs_reference(name):
                                             g["test_user"], g["test_item"], g["test_rating"], float(g["alpha"]))
     assert np.array_equal(p0, g["pred_nodecay"]) and np.array_equal(p1, g["pred_decay"])
     assert abs(m0 - float(g["mae_nodecay"])) < 1e-12 and abs(m1 - float(g["mae_decay"])) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["adj_low_overlap", "cos_half_ratings"])
+def test_restatement_private_neighbors_vs_reference(name):
+    """The PRIVATE branch of SURVEY.md 8(f) #2: private_neighbor_selection + noise_perturbation run by the unmodified
+    reference with its np.random draws logged (tests/golden/*_recpriv.npz, oracle/make_golden_recpriv.py); the restatement
+    fed the same uniforms picks the same neighbour for every item and returns the same noisy similarity."""
+    g0, g = PT.load_golden(name), PT.load_golden(name + "_recpriv")
+    nI = len(g0["iids"])
+    P = RS.recommender_cosine_item(g["ae_user"], g["ae_item"], g["ae_rating"], nI, int(g["num_atleast"]))
+    it, ch, out = RS.recommender_private_neighbors(P, nI, int(g["mapping_range"]), float(g["epsilon"]), float(g["rpo"]),
+                                                   g["u_pick"], g["u_noise"])
+    assert len(it) > 100 and np.array_equal(it, g["item"]) and np.array_equal(ch, g["chosen"])
+    np.testing.assert_allclose(out, g["noisy_sim"], rtol=1e-13, atol=0)
+    # the draw is not the arg-max: the mechanism really samples
+    nb = RS.recommender_neighbors(P, nI, 1)
+    assert 0 < int((ch != nb[1]).sum())

@@ -78,6 +78,8 @@ _SIGS = {
     "xmap_recsim_neighbors": (C.c_int, [_p, _p, _p, C.c_int32, C.c_int32, _p, _p, _p, _p]),
     "xmap_recsim_predict": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, C.c_int32, _p, _p, C.c_int64, C.c_double,
                                       _p, _p, _p, _p]),
+    "xmap_recsim_private_neighbor": (C.c_int, [_p, _p, _p, _p, C.c_int32, C.c_int32, C.c_double, C.c_double, _p, _p, C.c_uint64,
+                                               _p, _p, _p, _p, _p]),
     "xmap_clean_records": (C.c_int, [_p, _p, _p, _p, C.c_int64, C.c_int32, C.c_double, C.c_double, C.c_int32, _p, _p, _p]),
     "xmap_choose_mapping": (C.c_int, [_p, _p, _p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_double, C.c_int32, C.c_int32, _p, C.c_uint64, _p, _p]),

@@ -4,8 +4,8 @@
 Offered: item-based `cosine_item` similarity with local sensitivity, NON-private neighbour selection, item-based
 prediction with and without temporal decay, MAE.  `adjust_cosine_item` is accepted and, as in the reference (whose
 dispatch tests the substring "cosine_item" first, recommenderSim.py:188), runs the same cosine_item path.  Not offered
-(ValueError): the user-based variants (absent from the reference's own source tree) and the private neighbour selection
-(recommenderPrivacy.py:70-139: unseeded np.random draws).  The work happens in csrc/recsim.cu; these classes
+(ValueError): the user-based variants (absent from the reference's own source tree).  The private neighbour
+selection (recommenderPrivacy.py:70-139, 152-171) is offered as it behaves under Python 3, with injectable uniforms.  The work happens in csrc/recsim.cu; these classes
 encode the flat (uid, iid, rating, time) records once and keep the device state on the objects they return.
 """
 import calendar
@@ -79,17 +79,19 @@ class RecommenderSim(object):
 
 
 class RecommenderPrivacy(object):
-    def __init__(self, mapping_range, privacy_epsilon, rpo):
+    def __init__(self, mapping_range, privacy_epsilon, rpo, uniforms=None, seed=None):
+        """uniforms: optional (u_pick, u_noise), one injected uniform per item that has neighbours, in item order (the
+        reference's np.random draws replayed); seed: Philox seed of the private branch (None: fresh entropy per object)."""
         self.mapping_range = mapping_range
         self.privacy_epsilon = privacy_epsilon / 2          # recommenderPrivacy.py:18
         self.rpo = rpo
+        self.uniforms = uniforms
+        if seed is None:
+            import secrets
+            seed = secrets.randbits(64)
+        self.seed, self._calls = int(seed), 0
 
-    def nonprivate_neighbor_selection(self, rdd):
-        """(iid, [(neighbour, [sim, ls])*]) -- recommenderPrivacy.py:141-150; here the sensitivity is already dropped
-        (nonnoise_perturbation, :180-189), which is all the non-private pipeline keeps."""
-        state = rdd.handle
-        state.nb = RS.neighbors(state.sim, len(state.iids), int(self.mapping_range))
-
+    def _neighbour_rdd(self, state):
         def build():
             ln, idx, sim = state.nb.len.cpu().numpy(), state.nb.idx.cpu().numpy(), state.nb.sim.cpu().numpy()
             for it in np.flatnonzero(ln):
@@ -98,13 +100,30 @@ class RecommenderPrivacy(object):
         out.collectAsMap = lambda: _handle_dict(out.collect(), state)
         return out
 
+    def nonprivate_neighbor_selection(self, rdd):
+        """(iid, [(neighbour, [sim, ls])*]) -- recommenderPrivacy.py:141-150; here the sensitivity is already dropped
+        (nonnoise_perturbation, :180-189), which is all the non-private pipeline keeps."""
+        state = rdd.handle
+        state.nb = RS.neighbors(state.sim, len(state.iids), int(self.mapping_range))
+        return self._neighbour_rdd(state)
+
     def nonnoise_perturbation(self, rdd):
         return rdd
 
     def private_neighbor_selection(self, rdd):
-        raise ValueError("the private neighbour selection (recommenderPrivacy.py:70-139) is not offered")
+        """recommenderPrivacy.py:70-139 as it behaves under Python 3 -- one neighbour per item, drawn by the exponential
+        mechanism over all its neighbours (`np.count_nonzero(map(...))`, :81, counts the map object) -- fused with
+        noise_perturbation (:152-171): the rows already carry sim + Laplace(|local sensitivity| / eps)."""
+        state = rdd.handle
+        up, un = self.uniforms if self.uniforms is not None else (None, None)
+        seed = (self.seed + 0x9E3779B97F4A7C15 * self._calls) & (2 ** 64 - 1)
+        self._calls += 1
+        state.nb = RS.private_neighbors(state.sim, len(state.iids), int(self.mapping_range), 2 * self.privacy_epsilon,
+                                        self.rpo, up, un, seed)
+        return self._neighbour_rdd(state)
 
-    noise_perturbation = private_neighbor_selection
+    def noise_perturbation(self, rdd):
+        return rdd
 
 
 def _handle_dict(pairs, state):

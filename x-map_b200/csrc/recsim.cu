@@ -218,6 +218,137 @@ __global__ void __launch_bounds__(128) recsim_predict_kernel(const int64_t *__re
     pred0[q] = rs_bound_rating(p0); pred1[q] = rs_bound_rating(p1);
 }
 
+
+// ---- private neighbour selection + noise perturbation (recommenderPrivacy.py:35-139, 152-171) -----------------------
+// As the reference behaves under Python 3: np.count_nonzero(map(...)) (:81) counts the map object, so ONE neighbour is
+// drawn per item, from the exponential-mechanism weights over all its neighbours in |sim|-descending order, and Laplace
+// noise of scale |local sensitivity| / eps is added to its similarity.  One thread per item: every sum is formed in the
+// reference's order (Python's sum(): sequential; np.cumsum: sequential; np.sum: numpy's pairwise scheme), so an injected
+// uniform picks the same neighbour.
+
+// Philox4x32-10 uniform in [0, 1) with 53 random bits (the generator of generate.cu; counter = (lo, hi), key = seed)
+__device__ __forceinline__ double rs_philox_uniform(uint64_t seed, uint32_t c0, uint32_t c1) {
+    uint32_t c[4] = {c0, c1, 0u, 0u};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const unsigned long long bits = (((unsigned long long)c[0] << 32) | c[1]) >> 11;
+    return (double)bits * (1.0 / 9007199254740992.0);
+}
+
+// numpy's pairwise summation of a contiguous double array (the algorithm behind np.sum): blocks of <= 128 elements with
+// 8 running sums, longer arrays halved (the left half a multiple of 8) recursively
+__device__ double np_block_sum(const double *a, long long n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (long long i = 0; i < n; ++i) r = __dadd_rn(r, a[i]);
+        return r;
+    }
+    double r[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) r[q] = a[q];
+    long long i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r[q] = __dadd_rn(r[q], a[i + q]);
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+    return res;
+}
+
+__device__ double np_pairwise_sum(const double *a, long long n) {
+    // explicit stack instead of recursion: (offset, length) of the pieces still to be summed, left to right;
+    // results are combined in the order the recursion would: res(left) + res(right)
+    struct Frame { long long off, len; int state; double left; };
+    Frame st[48];
+    int sp = 0;
+    st[0].off = 0; st[0].len = n; st[0].state = 0; st[0].left = 0.0;
+    double ret = 0.0;
+    for (;;) {
+        Frame &f = st[sp];
+        if (f.len <= 128) {
+            ret = np_block_sum(a + f.off, f.len);
+            if (sp == 0) return ret;
+            --sp;
+            continue;
+        }
+        long long n2 = f.len / 2;
+        n2 -= n2 % 8;
+        if (f.state == 0) {                                // descend into the left half
+            f.state = 1;
+            st[sp + 1].off = f.off; st[sp + 1].len = n2; st[sp + 1].state = 0;
+            ++sp;
+        } else if (f.state == 1) {                         // left done: keep it, descend into the right half
+            f.left = ret; f.state = 2;
+            st[sp + 1].off = f.off + n2; st[sp + 1].len = f.len - n2; st[sp + 1].state = 0;
+            ++sp;
+        } else {                                           // both done
+            ret = __dadd_rn(f.left, ret);
+            if (sp == 0) return ret;
+            --sp;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) recsim_private_kernel(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ nbr,
+                                                             const double *__restrict__ sim, const double *__restrict__ ls,
+                                                             int n_items, int k, double eps, double rpo,
+                                                             const double *__restrict__ u_pick, const double *__restrict__ u_noise,
+                                                             uint64_t seed, double *__restrict__ scratch,
+                                                             int32_t *__restrict__ out_nbr, double *__restrict__ out_sim,
+                                                             int32_t *__restrict__ out_len) {
+    const int it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items) return;
+    const long long a = row_ptr[it], b = row_ptr[it + 1], n = b - a;
+    if (n <= 0) { out_len[it] = 0; return; }
+    // the local sensitivity of largest magnitude, the first one among equals (:103-106)
+    double max_rs = ls[a], m = fabs(ls[a]);
+    for (long long q = a + 1; q < b; ++q) {
+        const double v = fabs(ls[q]);
+        if (v > m || (m != m && v == v)) { m = v; max_rs = ls[q]; }
+    }
+    const double k_sim = n >= k ? sim[a + k - 1] : sim[b - 1];                       // :43-46
+    double w = k_sim;                                                               // :54-66
+    if (n > k) {
+        const double x = __dmul_rn(__ddiv_rn(__dmul_rn((double)(2 * k), max_rs), eps),
+                                   log(__ddiv_rn((double)((long long)k * (n - k)), rpo)));
+        if (x < k_sim) w = x;                                                       // Python's min(k_sim, x)
+    }
+    const double two_k = (double)(2 * k);
+    double tot = 0.0;
+    for (long long q = a; q < b; ++q) {
+        const double s_ = sim[q], sw = __dsub_rn(s_, w);
+        const double ms = sw > s_ ? sw : s_;                                        // :71-73 max(sim, sim - w)
+        const double pr = exp(__ddiv_rn(__dmul_rn(eps, ms), __dmul_rn(two_k, ls[q])));   // :88-93
+        scratch[q] = pr;
+        tot = __dadd_rn(tot, pr);                                                   // Python sum(): sequential
+    }
+    for (long long q = a; q < b; ++q) scratch[q] = __ddiv_rn(scratch[q], tot);      // :97-99
+    const double up = u_pick ? u_pick[it] : rs_philox_uniform(seed, (uint32_t)it, 0u);
+    const double target = __dmul_rn(up, np_pairwise_sum(scratch + a, n));           // rand * np.sum(weights), :116-118
+    long long idx = n - 1;
+    double cum = 0.0;
+    for (long long q = 0; q < n; ++q) {                                             // np.searchsorted(np.cumsum(w), target), side='left'
+        cum = __dadd_rn(cum, scratch[a + q]);
+        if (cum >= target) { idx = q; break; }
+    }
+    const double un = u_noise ? u_noise[it] : rs_philox_uniform(seed, (uint32_t)it, 1u);
+    const double scale = __ddiv_rn(fabs(ls[a + idx]), eps);                         // :159-166, legacy RandomState.laplace
+    const double noise = un >= 0.5 ? __dsub_rn(0.0, __dmul_rn(scale, log(__dsub_rn(__dsub_rn(2.0, un), un))))
+                                   : __dadd_rn(0.0, __dmul_rn(scale, log(__dadd_rn(un, un))));
+    out_nbr[it] = nbr[a + idx];
+    out_sim[it] = __dadd_rn(sim[a + idx], noise);
+    out_len[it] = 1;
+}
+
 }  // namespace xmap
 
 using namespace xmap;
@@ -269,6 +400,19 @@ extern "C" int xmap_recsim_predict(const int64_t *prof_ptr, const int32_t *prof_
     recsim_predict_kernel<<<(unsigned)((n_test + 127) / 128), 128, 0, (cudaStream_t)stream_>>>(
         prof_ptr, prof_item, prof_rating, prof_ts, info, nb_idx, nb_sim, nb_len, k, t_user, t_item, n_test, alpha,
         pred_nodecay, pred_decay, error_flag);
+    XMAP_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int xmap_recsim_private_neighbor(const int64_t *row_ptr, const int32_t *nbr, const double *sim, const double *ls,
+                                            int32_t n_items, int32_t mapping_range, double eps, double rpo,
+                                            const double *u_pick, const double *u_noise, uint64_t seed, double *scratch,
+                                            int32_t *out_nbr, double *out_sim, int32_t *out_len, void *stream_) {
+    if (n_items <= 0) return 0;
+    if (mapping_range < 1) return fail_msg("xmap_recsim_private_neighbor: mapping_range must be >= 1");
+    if (!(eps > 0.0) || !(rpo > 0.0)) return fail_msg("xmap_recsim_private_neighbor: eps and rpo must be positive");
+    recsim_private_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, (cudaStream_t)stream_>>>(
+        row_ptr, nbr, sim, ls, n_items, mapping_range, eps, rpo, u_pick, u_noise, seed, scratch, out_nbr, out_sim, out_len);
     XMAP_LAUNCH_CHECK();
     return 0;
 }

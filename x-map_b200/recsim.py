@@ -97,6 +97,43 @@ def neighbors(rs, n_items, k=10):
     return Neighbors(nb_idx, nb_sim, nb_len)
 
 
+def private_neighbors(rs, n_items, mapping_range=10, privacy_epsilon=0.6, rpo=0.1, u_pick=None, u_noise=None, seed=0):
+    """RecommenderPrivacy.private_neighbor_selection + noise_perturbation (recommenderPrivacy.py:35-139, 152-171) as the
+    reference behaves under Python 3: ONE neighbour per item, drawn by the exponential mechanism over all its neighbours,
+    its similarity plus Laplace noise.  u_pick / u_noise: one injected uniform per item THAT HAS NEIGHBOURS, in item
+    order (the reference's np.random draws replayed), or None -> Philox4x32-10(seed, item).  Returns Neighbors with k = 1."""
+    L = N.lib()
+    dev = rs.i.device
+    cnt = torch.bincount(rs.i.long(), minlength=n_items)
+    row_ptr = torch.zeros(n_items + 1, dtype=torch.int64, device=dev)
+    row_ptr[1:] = torch.cumsum(cnt, 0)
+    # |sim| descending, stable (ties keep the (i, j) order), inside every item (recommenderPrivacy.py:123)
+    o1 = torch.sort(rs.sim.abs(), descending=True, stable=True).indices
+    o = o1[torch.sort(rs.i.long()[o1], stable=True).indices]
+    nbr, sim, ls = rs.j[o].contiguous(), rs.sim[o].contiguous(), rs.ls[o].contiguous()
+
+    def per_item(u):
+        if u is None:
+            return None
+        u = torch.as_tensor(u, dtype=torch.float64).to(dev)
+        have = torch.nonzero(cnt > 0).flatten()
+        if u.numel() != have.numel():
+            raise ValueError("need one uniform per item that has neighbours (%d), got %d" % (have.numel(), u.numel()))
+        full = torch.zeros(n_items, dtype=torch.float64, device=dev)
+        full[have] = u
+        return full
+    up, un = per_item(u_pick), per_item(u_noise)
+    scratch = torch.empty(max(int(sim.numel()), 1), dtype=torch.float64, device=dev)
+    nb_idx = torch.full((n_items, 1), -1, dtype=torch.int32, device=dev)
+    nb_sim = torch.zeros((n_items, 1), dtype=torch.float64, device=dev)
+    nb_len = torch.zeros(n_items, dtype=torch.int32, device=dev)
+    N.check(L.xmap_recsim_private_neighbor(N.ptr(row_ptr), N.ptr(nbr), N.ptr(sim), N.ptr(ls), n_items, int(mapping_range),
+                                           float(privacy_epsilon) / 2.0, float(rpo), N.ptr(up), N.ptr(un),
+                                           int(seed) & (2 ** 64 - 1), N.ptr(scratch), N.ptr(nb_idx), N.ptr(nb_sim),
+                                           N.ptr(nb_len), _st()), "xmap_recsim_private_neighbor")
+    return Neighbors(nb_idx, nb_sim, nb_len)
+
+
 def predict(user, item, rating, ts, n_users, rs, nb, test_user, test_item, test_rating=None, alpha=0.03):
     """RecommenderPrediction.item_based_recommendation + calculate_mae (recommenderPrediction.py:26-139) on the
     profile records (list order).  Returns (pred_nodecay, pred_decay, mae_nodecay, mae_decay); predictions are -1
